@@ -1,0 +1,240 @@
+/*
+ * lumen_b200.h — C ABI of the B200-native wavefront path-tracing core.
+ *
+ * This is the drop-in boundary for the reference's `LumenRenderer` / `WaveFront::WaveFrontRenderer`
+ * hot path (scene/mesh/material/light upload, camera, frame settings, TraceFrame, output read-back).
+ * Every entry point cites the reference interface it replaces. Paths are relative to
+ * /root/reference/Lumen_Engine/ :
+ *   LM/ = Lumen/src/Lumen/            PT/ = LumenPT/src/
+ *
+ * Conventions
+ *   - plain C, opaque renderer pointer, integer resource handles (>= 0), plain pointers + sizes;
+ *   - every call returns LB_OK (0) or a negative LB_ERR_* code; lb_last_error() gives the text;
+ *   - inputs are copied before the call returns (reference uploads are synchronous as well,
+ *     PT/Framework/MemoryBuffer.cpp:50-56), so callers may free host memory immediately;
+ *   - one renderer instance per GPU, not thread-safe across concurrent calls on the same instance;
+ *   - there is NO CPU fallback: lb_create fails with LB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * The same declarations, prefixed `lo_` instead of `lb_`, are exported by the CPU oracle
+ * (oracle/liblumen_oracle.so) — test infrastructure only, never linked by the product.
+ */
+#ifndef LUMEN_B200_H
+#define LUMEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef LB_API
+#define LB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct LbRendererOpaque* LbRenderer;
+typedef int32_t LbHandle;
+#define LB_NO_HANDLE (-1)
+
+enum {
+    LB_OK = 0,
+    LB_ERR_INVALID_ARGUMENT = -1,
+    LB_ERR_INVALID_HANDLE = -2,
+    LB_ERR_CUDA = -3,
+    LB_ERR_OUT_OF_MEMORY = -4,
+    LB_ERR_UNSUPPORTED = -5,
+    LB_ERR_STATE = -6
+};
+
+/* Lumen::EmissionMode, LM/ModelLoading/MeshInstance.h:14-19 */
+enum { LB_EMISSION_ENABLED = 0, LB_EMISSION_DISABLED = 1, LB_EMISSION_OVERRIDE = 2 };
+
+/* WaveFront::LightChannel, PT/Shaders/CppCommon/WaveFrontDataStructs/LightData.h:12-19 */
+enum { LB_CHANNEL_DIRECT = 0, LB_CHANNEL_INDIRECT = 1, LB_CHANNEL_SPECULAR = 2, LB_CHANNEL_VOLUMETRIC = 3, LB_NUM_CHANNELS = 4 };
+
+/* Volume shading model. COMPAT = the reference's fixed 5-step constant-density march
+ * (PT/CUDAKernels/VolumetricKernels/GPUVolumetricShadeDirect.cu:8-101); DELTA = delta tracking with a
+ * per-grid majorant over the (procedural / NanoVDB-style dense) density grid (north_star item 4). */
+enum { LB_VOLUME_COMPAT = 0, LB_VOLUME_DELTA = 1 };
+
+/* WaveFront::WaveFrontSettings, PT/Framework/WaveFrontRenderer.h:31-48 (+ ReSTIRSettings toggles,
+ * PT/Shaders/CppCommon/ReSTIRData.h:25-66). depth counts extend waves (= bounces + 1). */
+typedef struct LbSettings {
+    uint32_t width;            /* renderResolution.x */
+    uint32_t height;           /* renderResolution.y */
+    uint32_t depth;            /* WaveFrontSettings::depth */
+    uint32_t blend_output;     /* WaveFrontSettings::blendOutput (progressive accumulation) */
+    uint32_t restir;           /* 1: ReSTIR at depth 0 (reference behaviour); 0: NEE at depth 0 (SURVEY hazard 11) */
+    uint32_t restir_temporal;  /* ReSTIRSettings::enableTemporal */
+    uint32_t restir_spatial;   /* ReSTIRSettings::enableSpatial */
+    int32_t  device;           /* CUDA device ordinal (ignored by the oracle) */
+    uint32_t volume_mode;      /* LB_VOLUME_* */
+    uint32_t first_frame_count;/* value of the reference's static frameCount for the first frame minus 1 (0 = reference);
+                                  sample sharding sets 2*rank so that streams do not overlap */
+    uint32_t frame_count_stride;/* frameCount advance per frame; 0 means the reference's 2 (SURVEY hazard 10) */
+    uint32_t reserved[5];
+} LbSettings;
+
+/* LumenRenderer::MaterialData, LM/Renderer/LumenRenderer.h:64-112 (defaults :66-82).
+ * Texture handles may be LB_NO_HANDLE = the renderer's default 1x1 texture
+ * (white; normal map default (128,128,255), LM/Renderer/LumenRenderer.cpp:50-58). */
+typedef struct LbMaterialDesc {
+    float diffuse_color[4];
+    float emission[3];
+    float transmission_factor;
+    float clear_coat_factor;
+    float clear_coat_roughness_factor;
+    float index_of_refraction;
+    float specular_factor;
+    float specular_tint_factor;
+    float subsurface_factor;
+    float luminance;
+    float anisotropic;
+    float sheen_factor;
+    float sheen_tint_factor;
+    float metallic_factor;
+    float roughness_factor;
+    float tint_factor[3];
+    float transmittance[3];
+    LbHandle diffuse_texture;
+    LbHandle normal_texture;
+    LbHandle metallic_roughness_texture;
+    LbHandle emissive_texture;
+    LbHandle transmission_texture;
+    LbHandle clear_coat_texture;
+    LbHandle clear_coat_roughness_texture;
+    LbHandle tint_texture;
+} LbMaterialDesc;
+
+/* LumenRenderer::PrimitiveData, LM/Renderer/LumenRenderer.h:44-61. Attribute streams are given as base
+ * pointer + byte stride, which covers both the interleaved 48-byte `Vertex` (PT/Shaders/CppCommon/ModelStructs.h:21-28)
+ * and the non-interleaved VectorViews. uvs/normals/tangents may be NULL (zeros / +Z / +X,w=1 are used). */
+typedef struct LbPrimitiveDesc {
+    const void* positions;  uint32_t position_stride;   /* float3 */
+    const void* uvs;        uint32_t uv_stride;         /* float2 */
+    const void* normals;    uint32_t normal_stride;     /* float3 */
+    const void* tangents;   uint32_t tangent_stride;    /* float4, w = bitangent sign */
+    uint32_t vertex_count;
+    const void* indices;    uint32_t index_size;        /* 2 or 4 bytes, m_IndexSize */
+    uint32_t index_count;                               /* 3 * triangles */
+    LbHandle material;
+} LbPrimitiveDesc;
+
+/* MeshInstance::Emissiveness, LM/ModelLoading/MeshInstance.h:24-34 */
+typedef struct LbEmissiveness {
+    int32_t mode;               /* LB_EMISSION_* */
+    float override_radiance[3];
+    float scale;
+} LbEmissiveness;
+
+/* Procedural / dense float density grid standing in for nanovdb::FloatGrid
+ * (PT/Framework/PTVolume.cpp:47-108 loads .vdb/.vndb; file decode is out of scope).
+ * density[(z*ny + y)*nx + x], world bbox = bbox_min..bbox_max in the volume's object space. */
+typedef struct LbVolumeDesc {
+    const float* density;       /* may be NULL: homogeneous medium of value 1 */
+    uint32_t nx, ny, nz;
+    float bbox_min[3];
+    float bbox_max[3];
+} LbVolumeDesc;
+
+/* ---- lifetime: WaveFrontRenderer::Init, PT/Framework/WaveFrontRenderer.cpp:70-322 ---- */
+LB_API int lb_create(const LbSettings* settings, LbRenderer* out);
+LB_API int lb_destroy(LbRenderer r);
+LB_API const char* lb_last_error(void);
+LB_API const char* lb_version(void);
+
+/* ---- resources ---- */
+/* LumenRenderer::CreateTexture, LM/Renderer/LumenRenderer.h:161; PT/Framework/PTTexture.cpp:35-74
+ * (RGBA8, wrap addressing, bilinear, normalised coords, optional sRGB decode). */
+LB_API int lb_texture_create(LbRenderer r, const uint8_t* rgba8, uint32_t width, uint32_t height, int srgb, LbHandle* out);
+/* LumenRenderer::CreateMaterial, LM/Renderer/LumenRenderer.h:164; PT/Framework/WaveFrontRenderer.cpp:1260-1311 */
+LB_API int lb_material_create(LbRenderer r, const LbMaterialDesc* desc, LbHandle* out);
+/* ILumenMaterial setters, LM/Renderer/ILumenResources.h:18-87 (re-uploads on next frame, PT/Framework/PTMaterial.cpp:21-36) */
+LB_API int lb_material_update(LbRenderer r, LbHandle material, const LbMaterialDesc* desc);
+/* LumenRenderer::CreatePrimitive, LM/Renderer/LumenRenderer.h:157; PT/Framework/WaveFrontRenderer.cpp:1148-1252 */
+LB_API int lb_primitive_create(LbRenderer r, const LbPrimitiveDesc* desc, LbHandle* out);
+/* LumenRenderer::CreateMesh, LM/Renderer/LumenRenderer.h:159 */
+LB_API int lb_mesh_create(LbRenderer r, const LbHandle* primitives, uint32_t count, LbHandle* out);
+/* LumenRenderer::CreateVolume, LM/Renderer/LumenRenderer.h:168 (file path replaced by an in-memory grid) */
+LB_API int lb_volume_create(LbRenderer r, const LbVolumeDesc* desc, LbHandle* out);
+
+/* ---- scene: ILumenScene::AddMesh / AddVolume, LM/ModelLoading/ILumenScene.h:11-71; PT/Framework/PTScene.cpp:67-171 ---- */
+/* transform: row-major 4x4 world matrix (what PT/Framework/PTMeshInstance.cpp:143-147 uploads). */
+LB_API int lb_scene_add_mesh_instance(LbRenderer r, LbHandle mesh, const float* transform16,
+                                      const LbEmissiveness* emissiveness, LbHandle override_material, LbHandle* out);
+/* Transform::Set*, MeshInstance::SetEmissiveness / SetOverrideMaterial, PT/Framework/PTMeshInstance.cpp:36-40,110-115 */
+LB_API int lb_instance_set_transform(LbRenderer r, LbHandle instance, const float* transform16);
+LB_API int lb_instance_set_emissiveness(LbRenderer r, LbHandle instance, const LbEmissiveness* emissiveness);
+LB_API int lb_instance_set_override_material(LbRenderer r, LbHandle instance, LbHandle material);
+/* ILumenScene::AddVolume + VolumeInstance::m_Density, LM/ModelLoading/VolumeInstance.h:24 */
+LB_API int lb_scene_add_volume_instance(LbRenderer r, LbHandle volume, const float* transform16, float density, LbHandle* out);
+LB_API int lb_scene_clear(LbRenderer r);
+
+/* ---- camera: Camera::GetVectorData, LM/Renderer/Camera.cpp:79-93,122-140 ---- */
+/* position + rotation quaternion (w,x,y,z); fovY is the reference's hard-coded 90 degrees (Camera.h:63) unless overridden. */
+LB_API int lb_camera_set_pose(LbRenderer r, const float* position3, const float* rotation_wxyz);
+LB_API int lb_camera_set_fov_y(LbRenderer r, float degrees);
+
+/* ---- frame settings: LumenRenderer::Set/GetRenderResolution, SetBlendMode, LM/Renderer/LumenRenderer.h:178-196 ---- */
+LB_API int lb_set_render_resolution(LbRenderer r, uint32_t width, uint32_t height);
+LB_API int lb_get_render_resolution(LbRenderer r, uint32_t* width, uint32_t* height);
+LB_API int lb_set_depth(LbRenderer r, uint32_t depth);
+LB_API int lb_set_blend_mode(LbRenderer r, int blend);
+LB_API int lb_get_blend_mode(LbRenderer r, int* blend);
+/* Discards progressive accumulation and ReSTIR history (what a ResizeBuffers does, PT/Framework/WaveFrontRenderer.cpp:1424-1540). */
+LB_API int lb_reset_history(LbRenderer r);
+
+/* ---- the hot path: WaveFrontRenderer::TraceFrame, PT/Framework/WaveFrontRenderer.cpp:435-1089 ---- */
+/* Renders `frames` frames back to back, asynchronously on the renderer's stream; read-backs synchronise. */
+LB_API int lb_render_frames(LbRenderer r, uint32_t frames);
+LB_API int lb_synchronize(LbRenderer r);
+/* LumenRenderer::StartRendering (render thread, PT/Framework/WaveFrontRenderer.cpp:1109-1117) */
+LB_API int lb_start_rendering(LbRenderer r);
+LB_API int lb_stop_rendering(LbRenderer r);
+
+/* ---- output: GetOutputTexturePixels, PT/Framework/WaveFrontRenderer.cpp:1379-1394 (+ fp32 HDR, north_star) ---- */
+LB_API int lb_read_hdr(LbRenderer r, float* rgba32f, size_t capacity_bytes);      /* width*height*4 floats, merged/blended image */
+LB_API int lb_read_ldr(LbRenderer r, uint8_t* rgba8, size_t capacity_bytes);      /* clamp + sRGB OETF + 8 bit, GPUShadingKernels.cu:28-56 */
+LB_API int lb_read_channel(LbRenderer r, int channel, float* rgba32f, size_t capacity_bytes);
+LB_API int lb_read_motion_vectors(LbRenderer r, float* xy32f, size_t capacity_bytes); /* MotionVectors.cu:8-55 (fp16-rounded values) */
+
+/* FrameStats, LM/Renderer/LumenRenderer.h:29-34: per-stage device time (CUDA events) of the last frame, microseconds.
+ * names are returned as a single ';'-separated string valid until the next call. */
+LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint32_t capacity, uint32_t* count);
+/* counters of the last frame: [0]=extend rays, [1]=shadow rays, [2]=ReSTIR visibility rays, [3]=kernel launches,
+ * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes */
+LB_API int lb_frame_counters(LbRenderer r, uint64_t* values, uint32_t capacity, uint32_t* count);
+
+/* ---- multi-GPU / framework interop ---- */
+/* Device pointer of the fp32 RGBA accumulation buffer (sum over blended frames) and its frame count, for an
+ * external NCCL reduce; lb_resolve_accum divides by `total_frames` and refreshes HDR/LDR. */
+LB_API int lb_accum_buffer(LbRenderer r, void** device_ptr, size_t* bytes, uint32_t* frames);
+LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
+/* Run all work on an externally owned CUDA stream (e.g. torch's current stream); 0/NULL = the renderer's own. */
+LB_API int lb_set_stream(LbRenderer r, void* cuda_stream);
+
+/* ---- debug taps used by the parity tests ---- */
+/* Trace caller-supplied rays with the extend kernel (closest hit) or the any-hit kernel.
+ * rays: n x {ox,oy,oz,dx,dy,dz}; hits: n x {u32 instance, u32 primitive, f32 bary_u, f32 bary_v, f32 t} (t=-1: miss). */
+LB_API int lb_debug_trace_closest(LbRenderer r, const float* rays6, uint32_t n, float tmin, float tmax, void* hits20);
+LB_API int lb_debug_trace_any(LbRenderer r, const float* rays6, const float* tmax_per_ray, uint32_t n, float tmin, uint8_t* occluded);
+/* Sorted emissive triangle list + CDF after the last frame: lights n x 16 floats (p0,p1,p2,normal,radiance,area). */
+LB_API int lb_debug_read_lights(LbRenderer r, float* lights16, float* cdf, uint32_t capacity, uint32_t* count);
+/* Primary-hit records of the last frame, one per pixel, same layout as lb_debug_trace_closest. */
+LB_API int lb_debug_read_primary_hits(LbRenderer r, void* hits20, size_t capacity_bytes);
+/* Primary surface data of the last frame, per pixel 24 floats:
+ * position3,t, normal3,flags, tangent3,0, incoming3,0, transport3,0, color4 (SurfaceData.h:49-104). */
+LB_API int lb_debug_read_surface(LbRenderer r, float* surf24, size_t capacity_bytes);
+/* Current-frame reservoirs after ReSTIR::Run, per pixel 20 floats: weightSum, weight, sampleCount, pdf,
+ * position3, area, normal3, 0, radiance3, 0, contribution3, 0 (ReSTIRData.h:107-183). */
+LB_API int lb_debug_read_reservoirs(LbRenderer r, float* res20, size_t capacity_bytes);
+/* Stand-alone BSDF evaluation on the device for parity against the reference headers
+ * (disney.cuh:173-405). mat24: color4, transmittance3, ior(eta), tint3, luminance, metallic, subsurface, specular, roughness,
+ * spectint, anisotropic, sheen, sheentint, clearcoat, clearcoatgloss, transmission, pad (params are byte-quantised like MaterialStructs.h:84-260). */
+LB_API int lb_debug_eval_bsdf(LbRenderer r, const float* mat24, const float* n_t_wo_wi12, uint32_t n, float* bsdf_pdf4);
+LB_API int lb_debug_sample_bsdf(LbRenderer r, const float* mat24, const float* n_t_wo_r12, uint32_t n, float* bsdf_wi_pdf_spec8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMEN_B200_H */
