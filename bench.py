@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the wavefront path-tracing hot path (BASELINE.json metric, config C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--width 2560 --height 1440]
+
+A step = one frame (1 spp) of the C2 workload: the procedural Sponza-class atrium (~262 K triangles, 16 textures of
+1024^2, 32 override-emissive lamps = 1 024 light triangles), 2560x1440, depth 4 (= 3 bounces), ReSTIR direct lighting
+with temporal + spatial reuse, static camera (temporal reuse active after the warm-up frames).
+  value  : Mrays/s = (extend + shadow + ReSTIR-visibility rays of the timed frames, all ranks) / time, scene resident in HBM,
+           timed with CUDA events on the renderer's stream, barrier + synchronize on both sides, max over ranks.
+  e2e    : the same metric through the C ABI with host buffers: every step uploads the camera pose and reads the fp32 HDR
+           frame back into pinned host memory inside the timed region.
+  N > 1  : sample sharding — every rank renders its own K frames with a disjoint frameCount stream into its
+           fp32 accumulation buffer; ONE NCCL reduce of that buffer (inside the timed region) produces the image. scaling=weak.
+  --impl reference : the CPU implementation of the same path (the oracle port; the reference itself has no CPU renderer and
+           its OptiX trace cannot be built here) on all host threads, each step one frame of a bounded sample (320x180).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "Mrays/sec @1440p 1spp 3-bounce ReSTIR (ms/frame in ms_per_step)"
+SAMPLE_W, SAMPLE_H = 320, 180
+# algorithmic bytes per unit (DESIGN.md "roofline"): what a stage must move per ray / pixel, fp32 payloads
+ALG_BYTES = {"extend": 40.0, "shadow": 44.0}
+
+
+def workload_scene(args):
+    from lumenrenderer_b200 import scenes
+    return scenes.atrium(detail=args.detail, texture_size=args.texture_size)
+
+
+def settings(args, width, height, rank=0, world=1, blend=False):
+    import lumenrenderer_b200 as lr
+    return lr.Settings(width=width, height=height, depth=args.depth, restir=True, restir_temporal=True, restir_spatial=True,
+                       blend_output=blend, device=0, first_frame_count=2 * rank, frame_count_stride=2 * world)
+
+
+def rays_of(counters):
+    return counters["extend_rays"] + counters["shadow_rays"] + counters["visibility_rays"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DevPtr:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (for the NCCL reduce of the accumulation buffer)."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def cpu_run(args, steps, warmup, threads=None):
+    """The CPU port of the path (oracle) on a bounded sample of the workload: same scene, 320x180."""
+    import __graft_entry__ as ge
+    from lumenrenderer_b200 import api
+    ob = ge.oracle_bindings()
+    lib = ob.lib
+    lib.lo_num_threads.restype = ctypes.c_int
+    if threads:
+        lib.lo_set_num_threads(int(threads))
+    cores = int(lib.lo_num_threads())
+    scene = workload_scene(args)
+    r = api.Renderer(ob, settings(args, SAMPLE_W, SAMPLE_H))
+    r.load_scene(scene)
+    t_build = time.time(); r.read_lights(); t_build = time.time() - t_build       # commits the scene (BVH build, light list)
+    r.render_frames(max(warmup, 1))
+    rays, t0 = 0, time.time()
+    for _ in range(steps):
+        r.render_frames(1); rays += rays_of(r.frame_counters())
+    dt = time.time() - t0
+    r.close()
+    return {"mrays": rays / dt / 1e6, "ms_per_step": dt / steps * 1e3, "cores": cores, "rays_per_step": rays / steps, "scene_build_s": t_build,
+            "sample": f"same atrium scene, {SAMPLE_W}x{SAMPLE_H} (1/64 of the pixels), depth {args.depth}, ReSTIR, {steps} frames after {max(warmup, 1)} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_run(args, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, SAMPLE_W, SAMPLE_H, "cpu"),
+            "cpu_baseline": {"value": res["mrays"], "unit": "Mrays/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+            "e2e": {"value": res["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference has no CPU renderer and its ray tracing is closed-source OptiX (SURVEY 8c): this arm is the scalar C++ port of the same wavefront algorithm (oracle/), OpenMP over all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def config_of(args, w, h, where):
+    return {"workload": f"C2 procedural Sponza-class atrium (detail {args.detail}), {w}x{h}, 1 spp, depth {args.depth} (3 bounces), ReSTIR 32 candidates + temporal + 2x spatial, static camera",
+            "resolution": [w, h], "depth": args.depth, "restir": True, "textures": f"16 x {args.texture_size}^2 RGBA8",
+            "l2": "per-frame working set (~0.9 KB/pixel of SoA planes, 3.3 GB at 1440p) is far larger than the 126 MB L2; no explicit flush",
+            "parallelism": f"sample-sharded x{args.gpus}" if where == "gpu" else "OpenMP"}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import lumenrenderer_b200 as lr
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = args.width, args.height
+    st = settings(args, W, H, rank, world, blend=world > 1)
+    st.device = local
+    scene = workload_scene(args)
+    r = lr.Renderer(st)
+    r.load_scene(scene)
+    stream = torch.cuda.current_stream()
+    r.set_stream(stream.cuda_stream)
+    cam_pos, cam_rot = scene.camera["position"], scene.camera["rotation"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    accum = None
+    if world > 1:
+        ptr, nbytes, _ = r.accum_buffer()
+        accum = torch.as_tensor(DevPtr(ptr, nbytes // 4), device=torch.device("cuda", local))
+        warm = torch.zeros(1024, device="cuda"); dist.all_reduce(warm)          # NCCL communicator warm-up outside the timed region
+
+    r.render_frames(max(args.warmup, 3))            # >= 3 warm-up frames; also fills the temporal ReSTIR history
+    r.synchronize()
+    counters = r.frame_counters()
+    tris, lights, bvh_bytes, launches = counters["triangles"], counters["lights"], counters["bvh_bytes"], counters["kernel_launches"]
+
+    # ---- timed region 1: device-resident throughput
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    rays = 0
+    for _ in range(args.steps):
+        r.render_frames(1)
+    if world > 1:
+        dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)                         # the one collective of the path
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    rays_per_frame = rays_of(r.frame_counters())                                # static camera: every timed frame traces the same number of rays
+    rays = rays_per_frame * args.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if world > 1:
+        if rank == 0:
+            r.resolve_accum(args.steps * world + 0)     # accumulation started at set_blend... warm-up frames are part of the sum
+        t = torch.tensor([ms, float(rays)], device="cuda", dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, rays = float(tmax[0]), float(tsum[1])
+
+    # ---- timed region 2: end to end through the C ABI with host buffers (camera in, HDR frame out, every step)
+    host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    r.set_camera(cam_pos, cam_rot); r.render_frames(1); r.read_hdr_into(host.data_ptr(), host.numel() * 4)
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        r.set_camera(cam_pos, cam_rot)
+        r.render_frames(1)
+        r.read_hdr_into(host.data_ptr(), host.numel() * 4)
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    e2e_rays = rays_per_frame * args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
+        t = torch.tensor([float(e2e_rays)], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM); e2e_rays = float(t[0])
+    finite = bool(np.isfinite(host.numpy()).all())
+
+    # ---- per-stage device time (CUDA events on the renderer's stream, per frame) for the roofline lines
+    stage_ms, stage_frames = {}, max(3, min(args.steps, 10))
+    for _ in range(stage_frames):
+        r.render_frames(1)
+        for k, v in r.frame_stats().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / 1e3
+    stage_ms = {k: v / stage_frames for k, v in stage_ms.items()}
+    fc = r.frame_counters()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ext_gbs = fc["extend_rays"] * ALG_BYTES["extend"] / (stage_ms["extend"] * 1e-3) / 1e9
+        top = max(stage_ms, key=stage_ms.get)
+        roofline = {"kernel": "k_extend (BVH8 traversal, all waves of a frame)", "bound": "hbm", "achieved": ext_gbs, "peak": peak, "unit": "GB/s", "frac": ext_gbs / peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "traffic": None, "alg_bytes_per_ray": ALG_BYTES["extend"], "rays_per_launch_avg": fc["extend_rays"] / args.depth,
+                    "ms_per_frame": stage_ms["extend"], "share_of_frame": stage_ms["extend"] / sum(stage_ms.values()),
+                    "mrays_per_s": fc["extend_rays"] / (stage_ms["extend"] * 1e-3) / 1e6, "top_stage": top}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_run(args, 3, 1)
+            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "ms_per_sample_frame": c["ms_per_step"]}
+        line = {"metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_of(args, W, H, "gpu"),
+                "fps": args.steps / (ms * 1e-3), "samples_per_s": W * H * args.steps * world / (ms * 1e-3), "rays_per_frame": rays_per_frame,
+                "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes},
+                "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
+                "gpu_launches": launches * args.steps, "launches_per_frame": launches,
+                "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=2560)
+    ap.add_argument("--height", type=int, default=1440)
+    ap.add_argument("--depth", type=int, default=4)
+    ap.add_argument("--detail", type=float, default=0.78)
+    ap.add_argument("--texture-size", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,295 @@
+// lb_bvh.cu — GPU acceleration-structure build for the extend / shadow / visibility kernels.
+//
+// Replaces optixAccelBuild (GAS per primitive + IAS per instance + scene IAS, LumenPT/src/Framework/OptixWrapper.cpp:46-131,
+// PTScene.cpp:74-156). B200 design: with 180 GB of HBM the instances are flattened into world space (48 B per
+// triangle), so there is ONE bounding hierarchy and no per-instance ray transform in the traversal loop.
+//   1. per-triangle padded AABB + centroid bounds           (k_tri_bounds)
+//   2. 63-bit Morton codes, CUB radix sort                   (k_morton, cub::DeviceRadixSort)
+//   3. binary radix tree, Karras 2012                        (k_hierarchy)
+//   4. bottom-up AABB refit with arrival counters            (k_refit)
+//   5. level-synchronous greedy collapse into compressed 8-wide nodes (80 B, quantised child boxes, octant-ordered
+//      slots, <= 3 triangles per leaf child), triangles re-emitted in node order            (k_collapse)
+#include "lb_host.h"
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <vector>
+
+namespace lb {
+
+namespace {
+
+constexpr uint32_t kLeafMax = 3;
+
+__device__ __forceinline__ int float_order(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// conservative padding: the slab test of the traversal is evaluated in floating point
+__device__ __forceinline__ float pad_of(float lo, float hi) { return 1e-5f + fmaxf(fabsf(lo), fabsf(hi)) * 1e-5f; }
+
+__global__ void k_tri_bounds(const DevTri* __restrict__ tris, uint32_t n, float4* __restrict__ lo, float4* __restrict__ hi, int* __restrict__ cbounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 c = f3(0.f); bool ok = i < n;
+    if (ok) {
+        const float3 a = f3(tris[i].v0), b = f3(tris[i].v1), cc = f3(tris[i].v2);
+        float3 l = f3(fminf(a.x, fminf(b.x, cc.x)), fminf(a.y, fminf(b.y, cc.y)), fminf(a.z, fminf(b.z, cc.z)));
+        float3 h = f3(fmaxf(a.x, fmaxf(b.x, cc.x)), fmaxf(a.y, fmaxf(b.y, cc.y)), fmaxf(a.z, fmaxf(b.z, cc.z)));
+        c = (l + h) * 0.5f;
+        const float3 p = f3(pad_of(l.x, h.x), pad_of(l.y, h.y), pad_of(l.z, h.z));
+        l = l - p; h = h + p;
+        lo[i] = f4(l, 0.f); hi[i] = f4(h, 0.f);
+        ok = isfinite(c.x) && isfinite(c.y) && isfinite(c.z);
+    }
+    // warp reduce, then one atomic per warp and axis
+    int mn[3] = {ok ? float_order(c.x) : INT_MAX, ok ? float_order(c.y) : INT_MAX, ok ? float_order(c.z) : INT_MAX};
+    int mx[3] = {ok ? float_order(c.x) : INT_MIN, ok ? float_order(c.y) : INT_MIN, ok ? float_order(c.z) : INT_MIN};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = __reduce_min_sync(0xFFFFFFFFu, mn[k]);
+        mx[k] = __reduce_max_sync(0xFFFFFFFFu, mx[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&cbounds[k], mn[k]); atomicMax(&cbounds[3 + k], mx[k]); }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {
+    x &= 0x1FFFFFull;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, const int* __restrict__ cbounds,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 bl = f3(order_float(cbounds[0]), order_float(cbounds[1]), order_float(cbounds[2]));
+    const float3 bh = f3(order_float(cbounds[3]), order_float(cbounds[4]), order_float(cbounds[5]));
+    const float3 c = (f3(lo[i]) + f3(hi[i])) * 0.5f;
+    const float3 e = bh - bl;
+    const float sx = e.x > 0.f ? 2097151.f / e.x : 0.f, sy = e.y > 0.f ? 2097151.f / e.y : 0.f, sz = e.z > 0.f ? 2097151.f / e.z : 0.f;
+    const uint64_t qx = (uint64_t)fminf(fmaxf((c.x - bl.x) * sx, 0.f), 2097151.f);
+    const uint64_t qy = (uint64_t)fminf(fmaxf((c.y - bl.y) * sy, 0.f), 2097151.f);
+    const uint64_t qz = (uint64_t)fminf(fmaxf((c.z - bl.z) * sz, 0.f), 2097151.f);
+    keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+    vals[i] = i;
+}
+
+// ---- binary radix tree. Node ids: internal i in [0, n-2]; leaf j is id (n-1)+j.
+__device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_hierarchy(const uint64_t* __restrict__ keys, int n, uint2* __restrict__ children, uint32_t* __restrict__ parent, uint2* __restrict__ range) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do { t = (t + 1) >> 1; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const uint32_t left = (first == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+    const uint32_t right = (last == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+    children[i] = make_uint2(left, right);
+    range[i] = make_uint2((uint32_t)first, (uint32_t)last);
+    parent[left] = (uint32_t)i; parent[right] = (uint32_t)i;
+}
+
+__global__ void k_refit(const uint32_t* __restrict__ sorted, const float4* __restrict__ tlo, const float4* __restrict__ thi, int n,
+                        const uint2* __restrict__ children, const uint32_t* __restrict__ parent, float4* nlo, float4* nhi, uint32_t* flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t leaf = (uint32_t)(n - 1 + j);
+    const uint32_t src = sorted[j];
+    nlo[leaf] = tlo[src]; nhi[leaf] = thi[src];
+    if (n == 1) return;
+    uint32_t cur = parent[leaf];
+    for (;;) {
+        __threadfence();
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;      // first child to arrive stops; the second one owns the node
+        __threadfence();
+        const uint2 ch = children[cur];
+        const float4 al = __ldcg(&nlo[ch.x]), ah = __ldcg(&nhi[ch.x]), bl = __ldcg(&nlo[ch.y]), bh = __ldcg(&nhi[ch.y]);
+        nlo[cur] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+        nhi[cur] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+        if (cur == 0u) return;
+        cur = parent[cur];
+    }
+}
+
+struct WorkItem { uint32_t bnode, wnode; };
+
+__device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
+    const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// exponent byte e (biased) with 2^(e-127) * 255 >= extent
+__device__ __forceinline__ uint32_t quant_exponent(float extent) {
+    int e = 0;
+    frexpf(extent / 255.f, &e);               // extent/255 = m * 2^e, m in [0.5, 1)  =>  2^e >= extent/255
+    e += 127;
+    return (uint32_t)max(1, min(254, e));
+}
+
+__global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items, WorkItem* __restrict__ next, uint32_t* __restrict__ counters /* 0: nodes, 1: tris, 2: next items */,
+                           int n, const uint2* __restrict__ children, const uint2* __restrict__ range, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                           const uint32_t* __restrict__ sorted, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_items) return;
+    const WorkItem item = items[w];
+    const uint32_t first_leaf = (uint32_t)(n - 1);
+    auto tri_count = [&](uint32_t node) -> uint32_t { if (node >= first_leaf) return 1u; const uint2 r = range[node]; return r.y - r.x + 1u; };
+    auto first_tri = [&](uint32_t node) -> uint32_t { return node >= first_leaf ? node - first_leaf : range[node].x; };
+
+    uint32_t cand[8]; int nc = 0;
+    if (tri_count(item.bnode) <= kLeafMax) cand[nc++] = item.bnode;
+    else { const uint2 ch = children[item.bnode]; cand[nc++] = ch.x; cand[nc++] = ch.y; }
+    while (nc < 8) {                      // open the largest openable child until the node is full
+        int best = -1; float best_area = -1.f;
+        for (int c = 0; c < nc; ++c) {
+            if (tri_count(cand[c]) <= kLeafMax) continue;
+            const float a = half_area(nlo[cand[c]], nhi[cand[c]]);
+            if (a > best_area) { best_area = a; best = c; }
+        }
+        if (best < 0) break;
+        const uint2 ch = children[cand[best]];
+        cand[best] = ch.x; cand[nc++] = ch.y;
+    }
+
+    const float4 plo = nlo[item.bnode], phi = nhi[item.bnode];
+    const float3 pc = f3((plo.x + phi.x) * 0.5f, (plo.y + phi.y) * 0.5f, (plo.z + phi.z) * 0.5f);
+    // octant-ordered slots: slot bit (4,2,1) set <=> child lies towards +x,+y,+z of the parent centre
+    float cost[8][8];
+    for (int c = 0; c < nc; ++c) {
+        const float4 l = nlo[cand[c]], h = nhi[cand[c]];
+        const float3 dc = f3((l.x + h.x) * 0.5f - pc.x, (l.y + h.y) * 0.5f - pc.y, (l.z + h.z) * 0.5f - pc.z);
+        for (int s = 0; s < 8; ++s)
+            cost[c][s] = ((s & 4) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 1) ? dc.z : -dc.z);
+    }
+    int slot_of[8]; int child_at[8];
+    for (int s = 0; s < 8; ++s) child_at[s] = -1;
+    for (int c = 0; c < nc; ++c) slot_of[c] = -1;
+    for (int round = 0; round < nc; ++round) {
+        float bestv = -FLT_MAX; int bc = -1, bs = -1;
+        for (int c = 0; c < nc; ++c) {
+            if (slot_of[c] >= 0) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (child_at[s] >= 0) continue;
+                if (cost[c][s] > bestv) { bestv = cost[c][s]; bc = c; bs = s; }
+            }
+        }
+        slot_of[bc] = bs; child_at[bs] = bc;
+    }
+
+    uint32_t n_inner = 0, n_leaf_tris = 0;
+    for (int c = 0; c < nc; ++c) { const uint32_t k = tri_count(cand[c]); if (k <= kLeafMax) n_leaf_tris += k; else ++n_inner; }
+    const uint32_t child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0u;
+    const uint32_t tri_base = n_leaf_tris ? atomicAdd(&counters[1], n_leaf_tris) : 0u;
+    const uint32_t next_base = n_inner ? atomicAdd(&counters[2], n_inner) : 0u;
+
+    const uint32_t ex = quant_exponent(phi.x - plo.x), ey = quant_exponent(phi.y - plo.y), ez = quant_exponent(phi.z - plo.z);
+    const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+    const float ix = 1.0f / sx, iy = 1.0f / sy, iz = 1.0f / sz;
+
+    uint32_t imask = 0, rank = 0, tri_off = 0;
+    uint32_t meta[8], qlo[3][8], qhi[3][8];
+    for (int s = 0; s < 8; ++s) {
+        meta[s] = 0; for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; }
+        const int c = child_at[s];
+        if (c < 0) continue;
+        const uint32_t node = cand[c];
+        const float4 l = nlo[node], h = nhi[node];
+        auto qdown = [](float v, float p, float inv, float scale) { float q = floorf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q > 0.f && p + q * scale > v) q -= 1.f; return (uint32_t)q; };
+        auto qup = [](float v, float p, float inv, float scale) { float q = ceilf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q < 255.f && p + q * scale < v) q += 1.f; return (uint32_t)q; };
+        qlo[0][s] = qdown(l.x, plo.x, ix, sx); qlo[1][s] = qdown(l.y, plo.y, iy, sy); qlo[2][s] = qdown(l.z, plo.z, iz, sz);
+        qhi[0][s] = qup(h.x, plo.x, ix, sx); qhi[1][s] = qup(h.y, plo.y, iy, sy); qhi[2][s] = qup(h.z, plo.z, iz, sz);
+        const uint32_t k = tri_count(node);
+        if (k <= kLeafMax) {
+            meta[s] = (((1u << k) - 1u) << 5) | tri_off;
+            const uint32_t f = first_tri(node);
+            for (uint32_t t = 0; t < k; ++t) tris_out[tri_base + tri_off + t] = tris_in[sorted[f + t]];
+            tri_off += k;
+        } else {
+            meta[s] = (1u << 5) | (24u + (uint32_t)s);
+            imask |= 1u << s;
+            next[next_base + rank] = WorkItem{node, child_base + rank};
+            ++rank;
+        }
+    }
+    auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+    Bvh8Node out;
+    out.q0 = make_uint4(__float_as_uint(plo.x), __float_as_uint(plo.y), __float_as_uint(plo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+    out.q1 = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+    out.q2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    out.q3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    out.q4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    nodes[item.wnode] = out;
+}
+
+} // namespace
+
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out) {
+    out.num_nodes = 0; out.num_tris = 0; out.levels = 0; out.build_ms = 0.f;
+    if (n == 0) return;
+    cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
+    LB_CUDA(cudaEventRecord(e0, s));
+
+    const uint32_t n_binary = 2u * n - 1u;
+    DevBuf<float4> tlo, thi, nlo, nhi; DevBuf<int> cbounds; DevBuf<uint64_t> keys, keys_sorted; DevBuf<uint32_t> vals, sorted, parent, flags, counters;
+    DevBuf<uint2> children, range; DevBuf<WorkItem> items_a, items_b; DevBuf<unsigned char> cub_tmp;
+    tlo.reserve(n); thi.reserve(n); nlo.reserve(n_binary); nhi.reserve(n_binary); cbounds.reserve(6);
+    keys.reserve(n); keys_sorted.reserve(n); vals.reserve(n); sorted.reserve(n); parent.reserve(n_binary); flags.reserve(n); counters.reserve(4);
+    children.reserve(n); range.reserve(n); items_a.reserve(n); items_b.reserve(n);
+    out.nodes.reserve(n); out.tris.reserve(n);
+
+    const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
+    const int B = 256;
+    k_tri_bounds<<<grid_for(n, B), B, 0, s>>>(tris_in, n, tlo.p, thi.p, cbounds.p); LB_LAUNCH_CHECK();
+    k_morton<<<grid_for(n, B), B, 0, s>>>(tlo.p, thi.p, n, cbounds.p, keys.p, vals.p); LB_LAUNCH_CHECK();
+    size_t tmp_bytes = 0;
+    LB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
+    cub_tmp.reserve(tmp_bytes);
+    LB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
+    flags.zero(s);
+    if (n > 1) { k_hierarchy<<<grid_for(n - 1, B), B, 0, s>>>(keys_sorted.p, (int)n, children.p, parent.p, range.p); LB_LAUNCH_CHECK(); }
+    k_refit<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, (int)n, children.p, parent.p, nlo.p, nhi.p, flags.p); LB_LAUNCH_CHECK();
+
+    // level-synchronous collapse; binary root is internal node 0 (or the single leaf when n == 1)
+    const uint32_t h_counters[4] = {1u, 0u, 0u, 0u};
+    LB_CUDA(cudaMemcpyAsync(counters.p, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, s));
+    const WorkItem root{0u, 0u};
+    LB_CUDA(cudaMemcpyAsync(items_a.p, &root, sizeof root, cudaMemcpyHostToDevice, s));
+    uint32_t n_items = 1; WorkItem* cur = items_a.p; WorkItem* nxt = items_b.p;
+    uint32_t h_c[4];
+    while (n_items) {
+        LB_CUDA(cudaMemsetAsync(counters.p + 2, 0, sizeof(uint32_t), s));
+        k_collapse<<<grid_for(n_items, 128), 128, 0, s>>>(cur, n_items, nxt, counters.p, (int)n, children.p, range.p, nlo.p, nhi.p, sorted.p, tris_in, out.nodes.p, out.tris.p);
+        LB_LAUNCH_CHECK();
+        LB_CUDA(cudaMemcpyAsync(h_c, counters.p, sizeof h_c, cudaMemcpyDeviceToHost, s));
+        LB_CUDA(cudaStreamSynchronize(s));
+        n_items = h_c[2]; std::swap(cur, nxt); ++out.levels;
+    }
+    out.num_nodes = h_c[0]; out.num_tris = h_c[1];
+    LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
+    LB_CUDA(cudaEventElapsedTime(&out.build_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (out.num_tris != n) throw CudaError("bvh_build: triangle count mismatch after collapse");
+}
+
+} // namespace lb

@@ -1,0 +1,216 @@
+// lb_device.cuh — device-side vocabulary of the B200 wavefront path tracer: vector maths, RNG, buffer layouts.
+//
+// Arithmetic contract (DESIGN.md "parity"): this library is compiled with -fmad=false, IEEE division and
+// square root, so that every expression below evaluates exactly as written (no implicit contraction); fused
+// operations appear only where fmaf() is written out. The same contract holds for the CPU oracle
+// (-ffp-contract=off), which is what makes hit records bit-comparable.
+//
+// Reference semantics cited per item (paths relative to /root/reference/Lumen_Engine/LumenPT/):
+//   vector helpers     vendor/Include/sutil/vec_math.h:454-561 (dot = left-to-right sum, normalize = v * (1/sqrt))
+//   RNG                src/CUDAKernels/RandomUtilities.cuh:5-18
+//   surface flags      src/Shaders/CppCommon/WaveFrontDataStructs/SurfaceData.h:17-23
+//   material packing   src/Shaders/CppCommon/MaterialStructs.h:13-261
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define LB_HD __host__ __device__ __forceinline__
+#define LB_D __device__ __forceinline__
+
+namespace lb {
+
+// ---------------------------------------------------------------- float3 algebra
+LB_HD float3 f3(float a) { return make_float3(a, a, a); }
+LB_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+LB_HD float3 f3(const float4& a) { return make_float3(a.x, a.y, a.z); }
+LB_HD float4 f4(const float3& a, float w) { return make_float4(a.x, a.y, a.z, w); }
+LB_HD float3 operator+(const float3& a, const float3& b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+LB_HD float3 operator-(const float3& a, const float3& b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+LB_HD float3 operator-(const float3& a) { return f3(-a.x, -a.y, -a.z); }
+LB_HD float3 operator*(const float3& a, const float3& b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+LB_HD float3 operator*(const float3& a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+LB_HD float3 operator*(float s, const float3& a) { return f3(s * a.x, s * a.y, s * a.z); }
+LB_HD float3 operator/(const float3& a, float s) { const float inv = 1.0f / s; return a * inv; }
+LB_HD float3 operator+(const float3& a, float s) { return f3(a.x + s, a.y + s, a.z + s); }
+LB_HD float3 operator+(float s, const float3& a) { return f3(s + a.x, s + a.y, s + a.z); }
+LB_HD float3& operator+=(float3& a, const float3& b) { a = a + b; return a; }
+LB_HD float3& operator*=(float3& a, const float3& b) { a = a * b; return a; }
+LB_HD float3& operator*=(float3& a, float s) { a = a * s; return a; }
+LB_HD float3& operator/=(float3& a, float s) { a = a / s; return a; }
+LB_HD float4 operator+(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+LB_HD float4 operator*(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+LB_HD float4 operator*(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+LB_HD float2 operator+(const float2& a, const float2& b) { return make_float2(a.x + b.x, a.y + b.y); }
+LB_HD float2 operator*(const float2& a, float s) { return make_float2(a.x * s, a.y * s); }
+
+LB_HD float dot(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+LB_HD float3 cross(const float3& a, const float3& b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+LB_HD float length(const float3& v) { return sqrtf(dot(v, v)); }
+LB_HD float3 normalize(const float3& v) { const float inv = 1.0f / sqrtf(dot(v, v)); return v * inv; }
+LB_HD float3 reflect(const float3& i, const float3& n) { return i - 2.0f * n * dot(n, i); }
+LB_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+LB_HD float mixf(float a, float b, float t) { return a + t * (b - a); }
+LB_HD float sq(float a) { return a * a; }
+LB_HD float comp(const float3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+// fp16 round trip: barycentrics (IntersectionData.h:90) and motion vectors (MotionVectors.cu:44) are stored as half.
+LB_D float half_round(float f) { return __half2float(__float2half_rn(f)); }
+
+// ---------------------------------------------------------------- RNG (RandomUtilities.cuh:5-18)
+LB_HD uint32_t wang_hash(uint32_t s) { s = (s ^ 61u) ^ (s >> 16); s *= 9u; s = s ^ (s >> 4); s *= 0x27d4eb2du; s = s ^ (s >> 15); return s; }
+LB_HD uint32_t rand_u32(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+LB_HD float rand_f(uint32_t& s) { return (float)rand_u32(s) * 2.3283064365387e-10f; }
+
+// ---------------------------------------------------------------- affine transforms: row-major 3x4, explicit fused chain
+LB_HD float3 xform_point(const float* m, const float3& p) {
+    return f3(fmaf(m[0], p.x, fmaf(m[1], p.y, fmaf(m[2], p.z, m[3]))),
+              fmaf(m[4], p.x, fmaf(m[5], p.y, fmaf(m[6], p.z, m[7]))),
+              fmaf(m[8], p.x, fmaf(m[9], p.y, fmaf(m[10], p.z, m[11]))));
+}
+LB_HD float3 xform_vector(const float* m, const float3& v) {
+    return f3(fmaf(m[0], v.x, fmaf(m[1], v.y, m[2] * v.z)),
+              fmaf(m[4], v.x, fmaf(m[5], v.y, m[6] * v.z)),
+              fmaf(m[8], v.x, fmaf(m[9], v.y, m[10] * v.z)));
+}
+
+// ---------------------------------------------------------------- scene records (device)
+enum : uint32_t { SURF_EMISSIVE = 1u, SURF_ALPHA = 2u, SURF_MISS = 4u };
+
+// MaterialData (MaterialStructs.h:13-21): params.x = metallic|subsurface|specular|roughness (8 bit each, LSB first),
+// params.y = spectint|anisotropic|sheen|sheentint, params.z = clearcoat|clearcoatgloss|transmission.
+struct Material {
+    float4 color, emissive, transmittance /* w = ior or eta */, tint /* w = luminance */;
+    uint4 params;
+};
+struct DevMaterial {          // DeviceMaterial (ModelStructs.h) — material constants + 8 texture slots
+    Material mat;
+    int32_t tex_diffuse, tex_normal, tex_mr, tex_emissive, tex_transmission, tex_coat, tex_coat_rough, tex_tint;
+};
+struct DevTexture { uint32_t offset, w, h, srgb; };   // texels: RGBA8 in one pool (PTTexture.cpp:35-74: wrap, bilinear)
+
+// One row of the scene data table = (mesh instance, primitive): DevicePrimitiveInstance (ModelStructs.h:70-77,
+// PTMeshInstance.cpp:123-178). Vertex attributes stay in object space; m is the row-major world matrix.
+struct DevEntry {
+    float m[12];
+    uint32_t index_base, vertex_base, tri_count, material;
+    int32_t em_mode; float em_r, em_g, em_b, em_scale;
+    uint32_t tri_offset;     // first global (entry-major) triangle number of this entry
+    uint32_t lights_on;      // host decision of LightDataBuffer.cpp:37-125: does this entry contribute lights
+    uint32_t flag_offset;    // first per-(primitive, triangle) emissive flag of this entry's primitive
+};
+
+// World-space triangle in BVH leaf order: 48 B = 3 x LDG.128. ids ride in the w lanes.
+struct DevTri { float4 v0 /* w = instance(entry) bits */, v1 /* w = primitive index bits */, v2; };
+
+// TriangleLight (LightData.h:21-27), 64 B
+struct DevLight { float3 p0, p1, p2, normal, radiance; float area; };
+
+// 8-wide compressed BVH node, 80 B (layout after Ylitie, Karras, Laine 2017):
+//  q0: origin.xyz (f32), {ex, ey, ez, imask} bytes
+//  q1: child_base, tri_base, meta[0..3], meta[4..7]
+//  q2: qlo_x[0..7] | qlo_y[0..7]      q3: qlo_z[0..7] | qhi_x[0..7]      q4: qhi_y[0..7] | qhi_z[0..7]
+struct Bvh8Node { uint4 q0, q1, q2, q3, q4; };
+
+struct BvhView {
+    const Bvh8Node* nodes;
+    const DevTri* tris;
+    uint32_t num_tris;
+};
+
+struct SceneView {
+    const DevEntry* entries;
+    const DevMaterial* materials;
+    const DevTexture* textures;
+    const uchar4* texels;
+    const float* srgb_lut;            // 256 entries, computed on the host in double (bit-identical to the oracle)
+    const uint32_t* indices;
+    const float4* vtx_nu;             // normal.xyz, u
+    const float4* vtx_tv;             // tangent.xyz, v
+    const float* vtx_tw;              // tangent.w (bitangent sign)
+    const DevLight* lights;
+    const float* cdf;
+    uint32_t num_lights;
+    float cdf_sum;
+};
+
+// ---------------------------------------------------------------- per-pixel SoA planes (each plane: float4[npix])
+// Surface (SurfaceData.h:49-104, 176 B AoS in the reference) as 9 coalesced 16-B planes:
+//  0 position.xyz, t        1 normal.xyz, flags(bits)   2 tangent.xyz, -      3 incoming.xyz, -   4 transport.xyz, -
+//  5 color.rgba             6 transmittance.xyz, eta    7 tint.xyz, luminance 8 params (uint4 bits)
+constexpr int kSurfPlanes = 9;
+// Reservoir (ReSTIRData.h:107-183, 80 B AoS) as 5 planes:
+//  0 weightSum, weight, sampleCount(int bits), sample.pdf   1 position.xyz, area   2 normal.xyz, -   3 radiance.xyz, -
+//  4 unshadowed contribution.xyz, -
+constexpr int kResPlanes = 5;
+
+struct Surface {
+    float3 pos, normal, tangent, incoming, transport; float t; uint32_t flags; Material mat;
+};
+struct LightSample { float3 radiance, normal, position, contribution; float area, pdf; };
+struct Reservoir { float weight_sum, weight; int count; LightSample s; };
+
+LB_D void surface_store(float4* planes, size_t n, size_t i, const Surface& s) {
+    planes[0 * n + i] = f4(s.pos, s.t);
+    planes[1 * n + i] = f4(s.normal, __uint_as_float(s.flags));
+    planes[2 * n + i] = f4(s.tangent, 0.f);
+    planes[3 * n + i] = f4(s.incoming, 0.f);
+    planes[4 * n + i] = f4(s.transport, 0.f);
+    planes[5 * n + i] = s.mat.color;
+    planes[6 * n + i] = s.mat.transmittance;
+    planes[7 * n + i] = s.mat.tint;
+    planes[8 * n + i] = make_float4(__uint_as_float(s.mat.params.x), __uint_as_float(s.mat.params.y), __uint_as_float(s.mat.params.z), __uint_as_float(s.mat.params.w));
+}
+LB_D uint32_t surface_flags(const float4* planes, size_t n, size_t i) { return __float_as_uint(planes[1 * n + i].w); }
+// geometry part only (position/t/normal/flags): what the similarity tests of temporal/spatial reuse read
+LB_D void surface_load_geom(const float4* planes, size_t n, size_t i, Surface& s) {
+    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
+    s.pos = f3(a); s.t = a.w; s.normal = f3(b); s.flags = __float_as_uint(b.w);
+}
+LB_D void surface_load(const float4* planes, size_t n, size_t i, Surface& s) {
+    surface_load_geom(planes, n, i, s);
+    s.tangent = f3(planes[2 * n + i]); s.incoming = f3(planes[3 * n + i]); s.transport = f3(planes[4 * n + i]);
+    s.mat.color = planes[5 * n + i]; s.mat.transmittance = planes[6 * n + i]; s.mat.tint = planes[7 * n + i];
+    const float4 p = planes[8 * n + i];
+    s.mat.params = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.w));
+    s.mat.emissive = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+LB_D void reservoir_store(float4* planes, size_t n, size_t i, const Reservoir& r) {
+    planes[0 * n + i] = make_float4(r.weight_sum, r.weight, __int_as_float(r.count), r.s.pdf);
+    planes[1 * n + i] = f4(r.s.position, r.s.area);
+    planes[2 * n + i] = f4(r.s.normal, 0.f);
+    planes[3 * n + i] = f4(r.s.radiance, 0.f);
+    planes[4 * n + i] = f4(r.s.contribution, 0.f);
+}
+LB_D void reservoir_load(const float4* planes, size_t n, size_t i, Reservoir& r) {
+    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
+    r.weight_sum = a.x; r.weight = a.y; r.count = __float_as_int(a.z); r.s.pdf = a.w;
+    r.s.position = f3(b); r.s.area = b.w;
+    r.s.normal = f3(planes[2 * n + i]); r.s.radiance = f3(planes[3 * n + i]); r.s.contribution = f3(planes[4 * n + i]);
+}
+LB_D Reservoir reservoir_zero() {
+    Reservoir r; r.weight_sum = 0.f; r.weight = 0.f; r.count = 0;
+    r.s.radiance = f3(0.f); r.s.normal = f3(0.f); r.s.position = f3(0.f); r.s.contribution = f3(0.f); r.s.area = 0.f; r.s.pdf = 0.f;
+    return r;
+}
+
+// ---------------------------------------------------------------- wavefront queues
+// Ray queue (IntersectionRayData.h:24-78, 40 B AoS) as 3 planes: o.xyz,- | d.xyz,pixel(bits) | throughput.xyz,-
+// Shadow queue (ShadowRayData.h:13-62, 48 B AoS) as 3 planes: o.xyz,tmax | d.xyz,pixel(bits) | radiance.xyz,channel(bits)
+// Hit record (IntersectionData.h:82-108, 16 B): {instance(entry), primitive, half2 barycentrics, t}; t < 0 = miss.
+struct RayQueue { float4* o; float4* d; float4* T; };
+struct ShadowQueue { float4* o; float4* d; float4* L; };
+
+// Warp-aggregated queue append: one atomic per warp instead of one per ray (the reference's AtomicBuffer::Add does
+// one atomicAdd per element, AtomicBuffer.h:26-28).
+LB_D uint32_t queue_append_slot(uint32_t* counter) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+} // namespace lb

@@ -1,0 +1,62 @@
+// lb_host.h — host-side plumbing shared by the translation units of liblumen_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+#include <cstdint>
+#include <cstdio>
+#include "lb_device.cuh"
+
+namespace lb {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+        throw CudaError(buf);
+    }
+}
+#define LB_CUDA(expr) ::lb::cuda_check((expr), #expr, __FILE__, __LINE__)
+#define LB_LAUNCH_CHECK() ::lb::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+// RAII device array (the reference's MemoryBuffer, LumenPT/src/Framework/MemoryBuffer.cpp:26-101, without the implicit syncs)
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    // grow-only allocation; contents are not preserved
+    void reserve(size_t count) {
+        if (count <= n) return;
+        release();
+        if (count) LB_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void upload(const T* src, size_t count, cudaStream_t s) {
+        reserve(count);
+        if (count) LB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void zero(cudaStream_t s) { if (n) LB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct DeviceBvh {
+    DevBuf<Bvh8Node> nodes; DevBuf<DevTri> tris;
+    uint32_t num_nodes = 0, num_tris = 0, levels = 0;
+    float build_ms = 0.f;
+    BvhView view() const { return BvhView{nodes.p, tris.p, num_tris}; }
+    size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + (size_t)num_tris * sizeof(DevTri); }
+};
+
+// GPU LBVH (63-bit Morton, Karras 2012) -> bottom-up refit -> greedy surface-area collapse into compressed
+// 8-wide nodes. Replaces optixAccelBuild (LumenPT/src/Framework/OptixWrapper.cpp:46-131).
+// tris_in: world-space triangles in any order; the builder writes its own leaf-ordered copy into out.tris.
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out);
+
+inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
+
+} // namespace lb

@@ -1,0 +1,88 @@
+// lb_kernels.h — host-callable launchers of the wavefront, ReSTIR, volume and scene-preparation kernels.
+// One stream, no host round trips inside a frame: queue sizes live in device counters and every kernel is a
+// persistent grid (a multiple of the SM count) that strides over the device-side count.
+#pragma once
+#include "lb_host.h"
+
+namespace lb {
+
+// device counters (uint32): wavefront queue sizes + per-launch tickets for the dynamic ray fetch
+enum : uint32_t {
+    CNT_RAYS_A = 0, CNT_RAYS_B = 1, CNT_SHADOW = 2, CNT_VIS = 3, CNT_VOL_SHADOW = 4,
+    CNT_TICKET0 = 8,                 // tickets CNT_TICKET0 .. CNT_TICKET0+kMaxTickets-1, one per trace launch of a frame
+    kMaxTickets = 56, kNumCounters = 64
+};
+// device statistics (uint64): rays traced per kind this frame
+enum : uint32_t { STAT_EXTEND = 0, STAT_SHADOW = 1, STAT_VIS = 2, kNumStats = 4 };
+
+struct CameraBasis { float3 eye, U, V, W; };
+
+struct LaunchCfg { int sms = 148; cudaStream_t stream = nullptr; };
+
+struct FrameView {
+    uint32_t width = 0, height = 0, npix = 0;
+    RayQueue rays[2];
+    uint4* hits = nullptr;            // per queue slot (depth > 0)
+    uint4* primary_hits = nullptr;    // per pixel == per queue slot at depth 0
+    ShadowQueue shadow;
+    float4* surf_cur = nullptr; float4* surf_prev = nullptr;      // kSurfPlanes planes each
+    float4* res_cur = nullptr; float4* res_prev = nullptr; float4* res_tmp_a = nullptr; float4* res_tmp_b = nullptr;   // kResPlanes planes each
+    float4* channels = nullptr;       // LB_NUM_CHANNELS planes
+    float4* combined = nullptr; float4* accum = nullptr; float2* motion = nullptr; uchar4* ldr = nullptr;
+    float4* vol_hits = nullptr;       // per pixel: t0, t1, density, volume-instance (bits); t1 <= t0 = none
+    uint32_t* counters = nullptr; unsigned long long* stats = nullptr;
+};
+
+struct ShadeArgs {
+    uint32_t depth, max_depth, seed;
+    int do_nee, nee_channel, do_bounce;
+    float prev_view_proj[16];         // projection * inverse(previous camera), MotionVectors.cu:8-55
+    int volume_compat;                // 1: the reference's 5-step constant-density march feeds the volumetric shadow queue
+};
+
+struct RestirArgs { uint32_t seed; int temporal, spatial; };
+
+struct DevVolume {                    // dense density grid standing in for nanovdb::FloatGrid + its instance
+    float inv[12];                    // world -> volume object space (row-major 3x4)
+    float3 lo, hi;                    // object-space bounding box
+    const float* density;             // nx*ny*nz floats or nullptr (homogeneous 1)
+    uint32_t nx, ny, nz;
+    float instance_density, majorant;
+};
+
+// ---- wavefront (lb_wavefront.cu)
+void launch_raygen(const LaunchCfg&, const FrameView&, const CameraBasis&, uint32_t frame_count);
+void launch_extend(const LaunchCfg&, const FrameView&, const BvhView&, int queue, uint32_t ticket, bool primary, float tmin, float tmax);
+void launch_volume_extend(const LaunchCfg&, const FrameView&, int queue, bool primary, const DevVolume* volumes, uint32_t num_volumes, float tmin, float tmax);
+void launch_shade(const LaunchCfg&, const FrameView&, const SceneView&, int queue, const ShadeArgs&);
+void launch_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
+void launch_volume_shadow(const LaunchCfg&, const FrameView&, const BvhView&, const ShadowQueue& q, uint32_t ticket, float tmin);
+void launch_merge(const LaunchCfg&, const FrameView&, int blend, uint32_t blend_count);
+void launch_resolve(const LaunchCfg&, const FrameView&, float inv_frames);
+void launch_debug_trace(const LaunchCfg&, const BvhView&, const float* rays6, const float* tmax_per_ray, uint32_t n, float tmin, float tmax, void* hits20, uint8_t* occluded);
+void launch_debug_bsdf(const LaunchCfg&, const float* mat24, const float* v12, uint32_t n, float* out, bool sample);
+void launch_debug_surface(const LaunchCfg&, const float4* planes, uint32_t npix, float* out24);
+void launch_debug_reservoirs(const LaunchCfg&, const float4* planes, uint32_t npix, float* out20);
+void launch_debug_hits(const LaunchCfg&, const uint4* hits, uint32_t n, void* hits20);
+
+// ---- ReSTIR (lb_restir.cu)
+struct RestirBuffers { uint2* bags = nullptr; };      // kNumBags*kLightsPerBag entries {light index, pdf bits}
+void launch_restir(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView&, const RestirBuffers&, const RestirArgs&, uint32_t& ticket);
+
+// ---- scene preparation (lb_scene.cu)
+struct ScenePrepIn {
+    const DevEntry* entries; uint32_t num_entries; uint32_t total_tris;
+    const uint32_t* indices; const float4* vtx_pos;
+};
+void launch_flatten(const LaunchCfg&, const ScenePrepIn&, DevTri* out);
+// per (primitive, triangle) emissive flag: FindEmissivesGpu, GPUEmissiveLookup.cu:13-109
+struct DevPrimRange { uint32_t index_base, vertex_base, tri_count, material, flag_offset; };
+void launch_find_emissives(const LaunchCfg&, const SceneView&, const DevPrimRange* prims, uint32_t num_prims, uint32_t total_prim_tris,
+                           uint8_t* flags, uint32_t* per_prim_counts);
+// emissive triangle list + sorted CDF: LightDataBuffer.cpp:37-125, GPUDataBufferKernels.cu:66-186, ReSTIRKernels.cu:49-130
+struct LightBuild {
+    DevBuf<DevLight> lights; DevBuf<float> cdf; uint32_t num_lights = 0; float cdf_sum = 0.f;
+};
+void build_lights(const LaunchCfg&, const SceneView&, const ScenePrepIn&, const uint8_t* prim_flags, LightBuild& out);
+
+} // namespace lb

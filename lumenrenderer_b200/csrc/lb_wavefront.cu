@@ -1,0 +1,307 @@
+// lb_wavefront.cu — the wavefront kernels: ray generation, extend, fused extract+NEE+bounce, shadow, merge.
+//
+// Reference path (under /root/reference/Lumen_Engine/LumenPT/src/):
+//   K1  GeneratePrimaryRay        CUDAKernels/WaveFrontKernels/GPUGeneratePrimRay.cu:8-82
+//   K2  extend (optixTrace)       Shaders/WaveFrontShaders.cu:42-112, closest-hit pack :301-328
+//   K3  shadow rays + accumulate  Shaders/WaveFrontShaders.cu:114-179
+//   K6  ExtractSurfaceData        CUDAKernels/WaveFrontKernels/GPUExtractSurfaceData.cu:8-228
+//   K8  motion vectors            CUDAKernels/MotionVectors.cu:8-55
+//   K9  ResolveDirectLightHits    CUDAKernels/WaveFrontKernels/GPUShadeDirect.cu:11-40
+//   K10 ShadeDirect, K11 ShadeIndirect   GPUShadeDirect.cu:42-153, GPUShadeIndirect.cu:7-146
+//   K12 MergeOutputChannels, K13 WriteToOutput   GPUMergeOutputChannels.cu:5-88, GPUShadingKernels.cu:28-56
+// B200 design: SoA 16-byte planes, one fused shade kernel per wave (the 176-B SurfaceData only reaches HBM for the
+// primary hit, where ReSTIR needs it), warp-aggregated queue appends, persistent grids reading device-side counts.
+#include "lb_kernels.h"
+#include "lb_trace.cuh"
+#include "lb_shade.cuh"
+
+namespace lb {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------ K1 ray generation
+__device__ __forceinline__ float halton(uint32_t index, uint32_t base) {
+    ++index; float f = 1.f, r = 0.f;
+    while (index > 0) { f = f / (float)base; r = r + f * (float)(index % base); index = index / base; }
+    return r;
+}
+
+__global__ void __launch_bounds__(kBlock) k_raygen(FrameView fv, CameraBasis cam, uint32_t frame_count) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
+        const uint32_t sy = i / fv.width, sx = i - sy * fv.width;
+        const float jx = halton(frame_count + i, 2), jy = halton(frame_count + i, 3);
+        float dx = ((float)sx + jx) / (float)fv.width, dy = ((float)sy + jy) / (float)fv.height;
+        dx = -(dx * 2.0f - 1.0f); dy = -(dy * 2.0f - 1.0f);
+        const float3 d = f3(fmaf(dx, cam.U.x, fmaf(dy, cam.V.x, cam.W.x)), fmaf(dx, cam.U.y, fmaf(dy, cam.V.y, cam.W.y)), fmaf(dx, cam.U.z, fmaf(dy, cam.V.z, cam.W.z)));
+        const float len2 = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+        const float inv = 1.0f / sqrtf(len2);
+        fv.rays[0].o[i] = f4(cam.eye, 0.f);
+        fv.rays[0].d[i] = make_float4(d.x * inv, d.y * inv, d.z * inv, __uint_as_float(i));
+        fv.rays[0].T[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { fv.counters[CNT_RAYS_A] = fv.npix; fv.counters[CNT_RAYS_B] = 0u; }
+}
+
+// ------------------------------------------------------------------ K2 extend: persistent warps fetch 32 rays at a time
+__global__ void __launch_bounds__(kBlock) k_extend(BvhView bvh, const float4* __restrict__ ro, const float4* __restrict__ rd, const uint32_t* __restrict__ count,
+                                                    uint32_t* ticket, uint4* __restrict__ hits, float tmin, float tmax, unsigned long long* stat) {
+    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const float4 o = ro[i], d = rd[i];
+            HitInfo h; uint4 rec = make_uint4(0u, 0u, 0u, __float_as_uint(-1.f));
+            if (bvh8_trace<false>(bvh, f3(o), f3(d), tmin, tmax, h)) {
+                const __half2 b = __floats2half2_rn(h.u, h.v);            // fp16 barycentrics, WaveFrontShaders.cu:318-321
+                rec = make_uint4(h.inst, h.prim, *reinterpret_cast<const uint32_t*>(&b), __float_as_uint(h.t));
+            }
+            hits[i] = rec;
+        }
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------ fused shade: K6 (+K8, K9 at depth 0) + K10 + K11
+template <bool PRIMARY>
+__global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, int queue, ShadeArgs a) {
+    const uint32_t n = fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A];
+    const RayQueue in = fv.rays[queue], out = fv.rays[queue ^ 1];
+    uint32_t* out_count = &fv.counters[queue ? CNT_RAYS_A : CNT_RAYS_B];
+    const uint4* hits = PRIMARY ? fv.primary_hits : fv.hits;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const size_t np = fv.npix;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o4 = in.o[i], d4 = in.d[i], T4 = in.T[i];
+        const uint4 hr = hits[i];
+        const uint32_t pixel = __float_as_uint(d4.w);
+        const __half2 hb = *reinterpret_cast<const __half2*>(&hr.z);
+        const Surface s = extract_surface(sc, f3(o4), f3(d4), f3(T4), hr.x, hr.y, __low2float(hb), __high2float(hb), __uint_as_float(hr.w));
+
+        if (PRIMARY) {
+            surface_store(fv.surf_cur, np, pixel, s);
+            // K8 motion vector (fp16-rounded like the reference's half2 surface)
+            float2 mv = make_float2(0.f, 0.f);
+            if (s.t > 0.f) {
+                const uint32_t y = pixel / fv.width, x = pixel - y * fv.width;
+                const float cx = ((float)x + 0.5f) / (float)fv.width, cy = ((float)y + 0.5f) / (float)fv.height;
+                const float* M = a.prev_view_proj;
+                const float px = fmaf(M[0], s.pos.x, fmaf(M[1], s.pos.y, fmaf(M[2], s.pos.z, M[3])));
+                const float py = fmaf(M[4], s.pos.x, fmaf(M[5], s.pos.y, fmaf(M[6], s.pos.z, M[7])));
+                const float pw = fmaf(M[12], s.pos.x, fmaf(M[13], s.pos.y, fmaf(M[14], s.pos.z, M[15])));
+                const float inv = 1.0f / pw;
+                mv = make_float2(half_round((px * inv * 0.5f + 0.5f) - cx), half_round((py * inv * 0.5f + 0.5f) - cy));
+            }
+            fv.motion[pixel] = mv;
+            // the four light channels start the frame here: K9 writes emissive primary hits into DIRECT
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            fv.channels[0 * np + pixel] = (s.flags & SURF_EMISSIVE) ? s.mat.color : zero;
+            fv.channels[1 * np + pixel] = zero; fv.channels[2 * np + pixel] = zero;
+            if (!a.volume_compat) fv.channels[3 * np + pixel] = zero;
+        }
+
+        if (a.do_nee) {
+            uint32_t seed = wang_hash(a.seed + pixel);
+            ShadowRayOut sr;
+            const bool ok = nee_sample(sc, s, seed, sr);
+            if (ok) {
+                const uint32_t slot = queue_append_slot(&fv.counters[CNT_SHADOW]);
+                fv.shadow.o[slot] = f4(sr.o, sr.tmax);
+                fv.shadow.d[slot] = f4(sr.d, __uint_as_float(pixel));
+                fv.shadow.L[slot] = f4(sr.radiance, __int_as_float(a.nee_channel));
+            }
+        }
+        if (a.do_bounce) {
+            BounceOut b;
+            const bool ok = bounce_sample(s, pixel, wang_hash(a.seed), b);
+            if (ok) {
+                const uint32_t slot = queue_append_slot(out_count);
+                out.o[slot] = f4(b.o, 0.f);
+                out.d[slot] = f4(b.d, __uint_as_float(pixel));
+                out.T[slot] = f4(b.throughput, 0.f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3 shadow rays: any-hit, unoccluded rays add their radiance
+// One shadow ray per pixel per launch (one NEE sample per wave), so the fp32 read-modify-write below is race free —
+// the reference's fp16 RMW is racy (SURVEY hazard 2).
+__global__ void __launch_bounds__(kBlock) k_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket,
+                                                    float4* channels, size_t npix, float tmin, unsigned long long* stat) {
+    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const float4 o = q.o[i], d = q.d[i];
+            HitInfo h;
+            if (!bvh8_trace<true>(bvh, f3(o), f3(d), tmin, o.w, h)) {
+                const float4 L = q.L[i];
+                float4* dst = &channels[(size_t)__float_as_int(L.w) * npix + __float_as_uint(d.w)];
+                float4 c = *dst; c.x += L.x; c.y += L.y; c.z += L.z; *dst = c;
+            }
+        }
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------ K12 merge + progressive accumulate + K13 8-bit output
+__device__ __forceinline__ unsigned char to_srgb8(float c) {
+    c = clampf(c, 0.f, 1.f);
+    const float s = c < 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    const float x = clampf(s, 0.f, 1.f);
+    const uint32_t v = (uint32_t)(x * 256.f);
+    return (unsigned char)(v > 255u ? 255u : v);
+}
+
+__global__ void __launch_bounds__(kBlock) k_merge(FrameView fv, int blend, uint32_t blend_count) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const size_t np = fv.npix;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
+        const float4 d = fv.channels[i], in = fv.channels[np + i], sp = fv.channels[2 * np + i], vo = fv.channels[3 * np + i];
+        float4 m = make_float4((d.x + in.x) + sp.x, (d.y + in.y) + sp.y, (d.z + in.z) + sp.z, (d.w + in.w) + sp.w);
+        const float al = vo.w;
+        m = make_float4(m.x * (1.0f - al) + vo.x * al, m.y * (1.0f - al) + vo.y * al, m.z * (1.0f - al) + vo.z * al, m.w * (1.0f - al) + vo.w * al);
+        float4 c;
+        if (blend) {
+            float4 acc = fv.accum[i]; acc = acc + m; fv.accum[i] = acc;
+            const float inv = 1.0f / (float)(blend_count + 1u);
+            c = acc * inv;
+        } else { c = m; fv.accum[i] = m; }
+        fv.combined[i] = c;
+        fv.ldr[i] = make_uchar4(to_srgb8(c.x), to_srgb8(c.y), to_srgb8(c.z), 255);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_resolve(FrameView fv, float inv) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
+        const float4 c = fv.accum[i] * inv;
+        fv.combined[i] = c;
+        fv.ldr[i] = make_uchar4(to_srgb8(c.x), to_srgb8(c.y), to_srgb8(c.z), 255);
+    }
+}
+
+// ------------------------------------------------------------------ debug taps (parity tests)
+struct Hit20 { uint32_t inst, prim; float u, v, t; };
+
+__global__ void k_debug_trace(BvhView bvh, const float* __restrict__ rays6, const float* __restrict__ tmaxs, uint32_t n, float tmin, float tmax, Hit20* hits, uint8_t* occ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 o = f3(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]), d = f3(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
+    HitInfo h;
+    if (occ) { occ[i] = bvh8_trace<true>(bvh, o, d, tmin, tmaxs[i], h) ? 1 : 0; return; }
+    if (bvh8_trace<false>(bvh, o, d, tmin, tmax, h)) hits[i] = Hit20{h.inst, h.prim, h.u, h.v, h.t};
+    else hits[i] = Hit20{0u, 0u, 0.f, 0.f, -1.f};
+}
+
+__device__ Material unpack_mat24(const float* m) {
+    Material p;
+    p.color = make_float4(m[0], m[1], m[2], m[3]); p.transmittance = make_float4(m[4], m[5], m[6], m[7]); p.tint = make_float4(m[8], m[9], m[10], m[11]);
+    p.emissive = make_float4(0.f, 0.f, 0.f, 0.f); p.params = make_uint4(0u, 0u, 0u, 0u);
+    pack8(p.params.x, m[12], 0); pack8(p.params.x, m[13], 8); pack8(p.params.x, m[14], 16); pack8(p.params.x, m[15], 24);
+    pack8(p.params.y, m[16], 0); pack8(p.params.y, m[17], 8); pack8(p.params.y, m[18], 16); pack8(p.params.y, m[19], 24);
+    pack8(p.params.z, m[20], 0); pack8(p.params.z, m[21], 8); pack8(p.params.z, m[22], 16);
+    return p;
+}
+__global__ void k_debug_bsdf(const float* __restrict__ mat24, const float* __restrict__ v12, uint32_t n, float* out, int sample) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Material m = unpack_mat24(mat24);
+    const float* v = v12 + 12 * i;
+    const float3 nrm = f3(v[0], v[1], v[2]), tan = f3(v[3], v[4], v[5]), wo = f3(v[6], v[7], v[8]);
+    if (!sample) {
+        float pdf = 0.f; const float3 b = bsdf_eval(m, nrm, tan, wo, f3(v[9], v[10], v[11]), pdf);
+        out[4 * i] = b.x; out[4 * i + 1] = b.y; out[4 * i + 2] = b.z; out[4 * i + 3] = pdf;
+    } else {
+        float pdf = 0.f; bool spec = false; float3 wi = f3(0.f);
+        const float3 b = bsdf_sample(m, nrm, nrm, tan, wo, 1.f, v[9], v[10], v[11], wi, pdf, spec);
+        float* o = out + 8 * i; o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = wi.x; o[4] = wi.y; o[5] = wi.z; o[6] = pdf; o[7] = spec ? 1.f : 0.f;
+    }
+}
+__global__ void k_debug_surface(const float4* __restrict__ planes, uint32_t npix, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    Surface s; surface_load(planes, npix, i, s);
+    float* o = out + 24 * (size_t)i;
+    o[0] = s.pos.x; o[1] = s.pos.y; o[2] = s.pos.z; o[3] = s.t; o[4] = s.normal.x; o[5] = s.normal.y; o[6] = s.normal.z; o[7] = (float)s.flags;
+    o[8] = s.tangent.x; o[9] = s.tangent.y; o[10] = s.tangent.z; o[11] = 0; o[12] = s.incoming.x; o[13] = s.incoming.y; o[14] = s.incoming.z; o[15] = 0;
+    o[16] = s.transport.x; o[17] = s.transport.y; o[18] = s.transport.z; o[19] = 0; o[20] = s.mat.color.x; o[21] = s.mat.color.y; o[22] = s.mat.color.z; o[23] = s.mat.color.w;
+}
+__global__ void k_debug_reservoirs(const float4* __restrict__ planes, uint32_t npix, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    Reservoir q; reservoir_load(planes, npix, i, q);
+    float* o = out + 20 * (size_t)i;
+    o[0] = q.weight_sum; o[1] = q.weight; o[2] = (float)q.count; o[3] = q.s.pdf; o[4] = q.s.position.x; o[5] = q.s.position.y; o[6] = q.s.position.z; o[7] = q.s.area;
+    o[8] = q.s.normal.x; o[9] = q.s.normal.y; o[10] = q.s.normal.z; o[11] = 0; o[12] = q.s.radiance.x; o[13] = q.s.radiance.y; o[14] = q.s.radiance.z; o[15] = 0;
+    o[16] = q.s.contribution.x; o[17] = q.s.contribution.y; o[18] = q.s.contribution.z; o[19] = 0;
+}
+__global__ void k_debug_hits(const uint4* __restrict__ hits, uint32_t n, Hit20* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 h = hits[i];
+    const __half2 b = *reinterpret_cast<const __half2*>(&h.z);
+    const float t = __uint_as_float(h.w);
+    out[i] = t > 0.f ? Hit20{h.x, h.y, __low2float(b), __high2float(b), t} : Hit20{0u, 0u, 0.f, 0.f, -1.f};
+}
+
+inline int persistent_grid(const LaunchCfg& cfg, int per_sm) { return cfg.sms * per_sm; }
+
+} // namespace
+
+void launch_raygen(const LaunchCfg& cfg, const FrameView& fv, const CameraBasis& cam, uint32_t frame_count) {
+    k_raygen<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, cam, frame_count); LB_LAUNCH_CHECK();
+}
+void launch_extend(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, int queue, uint32_t ticket, bool primary, float tmin, float tmax) {
+    k_extend<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.rays[queue].o, fv.rays[queue].d, &fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A],
+        &fv.counters[CNT_TICKET0 + ticket], primary ? fv.primary_hits : fv.hits, tmin, tmax, &fv.stats[STAT_EXTEND]); LB_LAUNCH_CHECK();
+}
+void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, int queue, const ShadeArgs& a) {
+    if (a.depth == 0) k_shade<true><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
+    else k_shade<false><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
+    LB_LAUNCH_CHECK();
+}
+void launch_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
+    k_shadow<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.shadow, &fv.counters[CNT_SHADOW], &fv.counters[CNT_TICKET0 + ticket],
+        fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW]); LB_LAUNCH_CHECK();
+}
+void launch_merge(const LaunchCfg& cfg, const FrameView& fv, int blend, uint32_t blend_count) {
+    k_merge<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, blend, blend_count); LB_LAUNCH_CHECK();
+}
+void launch_resolve(const LaunchCfg& cfg, const FrameView& fv, float inv_frames) {
+    k_resolve<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, inv_frames); LB_LAUNCH_CHECK();
+}
+void launch_debug_trace(const LaunchCfg& cfg, const BvhView& bvh, const float* rays6, const float* tmaxs, uint32_t n, float tmin, float tmax, void* hits20, uint8_t* occluded) {
+    if (!n) return;
+    k_debug_trace<<<grid_for(n, 128), 128, 0, cfg.stream>>>(bvh, rays6, tmaxs, n, tmin, tmax, (Hit20*)hits20, occluded); LB_LAUNCH_CHECK();
+}
+void launch_debug_bsdf(const LaunchCfg& cfg, const float* mat24, const float* v12, uint32_t n, float* out, bool sample) {
+    if (!n) return;
+    k_debug_bsdf<<<grid_for(n, 128), 128, 0, cfg.stream>>>(mat24, v12, n, out, sample ? 1 : 0); LB_LAUNCH_CHECK();
+}
+void launch_debug_surface(const LaunchCfg& cfg, const float4* planes, uint32_t npix, float* out24) {
+    k_debug_surface<<<grid_for(npix, 256), 256, 0, cfg.stream>>>(planes, npix, out24); LB_LAUNCH_CHECK();
+}
+void launch_debug_reservoirs(const LaunchCfg& cfg, const float4* planes, uint32_t npix, float* out20) {
+    k_debug_reservoirs<<<grid_for(npix, 256), 256, 0, cfg.stream>>>(planes, npix, out20); LB_LAUNCH_CHECK();
+}
+void launch_debug_hits(const LaunchCfg& cfg, const uint4* hits, uint32_t n, void* hits20) {
+    k_debug_hits<<<grid_for(n, 256), 256, 0, cfg.stream>>>(hits, n, (Hit20*)hits20); LB_LAUNCH_CHECK();
+}
+
+} // namespace lb
