@@ -159,7 +159,8 @@ def run_gpu(args):
     scene = workload_scene(args)
     r = lr.Renderer(st)
     r.load_scene(scene)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                    # a real (non-null) stream shared by torch events, NCCL and the renderer
+    torch.cuda.set_stream(stream)
     r.set_stream(stream.cuda_stream)
     cam_pos, cam_rot = scene.camera["position"], scene.camera["rotation"]
 

@@ -1,6 +1,9 @@
 // C-callable wrapper over the UNMODIFIED reference BSDF headers, compiled for the host.
 // Built by oracle/Makefile into oracle/_ref/libref_bsdf.so; used only by tests to pin the oracle.
 #include "shim.h"
+// Compile the DEVICE branches of the reference headers (ggxmdf.cuh:90,208 sincosf ordering; disney.cuh:175 / frosted.cuh:126 default
+// `adjoint` parameter): that is the code the reference renders with. All system / CUDA headers are already included by shim.h.
+#define __CUDACC__ 1
 #include "CUDAKernels/RandomUtilities.cuh"
 #include "CUDAKernels/disney.cuh"
 

@@ -16,6 +16,9 @@ static inline float3 lerp(const float3& a, const float3& b, const float t) { ret
 static inline float saturate(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 using std::min; using std::max; using std::abs;
+// On the device CUDA supplies float overloads of the unqualified maths calls the headers make (fabs(float), sqrt(float), pow(float,float));
+// plain <cmath> leaves only C's double versions in the global namespace, which would silently evaluate those expressions in double.
+using std::fabs; using std::sqrt; using std::pow; using std::exp; using std::log; using std::sin; using std::cos; using std::floor;
 static inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
 // disney.cuh / frosted.cuh declare the `adjoint` default parameter only under __CUDACC__ but use it
 // in the body unconditionally; a file-scope constant with the default value restores that behaviour.
