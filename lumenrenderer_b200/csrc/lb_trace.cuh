@@ -32,9 +32,11 @@ LB_D bool tri_test(const float3& org, const RayShear& s, const float3& p0, const
     const float Ax = fmaf(-s.sx, Akz, comp(A, s.kx)), Ay = fmaf(-s.sy, Akz, comp(A, s.ky));
     const float Bx = fmaf(-s.sx, Bkz, comp(B, s.kx)), By = fmaf(-s.sy, Bkz, comp(B, s.ky));
     const float Cx = fmaf(-s.sx, Ckz, comp(C, s.kx)), Cy = fmaf(-s.sy, Ckz, comp(C, s.ky));
-    float U = fmaf(Cx, By, -(Cy * Bx));
-    float V = fmaf(Ax, Cy, -(Ay * Cx));
-    float W = fmaf(Bx, Ay, -(By * Ax));
+    // Edge functions with UNFUSED products (explicit _rn intrinsics are never contracted): for an edge shared by two triangles
+    // the two evaluations are exact negations of each other — the watertightness property. An FMA would round only one product.
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
     if (U == 0.0f || V == 0.0f || W == 0.0f) {          // edge-on: redo the edge functions in double (rare)
         U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
         V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
@@ -62,7 +64,10 @@ LB_D bool bvh8_trace(const BvhView& bvh, const float3& o, const float3& d, float
     if (bvh.num_tris == 0 || !(tmax > tmin)) return false;
     const RayShear sh = make_shear(d);
     const float3 idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-    const uint32_t octinv = (d.x < 0.f ? 0u : 4u) | (d.y < 0.f ? 0u : 2u) | (d.z < 0.f ? 0u : 1u);
+    // octant and near/far swizzle come from the sign of the INVERSE direction, so that a component of -0.0 (inverse -1e20)
+    // is treated consistently by both
+    const bool neg_x = idir.x < 0.f, neg_y = idir.y < 0.f, neg_z = idir.z < 0.f;
+    const uint32_t octinv = (neg_x ? 0u : 4u) | (neg_y ? 0u : 2u) | (neg_z ? 0u : 1u);
     const uint32_t octinv4 = octinv * 0x01010101u;
     float best = tmax; bool found = false; uint32_t bi = 0, bp = 0; float bu = 0.f, bv = 0.f;
 
@@ -97,9 +102,9 @@ LB_D bool bvh8_trace(const BvhView& bvh, const float3& o, const float3& d, float
                 const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
                 const uint32_t lox = h ? q2.y : q2.x, loy = h ? q2.w : q2.z, loz = h ? q3.y : q3.x;
                 const uint32_t hix = h ? q3.w : q3.z, hiy = h ? q4.y : q4.x, hiz = h ? q4.w : q4.z;
-                const uint32_t nx = d.x < 0.f ? hix : lox, fx = d.x < 0.f ? lox : hix;
-                const uint32_t ny = d.y < 0.f ? hiy : loy, fy = d.y < 0.f ? loy : hiy;
-                const uint32_t nz = d.z < 0.f ? hiz : loz, fz = d.z < 0.f ? loz : hiz;
+                const uint32_t nx = neg_x ? hix : lox, fx = neg_x ? lox : hix;
+                const uint32_t ny = neg_y ? hiy : loy, fy = neg_y ? loy : hiy;
+                const uint32_t nz = neg_z ? hiz : loz, fz = neg_z ? loz : hiz;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int sft = 8 * j;

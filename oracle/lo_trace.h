@@ -40,9 +40,11 @@ static inline bool tri_test(const V3& org, const RayShear& s, const V3& p0, cons
     const float Ax = fmaf(-s.sx, Akz, comp(A, s.kx)), Ay = fmaf(-s.sy, Akz, comp(A, s.ky));
     const float Bx = fmaf(-s.sx, Bkz, comp(B, s.kx)), By = fmaf(-s.sy, Bkz, comp(B, s.ky));
     const float Cx = fmaf(-s.sx, Ckz, comp(C, s.kx)), Cy = fmaf(-s.sy, Ckz, comp(C, s.ky));
-    float U = fmaf(Cx, By, -(Cy * Bx));
-    float V = fmaf(Ax, Cy, -(Ay * Cx));
-    float W = fmaf(Bx, Ay, -(By * Ax));
+    // Edge functions with UNFUSED products: for an edge shared by two triangles the two evaluations are then exact negations
+    // of each other, which is what makes the test watertight (a fused multiply-add rounds only one product and breaks this).
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
         U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
         V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
