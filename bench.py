@@ -201,7 +201,7 @@ def run_gpu(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     if world > 1:
         if rank == 0:
-            r.resolve_accum(args.steps * world + 0)     # accumulation started at set_blend... warm-up frames are part of the sum
+            r.resolve_accum(r.accum_buffer()[2] * world)     # every rank accumulated the same number of frames (warm-up included)
         t = torch.tensor([ms, float(rays)], device="cuda", dtype=torch.float64)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)

@@ -131,6 +131,7 @@ struct Renderer {
         for (auto& p : d_res) { p.reserve(n * kResPlanes); p.zero(stream); }
         d_channels.reserve(n * LB_NUM_CHANNELS); d_channels.zero(stream);
         d_combined.reserve(n); d_combined.zero(stream); d_accum.reserve(n); d_accum.zero(stream);
+        d_vol_hits.reserve(n); for (auto& p : d_vol_shadow) p.reserve(n * 5);
         d_hits.reserve(n); d_primary_hits.reserve(n); d_primary_hits.zero(stream); d_motion.reserve(n); d_motion.zero(stream); d_ldr.reserve(n); d_ldr.zero(stream);
         blend_count = 0; frame_index = 0; surf_cur = 0; res_cur = 0; have_prev_cam = false;
     }
@@ -298,7 +299,7 @@ struct Renderer {
         fv.surf_cur = d_surf[surf_cur].p; fv.surf_prev = d_surf[surf_cur ^ 1u].p;
         fv.res_cur = d_res[res_cur].p; fv.res_prev = d_res[res_cur ^ 1u].p; fv.res_tmp_a = d_res[2].p; fv.res_tmp_b = d_res[3].p;
         fv.channels = d_channels.p; fv.combined = d_combined.p; fv.accum = d_accum.p; fv.motion = d_motion.p; fv.ldr = d_ldr.p;
-        fv.vol_hits = d_vol_hits.p; fv.counters = d_counters.p; fv.stats = d_stats.p;
+        fv.vol_hits = d_vol_hits.p; fv.vol_shadow = ShadowQueue{d_vol_shadow[0].p, d_vol_shadow[1].p, d_vol_shadow[2].p}; fv.counters = d_counters.p; fv.stats = d_stats.p;
         return fv;
     }
 
@@ -327,19 +328,26 @@ struct Renderer {
         lap("raygen");
         uint32_t seed = wang_hash(frame_count);
         uint32_t ticket = 0;
-        ShadeArgs a{}; a.max_depth = st.depth; a.volume_compat = 0;
+        ShadeArgs a{}; a.max_depth = st.depth;
+        a.volumes = d_volumes.p; a.num_volumes = (uint32_t)vinstances.size(); a.volume_mode = (int)st.volume_mode;
         prev_view_proj(a.prev_view_proj);
         for (uint32_t depth = 0; depth < st.depth; ++depth) {
             const int queue = (int)(depth & 1u);
             launch_extend(c, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
             lap("extend");
-            // the next wave's queue and this wave's shadow queue start empty
+            // the next wave's queue and this wave's shadow queues start empty
             LB_CUDA(cudaMemsetAsync(d_counters.p + (queue ? CNT_RAYS_A : CNT_RAYS_B), 0, sizeof(uint32_t), stream));
             LB_CUDA(cudaMemsetAsync(d_counters.p + CNT_SHADOW, 0, sizeof(uint32_t), stream));
             a.depth = depth; a.seed = seed;
             a.do_nee = (depth > 0 || !st.restir) ? 1 : 0;
             a.nee_channel = depth == 0 ? LB_CHANNEL_DIRECT : LB_CHANNEL_INDIRECT;
             a.do_bounce = depth + 1u < st.depth ? 1 : 0;
+            if (a.num_volumes) {
+                LB_CUDA(cudaMemsetAsync(d_counters.p + CNT_VOL_SHADOW, 0, sizeof(uint32_t), stream));
+                launch_volume_extend(c, fv, queue, depth == 0, d_volumes.p, a.num_volumes, 0.01f, 5000.f); ++launches;
+                if (st.volume_mode == LB_VOLUME_DELTA) { launch_volume_delta(c, fv, sc, queue, depth == 0, a); ++launches; }
+                lap("volume");
+            }
             launch_shade(c, fv, sc, queue, a); ++launches;
             lap("shade");
             if (depth == 0 && st.restir) {
@@ -351,7 +359,8 @@ struct Renderer {
                 (void)t0;
                 lap("restir");
             }
-            if (a.do_nee) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
+            if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
+            if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
         launch_merge(c, fv, (int)st.blend_output, blend_count); ++launches;

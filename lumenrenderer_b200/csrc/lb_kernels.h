@@ -29,18 +29,10 @@ struct FrameView {
     float4* res_cur = nullptr; float4* res_prev = nullptr; float4* res_tmp_a = nullptr; float4* res_tmp_b = nullptr;   // kResPlanes planes each
     float4* channels = nullptr;       // LB_NUM_CHANNELS planes
     float4* combined = nullptr; float4* accum = nullptr; float2* motion = nullptr; uchar4* ldr = nullptr;
-    float4* vol_hits = nullptr;       // per pixel: t0, t1, density, volume-instance (bits); t1 <= t0 = none
+    float4* vol_hits = nullptr;       // per queue slot: t0, t1, density, volume-instance (int bits, < 0 = none)
+    ShadowQueue vol_shadow;           // compat-mode volumetric shadow rays, 5 per ray and wave
     uint32_t* counters = nullptr; unsigned long long* stats = nullptr;
 };
-
-struct ShadeArgs {
-    uint32_t depth, max_depth, seed;
-    int do_nee, nee_channel, do_bounce;
-    float prev_view_proj[16];         // projection * inverse(previous camera), MotionVectors.cu:8-55
-    int volume_compat;                // 1: the reference's 5-step constant-density march feeds the volumetric shadow queue
-};
-
-struct RestirArgs { uint32_t seed; int temporal, spatial; };
 
 struct DevVolume {                    // dense density grid standing in for nanovdb::FloatGrid + its instance
     float inv[12];                    // world -> volume object space (row-major 3x4)
@@ -50,13 +42,25 @@ struct DevVolume {                    // dense density grid standing in for nano
     float instance_density, majorant;
 };
 
+struct ShadeArgs {
+    uint32_t depth, max_depth, seed;
+    int do_nee, nee_channel, do_bounce;
+    float prev_view_proj[16];         // projection * inverse(previous camera), MotionVectors.cu:8-55
+    const DevVolume* volumes; uint32_t num_volumes;
+    int volume_mode;                  // LB_VOLUME_COMPAT: the reference's 5-step march; LB_VOLUME_DELTA: delta / ratio tracking
+};
+
+struct RestirArgs { uint32_t seed; int temporal, spatial; };
+
 // ---- wavefront (lb_wavefront.cu)
 void launch_raygen(const LaunchCfg&, const FrameView&, const CameraBasis&, uint32_t frame_count);
 void launch_extend(const LaunchCfg&, const FrameView&, const BvhView&, int queue, uint32_t ticket, bool primary, float tmin, float tmax);
+// ---- volumes (lb_volume.cu)
 void launch_volume_extend(const LaunchCfg&, const FrameView&, int queue, bool primary, const DevVolume* volumes, uint32_t num_volumes, float tmin, float tmax);
+void launch_volume_delta(const LaunchCfg&, const FrameView&, const SceneView&, int queue, bool primary, const ShadeArgs&);
 void launch_shade(const LaunchCfg&, const FrameView&, const SceneView&, int queue, const ShadeArgs&);
 void launch_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
-void launch_volume_shadow(const LaunchCfg&, const FrameView&, const BvhView&, const ShadowQueue& q, uint32_t ticket, float tmin);
+void launch_volume_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
 void launch_merge(const LaunchCfg&, const FrameView&, int blend, uint32_t blend_count);
 void launch_resolve(const LaunchCfg&, const FrameView&, float inv_frames);
 void launch_debug_trace(const LaunchCfg&, const BvhView&, const float* rays6, const float* tmax_per_ray, uint32_t n, float tmin, float tmax, void* hits20, uint8_t* occluded);

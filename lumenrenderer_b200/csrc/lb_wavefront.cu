@@ -14,6 +14,7 @@
 #include "lb_kernels.h"
 #include "lb_trace.cuh"
 #include "lb_shade.cuh"
+#include "lb_volume.cuh"
 
 namespace lb {
 
@@ -104,14 +105,43 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
             // the four light channels start the frame here: K9 writes emissive primary hits into DIRECT
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
             fv.channels[0 * np + pixel] = (s.flags & SURF_EMISSIVE) ? s.mat.color : zero;
-            fv.channels[1 * np + pixel] = zero; fv.channels[2 * np + pixel] = zero;
-            if (!a.volume_compat) fv.channels[3 * np + pixel] = zero;
+            fv.channels[1 * np + pixel] = zero; fv.channels[2 * np + pixel] = zero; fv.channels[3 * np + pixel] = zero;
         }
 
         if (a.do_nee) {
             uint32_t seed = wang_hash(a.seed + pixel);
+            if (a.num_volumes && a.volume_mode == 0 /* LB_VOLUME_COMPAT */ && sc.num_lights) {
+                // VolumetricShadeDirect (GPUVolumetricShadeDirect.cu:8-101): 5 fixed steps, constant density per unit length, the grid is
+                // never sampled; every step spawns a shadow ray of constant radiance 0.01; accumulated density becomes the alpha
+                const float4 vh = fv.vol_hits[i];
+                if (__float_as_int(vh.w) >= 0 && vh.y > vh.x) {
+                    const float3 rd3 = f3(d4), entry = f3(o4) + rd3 * vh.x;
+                    const float distance = vh.y - vh.x; float acc = 0.f; const float step = distance / 5;
+                    float3 prev = entry; const float offset = rand_f(seed) * step;
+                    for (int k = 0; k < 5 && acc < 1.0f && (float)k * step < distance; k++) {
+                        const float ts = (float)k * step + offset; const float3 p = entry + rd3 * ts;
+                        const float dprev = length(p - prev); prev = p;
+                        uint32_t li; float lpdf; cdf_get(sc, rand_f(seed), li, lpdf);
+                        const DevLight l = load_light(sc, li);
+                        const float u = rand_f(seed), v = rand_f(seed) * (1.f - u);
+                        const float3 point = l.p0 + ((l.p1 - l.p0) * u) + ((l.p2 - l.p0) * v);
+                        float3 dir = point - p; const float ld = length(dir); dir /= ld;
+                        const uint32_t slot = queue_append_slot(&fv.counters[CNT_VOL_SHADOW]);
+                        fv.vol_shadow.o[slot] = f4(p, ld - 0.2f);
+                        fv.vol_shadow.d[slot] = f4(dir, __uint_as_float(pixel));
+                        fv.vol_shadow.L[slot] = make_float4(0.01f, 0.01f, 0.01f, __int_as_float(3));
+                        acc += vh.z * dprev;
+                    }
+                    fv.channels[3 * np + pixel].w = acc;          // rgb of the channel is only ever touched by the shadow adds
+                }
+            }
             ShadowRayOut sr;
-            const bool ok = nee_sample(sc, s, seed, sr);
+            bool ok = nee_sample(sc, s, seed, sr);
+            if (ok && a.num_volumes && a.volume_mode == 1 /* LB_VOLUME_DELTA */) {
+                uint32_t vseed = wang_hash((a.seed ^ 0x85ebca6bu) + pixel);
+                const float tr = ratio_transmittance(a.volumes, a.num_volumes, sr.o, sr.d, 0.01f, sr.tmax, vseed);
+                sr.radiance *= tr;
+            }
             if (ok) {
                 const uint32_t slot = queue_append_slot(&fv.counters[CNT_SHADOW]);
                 fv.shadow.o[slot] = f4(sr.o, sr.tmax);

@@ -415,7 +415,7 @@ struct Renderer {
     // ------------------------------------------------------------------ NEE: ShadeDirect, GPUShadeDirect.cu:42-153
     bool shade_direct_pixel(const Surface& s, uint32_t pixel_index, uint32_t seed_in, int chan, const VolumeHit* vh, std::vector<ShadowRay>* vol_rays, ShadowRay& out) {
         uint32_t seed = wang_hash(seed_in + pixel_index);
-        if (vh && vh->t1 > vh->t0 && st.volume_mode == LB_VOLUME_COMPAT) volume_compat_pixel(s, pixel_index, *vh, seed, *vol_rays);
+        if (vh && vh->vinst >= 0 && vh->t1 > vh->t0 && st.volume_mode == LB_VOLUME_COMPAT && !lights.empty()) volume_compat_pixel(s, pixel_index, *vh, seed, *vol_rays);
         if (s.flags || lights.empty()) return false;
         uint32_t li; float lpdf; cdf_get(rand_f(seed), li, lpdf);
         const LightTri& l = lights[li];
@@ -430,6 +430,10 @@ struct Renderer {
         V3 c = (bsdf / bpdf) * solid * cos_in * l.radiance;
         c *= ((1.f / lpdf) * s.transport);
         out = {pixel_index % st.width, pixel_index / st.width, s.pos, dir, dist - 0.2f, c, chan};
+        if (!vinstances.empty() && st.volume_mode == LB_VOLUME_DELTA) {          // shadow rays cross the media: ratio-tracked transmittance
+            uint32_t vseed = wang_hash((seed_in ^ 0x85ebca6bu) + pixel_index);
+            out.radiance *= ratio_transmittance(out.o, out.d, 0.01f, out.tmax, vseed);
+        }
         return true;
     }
     // VolumetricShadeDirect (compat mode), GPUVolumetricShadeDirect.cu:8-101; ray data reconstructed from the pixel's ray
@@ -628,6 +632,71 @@ struct Renderer {
         return false;
     }
 
+    // ratio-tracking estimate of the transmittance of [tmin, tmax] through every volume instance (homogeneous media: analytic)
+    float ratio_transmittance(const V3& ro, const V3& rd, float tmin, float tmax, uint32_t& seed) const {
+        float tr = 1.f;
+        for (size_t k = 0; k < vinstances.size(); ++k) {
+            const VolumeInstance& vi = vinstances[k]; const Volume& vol = volumes[vi.volume];
+            const V3 o = xform_point(vi.inv, ro), d = xform_vector(vi.inv, rd);
+            float t0 = tmin, t1 = tmax; bool ok = true;
+            for (int a = 0; a < 3 && ok; ++a) {
+                const float inv = 1.0f / comp(d, a);
+                float ta = (comp(vol.lo, a) - comp(o, a)) * inv, tb = (comp(vol.hi, a) - comp(o, a)) * inv;
+                if (ta > tb) std::swap(ta, tb);
+                t0 = fmaxf(t0, ta); t1 = fminf(t1, tb); ok = t0 <= t1;
+            }
+            if (!ok) continue;
+            const float sigma_max = vi.density * vol.majorant;
+            if (!(sigma_max > 0.f)) continue;
+            if (vol.density.empty()) { tr *= expf(-sigma_max * (t1 - t0)); continue; }
+            float t = t0;
+            for (int it = 0; it < 1024; ++it) {
+                t -= logf(1.0f - rand_f(seed) * 0.99999994f) / sigma_max;
+                if (t >= t1) break;
+                const float dens = vi.density * volume_density(vol, o + d * t);
+                tr *= 1.0f - dens / sigma_max;
+                if (tr <= 0.f) return 0.f;
+            }
+        }
+        return tr;
+    }
+    // LB_VOLUME_DELTA: a real collision inside the nearest medium replaces this wave's surface interaction by an isotropic
+    // scattering event (albedo 0.8): NEE with ratio-tracked transmittance + continuation ray. RNG stream WangHash((seed ^ 0x9e3779b9) + pixel).
+    void delta_scatter_all(std::vector<Ray>& rays, std::vector<HitRec>& hits, const std::vector<VolumeHit>& vhits, uint32_t seed_in, int chan, bool bounce,
+                           std::vector<ShadowRay>& srays, std::vector<Ray>& next) const {
+        for (size_t i = 0; i < rays.size(); ++i) {
+            const VolumeHit& vh = vhits[i];
+            if (vh.vinst < 0) continue;
+            const Ray& ray = rays[i];
+            const uint32_t pixel = ray.py * st.width + ray.px;
+            uint32_t seed = wang_hash((seed_in ^ 0x9e3779b9u) + pixel);
+            float ts;
+            if (!delta_track(vh, ray, seed, ts)) continue;
+            hits[i].t = -2.f;
+            const V3 p = ray.o + ray.d * ts; const V3 T = ray.contrib;
+            if (!lights.empty()) {
+                uint32_t li; float lpdf; cdf_get(rand_f(seed), li, lpdf);
+                const LightTri& l = lights[li];
+                const float u = rand_f(seed), v = rand_f(seed) * (1.f - u);
+                const V3 point = l.p0 + ((l.p1 - l.p0) * u) + ((l.p2 - l.p0) * v);
+                V3 dir = point - p; const float dist = length(dir); dir /= dist;
+                const float cos_out = fmaxf(0.f, dot(l.normal, -dir));
+                if (dist > 0.01f && cos_out > 0.f) {
+                    const float solid = (cos_out * l.area) / (dist * dist);
+                    const float tr = ratio_transmittance(p, dir, 0.f, dist - 0.2f, seed);
+                    const V3 c = T * (0.8f * (0.25f * kInvPi) * solid * (1.f / lpdf) * tr) * l.radiance;
+                    srays.push_back({ray.px, ray.py, p, dir, dist - 0.2f, c, chan});
+                }
+            }
+            if (bounce) {
+                const float z = 1.f - 2.f * rand_f(seed);
+                const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+                const float phi = kTwoPi * rand_f(seed);
+                next.push_back({ray.px, ray.py, p, v3(r * cosf(phi), r * sinf(phi), z), T * 0.8f});
+            }
+        }
+    }
+
     // ------------------------------------------------------------------ frame: WaveFrontRenderer::TraceFrame, WaveFrontRenderer.cpp:435-1089
     void render_frame() {
         auto tic = std::chrono::steady_clock::now();
@@ -651,8 +720,11 @@ struct Renderer {
             extend(rays, hits); counters[0] += rays.size();
             extend_volumes(rays, hits, vhits);
             lap("extend");
-            if (depth == 0) primary_hits = hits;
-            // delta tracking replaces the surface hit by a medium interaction (handled as a scatter of the ray)
+            next.clear();
+            std::vector<ShadowRay> srays, vrays;
+            const bool delta = !vinstances.empty() && st.volume_mode == LB_VOLUME_DELTA;
+            if (delta) { delta_scatter_all(rays, hits, vhits, seed, depth == 0 ? LB_CHANNEL_DIRECT : LB_CHANNEL_INDIRECT, depth < st.depth - 1, srays, next); lap("volume"); }
+            if (depth == 0) { primary_hits = hits; for (auto& h : primary_hits) if (!(h.t > 0.f)) h = {0, 0, 0, 0, -1.f}; }
             std::vector<Surface>& S = surface[depth == 0 ? cur : 2];
             extract(rays, hits, S);
             lap("extract");
@@ -661,14 +733,13 @@ struct Renderer {
             std::fill(volhits.begin(), volhits.end(), VolumeHit{});
             for (size_t i = 0; i < rays.size(); ++i) if (vhits[i].vinst >= 0) volhits[(size_t)rays[i].py * st.width + rays[i].px] = vhits[i];
             if (depth == 0) { motion_vectors(S); lap("motion"); }
-            next.clear();
-            std::vector<ShadowRay> srays, vrays;
             if (depth == 0) {
                 // ResolveDirectLightHits, GPUShadeDirect.cu:11-40
                 for (uint32_t i = 0; i < n; ++i) if (S[i].flags & SURF_EMISSIVE) channel[LB_CHANNEL_DIRECT][i] = S[i].mat.color;
                 if (st.restir) {
                     if (!lights.empty()) restir_run(S, surface[prv], seed);
                     lap("restir");
+                    if (delta) resolve_shadow(srays);
                 } else {
                     shade_direct_all(S, rays, seed, LB_CHANNEL_DIRECT, srays, vrays);
                     resolve_shadow(srays); vol_groups.push_back(vrays);
