@@ -106,8 +106,7 @@ def cpu_run(args, steps, warmup, threads=None):
     ob = ge.oracle_bindings()
     lib = ob.lib
     lib.lo_num_threads.restype = ctypes.c_int
-    if threads:
-        lib.lo_set_num_threads(int(threads))
+    lib.lo_set_num_threads(int(threads or os.cpu_count() or 1))       # torchrun exports OMP_NUM_THREADS=1: ask for all host threads explicitly
     cores = int(lib.lo_num_threads())
     scene = workload_scene(args)
     r = api.Renderer(ob, settings(args, SAMPLE_W, SAMPLE_H))
