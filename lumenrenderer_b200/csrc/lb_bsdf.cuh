@@ -247,57 +247,158 @@ LB_D void lobe_weights(const Shading& s, float w[4]) {
 }
 
 // ---------------------------------------------------------------- EvaluateBSDF (disney.cuh:320-405)
+// The reference evaluates the whole BSDF from scratch per (surface, light direction) pair. RIS evaluates 32 light
+// directions and spatial reuse up to 5 against ONE surface, so everything that depends only on the surface and the
+// outgoing direction is computed once here (tangent frame, local outgoing direction, lobe weights, microfacet alphas,
+// the outgoing-side Lambda / G1 / Schlick terms, the GTR1 normalisation with its logf). Every hoisted value is the
+// same expression the per-call code evaluated, so results are bit-identical to the un-hoisted form.
+struct BsdfCtx {
+    Shading s;
+    float3 N, T, B, wow, wol;
+    float w[4];
+    float ax, ay;                       // GGX alphas (microfacet_alpha_from_roughness)
+    float3 spec_v, sheen_v;             // view-independent parts of the specular / sheen Fresnel colour
+    float lam_wo_ggx, g1_wo_ggx;        // Lambda(wol), G1(wol) of the specular lobe
+    float coat_a2, coat_norm, coat_log_a2, lam_wo_gtr;   // GTR1 clear-coat: alpha^2, (a2-1)/(pi log a2), log a2, Lambda(wol)
+    float cos_on, fv;                   // diffuse lobe: N.wo and its Schlick weight
+
+    LB_D BsdfCtx(const Material& mat, const float3& iN, const float3& iT, const float3& wow_) : s(mat) {
+        N = iN; wow = wow_;
+        B = normalize(cross(iN, iT)); T = normalize(cross(iN, B));
+        wol = to_local(wow, iN, T, B);
+        mf_alpha(s.roughness, s.anisotropic, ax, ay);
+        lobe_weights(s, w);
+        spec_v = (1.0f - s.spectint) + s.spectint * s.tint;
+        spec_v *= s.specular * 0.08f;
+        spec_v = (1.0f - s.metallic) * spec_v + s.metallic * s.color;
+        sheen_v = (1.0f - s.sheentint) + s.sheentint * s.tint;
+        lam_wo_ggx = ggx_Lambda(wol, ax, ay);
+        g1_wo_ggx = 1.0f / (1.0f + lam_wo_ggx);
+        const float ca = coat_alpha(s);
+        coat_a2 = sq(gtr1_clamp(ca));
+        coat_log_a2 = logf(coat_a2);
+        coat_norm = (coat_a2 - 1.0f) / (kPi * coat_log_a2);
+        lam_wo_gtr = (w[3] > 0) ? gtr1_Lambda(wol, ca) : 0.f;
+        cos_on = dot(iN, wow);
+        fv = schlick_w(cos_on);
+    }
+
+    LB_D float3 fresnel_spec_at(const float3& h) const {
+        const float f = schlick_w(fabsf(dot(wol, h)));
+        return (1.0f - f) * spec_v + f;
+    }
+    LB_D float ggx_pdf_wo(const float3& m) const {               // ggx_pdf(wol, m)
+        if (wol.z == 0.0f) return 0;
+        return g1_wo_ggx * fabsf(dot(wol, m)) * ggx_D(m, ax, ay) / fabsf(wol.z);
+    }
+    LB_D float gtr1_D_m(const float3& m) const { return coat_norm * (1 / (1 + (coat_a2 - 1) * sq(m.z))); }
+    LB_D float gtr1_Lambda_wi(const float3& v) const {
+        if (v.z == 0) return 0;
+        const float c2 = sq(v.z);
+        const float sn = sqrtf(fmaxf(0.0f, 1.0f - c2));
+        if (sn == 0) return 0;
+        const float cot2 = c2 / sq(sn);
+        const float cot = sqrtf(cot2);
+        const float a = sqrtf(cot2 + coat_a2);
+        const float b = sqrtf(cot2 + 1.0f);
+        const float c = logf(cot + b);
+        const float d = logf(cot + a);
+        return (a - b + cot * (c - d)) / (cot * coat_log_a2);
+    }
+    // lobe_eval<true> (GGX specular) and lobe_eval<false> (GTR1 clear coat) against the hoisted outgoing side
+    LB_D float spec_eval(const float3& wil, const float3& m, float3& bsdf) const {
+        if (wol.z == 0 || wil.z == 0) return 0;
+        const float cos_oh = dot(wol, m);
+        if (cos_oh == 0) return 0;
+        const float D = ggx_D(m, ax, ay), G = 1.0f / (1.0f + lam_wo_ggx + ggx_Lambda(wil, ax, ay));
+        bsdf = fresnel_spec_at(m);
+        bsdf *= D * G / fabsf(4.0f * wol.z * wil.z);
+        return ggx_pdf_wo(m) / fabsf(4.0f * cos_oh);
+    }
+    LB_D float coat_eval(const float3& wil, const float3& m, float3& bsdf) const {
+        if (wol.z == 0 || wil.z == 0) return 0;
+        const float cos_oh = dot(wol, m);
+        if (cos_oh == 0) return 0;
+        const float D = gtr1_D_m(m), G = 1.0f / (1.0f + lam_wo_gtr + gtr1_Lambda_wi(wil));
+        bsdf = f3(mixf(0.04f, 1.0f, schlick_w(fabsf(dot(wol, m)))) * 0.25f * s.clearcoat);
+        bsdf *= D * G / fabsf(4.0f * wol.z * wil.z);
+        return (D * fabsf(m.z)) / fabsf(4.0f * cos_oh);
+    }
+    LB_D float diffuse_eval(const float3& wi, const float3& m, float3& value) const {
+        const float cos_in = dot(N, wi), cos_ih = dot(wi, m);
+        const float fl = schlick_w(cos_in);
+        float fd = 0;
+        if (s.subsurface != 1.0f) {
+            const float fd90 = 0.5f + 2.0f * sq(cos_ih) * s.roughness;
+            fd = mixf(1.f, fd90, fl) * mixf(1.f, fd90, fv);
+        }
+        if (s.subsurface > 0) {
+            const float fss90 = sq(cos_ih) * s.roughness;
+            const float fss = mixf(1.0f, fss90, fl) * mixf(1.0f, fss90, fv);
+            const float ss = 1.25f * (fss * (1.0f / (fabsf(cos_on) + fabsf(cos_in)) - 0.5f) + 0.5f);
+            fd = mixf(fd, ss, s.subsurface);
+        }
+        value = s.color * fd * kInvPi * (1.0f - s.metallic);
+        return fabsf(cos_in) * kInvPi;
+    }
+    LB_D float sheen_eval(const float3& wi, const float3& m, float3& value) const {
+        const float fh = schlick_w(dot(wi, m));
+        value = sheen_v;
+        value *= fh * s.sheen * (1.0f - s.metallic);
+        return 1.0f / (2 * kPi);
+    }
+
+    LB_D float3 eval(const float3& wiw, float& pdf) const {
+        float3 trans_bsdf = f3(0.f); float trans_pdf = 0.f;
+        if (s.transmission > 0.f) {
+            const float3 wil = to_local(wiw, N, T, B);
+            const float eta = wol.z > 0 ? s.ior : (1.0f / s.ior);
+            if (eta == 1) { pdf = 0; return f3(0.f); }
+            float jac;
+            float3 m;
+            if (wil.z * wol.z >= 0) {
+                m = half_reflect(wol, wil);
+                const float cos_wom = dot(wol, m); float ct;
+                const float F = fresnel_dielectric(cos_wom, 1 / eta, ct);
+                eval_reflection(s.color, wol, wil, m, ax, ay, F, trans_bsdf);
+                trans_pdf = pick_reflection(1, 1, F); jac = jacobian_reflection(cos_wom);
+            } else {
+                m = half_refract(wol, wil, eta);
+                const float cos_wom = dot(wol, m); float ct;
+                const float F = fresnel_dielectric(cos_wom, 1 / eta, ct);
+                eval_refraction(eta, s.color, wol, wil, m, ax, ay, 1 - F, trans_bsdf);
+                trans_pdf = 1 - pick_reflection(1, 1, F); jac = jacobian_refraction(wol, wil, m, eta);
+            }
+            trans_pdf *= jac * ggx_pdf_wo(m);
+        }
+        if (s.roughness <= 0.001f) { pdf = trans_pdf; return trans_bsdf; }
+        pdf = 0; float3 value = f3(0.f);
+        if (w[0] + w[1] > 0) {
+            const float3 m = normalize(wiw + wow);
+            if (w[0] > 0) pdf += w[0] * diffuse_eval(wiw, m, value);
+            if (w[1] > 0) pdf += w[1] * sheen_eval(wiw, m, value);   // replaces the diffuse value, as the reference does (disney.cuh:377)
+        }
+        if (w[2] + w[3] > 0) {
+            const float3 wil = to_local(wiw, N, T, B);
+            const float3 m = normalize(wol + wil);
+            if (w[2] > 0) {
+                float3 c = f3(0.f); const float p = spec_eval(wil, m, c);
+                if (p > 0) { pdf += w[2] * p; value += c; }
+            }
+            if (w[3] > 0) {
+                float3 c = f3(0.f); const float p = coat_eval(wil, m, c);
+                if (p > 0) { pdf += w[3] * p; value += c; }
+            }
+        }
+        pdf = (pdf * (1.f - s.transmission));
+        pdf += (trans_pdf * s.transmission);
+        return (trans_bsdf * s.transmission) + (value * (1.f - s.transmission));
+    }
+};
+
 LB_D float3 bsdf_eval(const Material& mat, const float3& iN, const float3& iT, const float3& wow, const float3& wiw, float& pdf) {
-    const Shading s(mat);
-    float3 trans_bsdf = f3(0.f); float trans_pdf = 0.f;
-    if (s.transmission > 0.f) {
-        const float3 B = normalize(cross(iN, iT)), T = normalize(cross(iN, B));
-        const float3 wol = to_local(wow, iN, T, B), wil = to_local(wiw, iN, T, B);
-        const float eta = wol.z > 0 ? s.ior : (1.0f / s.ior);
-        if (eta == 1) { pdf = 0; return f3(0.f); }
-        float ax, ay, jac; mf_alpha(s.roughness, s.anisotropic, ax, ay);
-        float3 m;
-        if (wil.z * wol.z >= 0) {
-            m = half_reflect(wol, wil);
-            const float cos_wom = dot(wol, m); float ct;
-            const float F = fresnel_dielectric(cos_wom, 1 / eta, ct);
-            eval_reflection(s.color, wol, wil, m, ax, ay, F, trans_bsdf);
-            trans_pdf = pick_reflection(1, 1, F); jac = jacobian_reflection(cos_wom);
-        } else {
-            m = half_refract(wol, wil, eta);
-            const float cos_wom = dot(wol, m); float ct;
-            const float F = fresnel_dielectric(cos_wom, 1 / eta, ct);
-            eval_refraction(eta, s.color, wol, wil, m, ax, ay, 1 - F, trans_bsdf);
-            trans_pdf = 1 - pick_reflection(1, 1, F); jac = jacobian_refraction(wol, wil, m, eta);
-        }
-        trans_pdf *= jac * ggx_pdf(wol, m, ax, ay);
-    }
-    if (s.roughness <= 0.001f) { pdf = trans_pdf; return trans_bsdf; }
-    const float3 B = normalize(cross(iN, iT)), T = normalize(cross(iN, B));
-    float w[4]; lobe_weights(s, w);
-    pdf = 0; float3 value = f3(0.f);
-    if (w[0] + w[1] > 0) {
-        const float3 m = normalize(wiw + wow);
-        if (w[0] > 0) pdf += w[0] * diffuse_lobe(s, iN, wow, wiw, m, value);
-        if (w[1] > 0) pdf += w[1] * sheen_lobe(s, wiw, m, value);   // replaces the diffuse value, as the reference does (disney.cuh:377)
-    }
-    if (w[2] + w[3] > 0) {
-        const float3 wol = to_local(wow, iN, T, B), wil = to_local(wiw, iN, T, B);
-        const float3 m = normalize(wol + wil);
-        if (w[2] > 0) {
-            float ax, ay; mf_alpha(s.roughness, s.anisotropic, ax, ay);
-            float3 c = f3(0.f); const float p = lobe_eval<true>(s, ax, ay, wol, wil, m, c);
-            if (p > 0) { pdf += w[2] * p; value += c; }
-        }
-        if (w[3] > 0) {
-            const float a = coat_alpha(s);
-            float3 c = f3(0.f); const float p = lobe_eval<false>(s, a, a, wol, wil, m, c);
-            if (p > 0) { pdf += w[3] * p; value += c; }
-        }
-    }
-    pdf = (pdf * (1.f - s.transmission));
-    pdf += (trans_pdf * s.transmission);
-    return (trans_bsdf * s.transmission) + (value * (1.f - s.transmission));
+    const BsdfCtx c(mat, iN, iT, wow);
+    return c.eval(wiw, pdf);
 }
 
 // ---------------------------------------------------------------- SampleBSDF (disney.cuh:173-304)

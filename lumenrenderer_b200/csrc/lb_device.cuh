@@ -136,8 +136,10 @@ struct SceneView {
 
 // ---------------------------------------------------------------- per-pixel SoA planes (each plane: float4[npix])
 // Surface (SurfaceData.h:49-104, 176 B AoS in the reference) as 9 coalesced 16-B planes:
-//  0 position.xyz, t        1 normal.xyz, flags(bits)   2 tangent.xyz, -      3 incoming.xyz, -   4 transport.xyz, -
-//  5 color.rgba             6 transmittance.xyz, eta    7 tint.xyz, luminance 8 params (uint4 bits)
+//  0 position.xyz, flags(bits)   1 normal.xyz, t (sign bit set <=> flags != 0)   2 tangent.xyz, -   3 incoming.xyz, -
+//  4 transport.xyz, -            5 color.rgba   6 transmittance.xyz, eta   7 tint.xyz, luminance   8 params (uint4 bits)
+// Plane 1 alone answers the similarity test of temporal / spatial reuse (normal, depth, "is a plain surface"): a neighbour
+// probe is ONE 16-byte gather. t is never negative (0 on a miss), so its sign bit is free to carry "flagged".
 constexpr int kSurfPlanes = 9;
 // Reservoir (ReSTIRData.h:107-183, 80 B AoS) as 5 planes:
 //  0 weightSum, weight, sampleCount(int bits), sample.pdf   1 position.xyz, area   2 normal.xyz, -   3 radiance.xyz, -
@@ -151,8 +153,8 @@ struct LightSample { float3 radiance, normal, position, contribution; float area
 struct Reservoir { float weight_sum, weight; int count; LightSample s; };
 
 LB_D void surface_store(float4* planes, size_t n, size_t i, const Surface& s) {
-    planes[0 * n + i] = f4(s.pos, s.t);
-    planes[1 * n + i] = f4(s.normal, __uint_as_float(s.flags));
+    planes[0 * n + i] = f4(s.pos, __uint_as_float(s.flags));
+    planes[1 * n + i] = f4(s.normal, s.flags ? __uint_as_float(__float_as_uint(s.t) | 0x80000000u) : s.t);
     planes[2 * n + i] = f4(s.tangent, 0.f);
     planes[3 * n + i] = f4(s.incoming, 0.f);
     planes[4 * n + i] = f4(s.transport, 0.f);
@@ -161,19 +163,28 @@ LB_D void surface_store(float4* planes, size_t n, size_t i, const Surface& s) {
     planes[7 * n + i] = s.mat.tint;
     planes[8 * n + i] = make_float4(__uint_as_float(s.mat.params.x), __uint_as_float(s.mat.params.y), __uint_as_float(s.mat.params.z), __uint_as_float(s.mat.params.w));
 }
-LB_D uint32_t surface_flags(const float4* planes, size_t n, size_t i) { return __float_as_uint(planes[1 * n + i].w); }
-// geometry part only (position/t/normal/flags): what the similarity tests of temporal/spatial reuse read
-LB_D void surface_load_geom(const float4* planes, size_t n, size_t i, Surface& s) {
-    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
-    s.pos = f3(a); s.t = a.w; s.normal = f3(b); s.flags = __float_as_uint(b.w);
+LB_D uint32_t surface_flags(const float4* planes, size_t n, size_t i) { return __float_as_uint(planes[0 * n + i].w); }
+// the similarity record of a pixel: normal, depth, flagged — one 16-byte load
+struct SurfGeom { float3 normal; float t; bool flagged; };
+LB_D SurfGeom surf_geom_unpack(const float4& b) {
+    SurfGeom g; g.normal = f3(b); g.flagged = (__float_as_uint(b.w) >> 31) != 0u; g.t = fabsf(b.w);
+    return g;
 }
-LB_D void surface_load(const float4* planes, size_t n, size_t i, Surface& s) {
-    surface_load_geom(planes, n, i, s);
-    s.tangent = f3(planes[2 * n + i]); s.incoming = f3(planes[3 * n + i]); s.transport = f3(planes[4 * n + i]);
+LB_D SurfGeom surface_geom(const float4* planes, size_t n, size_t i) { return surf_geom_unpack(planes[1 * n + i]); }
+// everything a BSDF evaluation at the pixel needs (no path throughput)
+LB_D void surface_load_shading(const float4* planes, size_t n, size_t i, Surface& s) {
+    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
+    s.pos = f3(a); s.flags = __float_as_uint(a.w); s.normal = f3(b); s.t = fabsf(b.w);
+    s.tangent = f3(planes[2 * n + i]); s.incoming = f3(planes[3 * n + i]);
     s.mat.color = planes[5 * n + i]; s.mat.transmittance = planes[6 * n + i]; s.mat.tint = planes[7 * n + i];
     const float4 p = planes[8 * n + i];
     s.mat.params = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.w));
     s.mat.emissive = make_float4(0.f, 0.f, 0.f, 0.f);
+    s.transport = f3(0.f);
+}
+LB_D void surface_load(const float4* planes, size_t n, size_t i, Surface& s) {
+    surface_load_shading(planes, n, i, s);
+    s.transport = f3(planes[4 * n + i]);
 }
 LB_D void reservoir_store(float4* planes, size_t n, size_t i, const Reservoir& r) {
     planes[0 * n + i] = make_float4(r.weight_sum, r.weight, __int_as_float(r.count), r.s.pdf);

@@ -40,18 +40,47 @@ LB_D bool similar(float d1, float d2, const float3& n1, const float3& n2) {
 }
 // CombineBiased over two reservoirs
 LB_D Reservoir combine_pair(const Reservoir& a, const Reservoir& b, const Surface& px, uint32_t seed) {
+    const BsdfCtx ctx = surface_ctx(px);
     Reservoir out = reservoir_zero(); int total = 0;
-    {
-        LightSample rs; resample(a.s, px, rs);
-        reservoir_update(out, rs, (float)a.count * a.weight * rs.pdf, seed); total += a.count;
-    }
-    {
-        LightSample rs; resample(b.s, px, rs);
-        reservoir_update(out, rs, (float)b.count * b.weight * rs.pdf, seed); total += b.count;
+#pragma unroll 1                                   // ONE inlined BSDF evaluation: the instruction footprint, not the trip count, is what costs here
+    for (int k = 0; k < 2; ++k) {
+        const Reservoir& q = k ? b : a;
+        LightSample rs; resample(q.s, px.pos, px.normal, ctx, rs);
+        reservoir_update(out, rs, (float)q.count * q.weight * rs.pdf, seed); total += q.count;
     }
     out.count = total; reservoir_update_weight(out);
     return out;
 }
+
+// Pixel order of the gather kernels (temporal / spatial reuse): 32x8-pixel tiles, one per block iteration, handed out by a
+// device ticket (so the tiles in flight are always consecutive, whatever the grid / occupancy) and walked in vertical strips
+// 16 tiles (512 px) wide. The blocks in flight then cover a compact 2-D region whose +-30-pixel neighbour
+// halo is mostly shared, instead of ~60 full image rows — the gathers stay in L2. A warp is one 32-pixel row segment, so
+// the pixel's own loads and stores are still 512-byte coalesced.
+constexpr uint32_t kTileW = 32, kTileH = 8, kStripTiles = 16;
+struct TileWalk {
+    uint32_t tiles_x, tiles_y, ntiles, full;
+    LB_D explicit TileWalk(const FrameView& fv) {
+        tiles_x = (fv.width + kTileW - 1u) / kTileW; tiles_y = (fv.height + kTileH - 1u) / kTileH;
+        ntiles = tiles_x * tiles_y; full = kStripTiles * tiles_y;
+    }
+    // pixel of this thread in tile t; false when it falls outside the image
+    LB_D bool pixel(const FrameView& fv, uint32_t t, int& x, int& y) const {
+        const uint32_t strip = t / full, r = t - strip * full;
+        const uint32_t sw = min(kStripTiles, tiles_x - strip * kStripTiles);
+        const uint32_t ty = r / sw, tx = strip * kStripTiles + (r - ty * sw);
+        x = (int)(tx * kTileW + (threadIdx.x & 31u)); y = (int)(ty * kTileH + (threadIdx.x >> 5));
+        return (uint32_t)x < fv.width && (uint32_t)y < fv.height;
+    }
+    // next tile of this block (block-uniform); >= ntiles when the image is exhausted
+    LB_D uint32_t next(uint32_t* ticket) const {
+        __shared__ uint32_t s_tile;
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        return s_tile;
+    }
+};
 
 __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __restrict__ bags, uint32_t a_seed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,29 +91,84 @@ __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __res
     bags[i] = make_uint2(li, __float_as_uint(pdf));
 }
 
-__global__ void __launch_bounds__(kBlock) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t seed) {
-    const uint32_t stride = gridDim.x * blockDim.x;
+// RIS over 32 bag candidates (the most expensive kernel of the reference's frame: 32 full BSDF evaluations per pixel).
+//  * The pixel's BSDF context is built once (BsdfCtx).
+//  * Phase A walks the 32 candidates with the whole warp converged and only decides which of them pass the geometric test
+//    (light above the pixel's horizon and facing it). A candidate that fails contributes weight +0: it changes nothing but
+//    the reservoir's sample count, so it needs no ordering and is accounted for by a popcount.
+//  * Phase B evaluates the survivors in candidate order, one per lane per round: the lanes re-align on the expensive BSDF
+//    evaluation, which the warp executes max-over-lanes(survivors) times instead of 32. The xorshift stream is replayed up
+//    to the candidate, so every random number is the one the sequential loop of the reference would have drawn.
+struct BagCandidate { LightSample ls; float bag_pdf; };
+LB_D BagCandidate draw_candidate(const SceneView& sc, const uint2* __restrict__ picked, uint32_t& s) {
+    BagCandidate c;
+    const float r = rand_f(s);
+    const uint2 be = __ldg(&picked[(int)roundf((float)(kLightsPerBag - 1u) * r)]);
+    const DevLight l = load_light(sc, be.x);
+    const float u = rand_f(s), v = rand_f(s) * (1.f - u);
+    c.ls.radiance = l.radiance; c.ls.normal = l.normal; c.ls.area = l.area; c.ls.contribution = f3(0.f); c.ls.pdf = 0.f;
+    c.ls.position = l.p0 + ((l.p1 - l.p0) * u) + ((l.p2 - l.p0) * v);
+    c.bag_pdf = __uint_as_float(be.y);
+    return c;
+}
+
+__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t seed) {
+    static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
+    const uint32_t stride = gridDim.x * blockDim.x;            // a multiple of 32: the pixel loop is warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
     const size_t np = fv.npix;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
-        if (surface_flags(fv.surf_cur, np, i)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); continue; }
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < fv.npix; base += stride) {
+        const uint32_t i = base + lane;
+        bool valid = i < fv.npix;
+        Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
+        px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
+        if (valid && surface_flags(fv.surf_cur, np, i)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); valid = false; }
+        if (valid) surface_load_shading(fv.surf_cur, np, i, px);
         uint32_t bag_seed = wang_hash(seed + i / 256u);
         const int bag = (int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
         const uint2* picked = bags + (size_t)bag * kLightsPerBag;
-        Surface px; surface_load(fv.surf_cur, np, i, px);
-        uint32_t s = wang_hash(seed + wang_hash(i));
+        const uint32_t s0 = wang_hash(seed + wang_hash(i));
         Reservoir fresh = reservoir_zero();
-        for (uint32_t k = 0; k < kPrimarySamples; ++k) {
-            const float r = rand_f(s);
-            const uint2 be = __ldg(&picked[(int)roundf((float)(kLightsPerBag - 1u) * r)]);
-            const DevLight l = load_light(sc, be.x);
-            const float u = rand_f(s), v = rand_f(s) * (1.f - u);
-            LightSample ls; ls.radiance = l.radiance; ls.normal = l.normal; ls.area = l.area; ls.contribution = f3(0.f); ls.pdf = 0.f;
-            ls.position = l.p0 + ((l.p1 - l.p0) * u) + ((l.p2 - l.p0) * v);
-            LightSample rs; resample(ls, px, rs);
-            reservoir_update(fresh, rs, rs.pdf / __uint_as_float(be.y), s);
+
+        // ---- phase A: which candidates need the ordered path
+        uint32_t mask = 0u;
+        if (valid) {
+            uint32_t sa = s0;
+#pragma unroll 2
+            for (uint32_t k = 0; k < kPrimarySamples; ++k) {
+                const BagCandidate c = draw_candidate(sc, picked, sa);
+                ResampleGeom g;
+                const bool have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
+                // ordered unless the update is provably a pure count increment: weight exactly 0 and a non-zero acceptance draw
+                const bool ordered = have || !(0.f / c.bag_pdf == 0.f) || sa == 0u;
+                mask |= (ordered ? 1u : 0u) << k;
+            }
+            fresh.count = (int)kPrimarySamples - __popc(mask);
         }
-        reservoir_update_weight(fresh);
-        reservoir_store(fv.res_cur, np, i, fresh);
+
+        // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation
+        const BsdfCtx ctx = surface_ctx(px);
+        uint32_t sb = s0, kb = 0u;
+        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+            const bool active = mask != 0u;
+            BagCandidate c; ResampleGeom g; bool have = false;
+            c.ls.radiance = f3(0.f); c.ls.normal = f3(0.f); c.ls.position = f3(0.f); c.ls.contribution = f3(0.f); c.ls.area = 0.f; c.ls.pdf = 0.f; c.bag_pdf = 1.f;
+            g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
+            if (active) {
+                const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
+                for (; kb < k; ++kb) { rand_u32(sb); rand_u32(sb); rand_u32(sb); }      // replay the draws of the skipped candidates
+                c = draw_candidate(sc, picked, sb); ++kb;
+                have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
+            }
+            __syncwarp();
+            if (have) resample_shade(ctx, g, c.ls);
+            if (active) reservoir_update(fresh, c.ls, (have ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
+            __syncwarp();
+        }
+        if (valid) {
+            reservoir_update_weight(fresh);
+            reservoir_store(fv.res_cur, np, i, fresh);
+        }
     }
 }
 
@@ -103,9 +187,8 @@ __global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhVi
         if (i < n) {
             float4 r0 = fv.res_cur[i];                         // weightSum, weight, count, pdf
             float weight = r0.y;
-            const float4 sp = fv.surf_cur[i];
-            const uint32_t flags = surface_flags(fv.surf_cur, np, i);
-            if (!flags && weight > 0.f) {
+            const float4 sp = fv.surf_cur[i];                  // position, flags
+            if (!__float_as_uint(sp.w) && weight > 0.f) {
                 const float3 pos = f3(sp);
                 float3 d = f3(fv.res_cur[np + i]) - pos; const float l = length(d); d /= l;
                 ++traced;
@@ -123,21 +206,24 @@ __global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhVi
     if (lane == 0 && traced) atomicAdd(stat, (unsigned long long)traced);
 }
 
-__global__ void __launch_bounds__(kBlock) k_temporal(FrameView fv, uint32_t seed, float shaded) {
-    const uint32_t stride = gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(kBlock, 2) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
-        const int cy = (int)(i / fv.width), cx = (int)(i - (uint32_t)cy * fv.width);
+    const TileWalk tw(fv);
+    for (uint32_t tile = tw.next(ticket); tile < tw.ntiles; tile = tw.next(ticket)) {
+        int cx, cy;
+        if (!tw.pixel(fv, tile, cx, cy)) continue;
+        const uint32_t i = (uint32_t)cy * fv.width + (uint32_t)cx;
         const float2 mvec = fv.motion[i];
         const int mx = (int)roundf((float)W * mvec.x), my = (int)roundf((float)H * mvec.y);
         const int ty = cy + my, tx = cx + mx; uint32_t ti = i;
         if (ty >= 0 && ty < H && tx >= 0 && tx < W) ti = (uint32_t)ty * fv.width + (uint32_t)tx;
-        Surface sp; surface_load_geom(fv.surf_prev, np, ti, sp);
-        if (sp.flags) continue;
-        if (surface_flags(fv.surf_cur, np, i)) continue;
-        Surface sc; surface_load(fv.surf_cur, np, i, sc);
-        if (!similar(sp.t, sc.t, sp.normal, sc.normal)) continue;
+        const SurfGeom gp = surface_geom(fv.surf_prev, np, ti);
+        if (gp.flagged) continue;
+        const SurfGeom gc = surface_geom(fv.surf_cur, np, i);
+        if (gc.flagged) continue;
+        if (!similar(gp.t, gc.t, gp.normal, gc.normal)) continue;
+        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
         Reservoir prev, cur; reservoir_load(fv.res_prev, np, ti, prev); reservoir_load(fv.res_cur, np, i, cur);
         if (prev.weight > 0.f) {
             const float3 c = prev.s.contribution * (prev.weight / shaded);
@@ -148,34 +234,60 @@ __global__ void __launch_bounds__(kBlock) k_temporal(FrameView fv, uint32_t seed
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_spatial(FrameView fv, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
-    const uint32_t stride = gridDim.x * blockDim.x;
+// what spatial reuse reads of a neighbour's reservoir: 4 of its 5 planes (the stored contribution is re-evaluated)
+struct ResProbe { float4 a, b, c, d; };
+LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i) {
+    ResProbe p; p.a = planes[i]; p.b = planes[n + i]; p.c = planes[2 * n + i]; p.d = planes[3 * n + i];
+    return p;
+}
+
+__global__ void __launch_bounds__(kBlock, 2) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
-        Surface sc; surface_load_geom(fv.surf_cur, np, i, sc);
-        if (sc.flags) continue;
+    const TileWalk tw(fv);
+    const float4* __restrict__ geom = fv.surf_cur + np;          // plane 1: normal, signed depth
+    const bool degenerate = seed == 0u;
+    for (uint32_t tile = tw.next(ticket); tile < tw.ntiles; tile = tw.next(ticket)) {
+        int x, y;
+        if (!tw.pixel(fv, tile, x, y)) continue;
+        const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
+        const SurfGeom gc = surf_geom_unpack(geom[i]);
+        if (gc.flagged) continue;
         uint32_t s = wang_hash(seed + i);
-        const int y = (int)(i / fv.width), x = (int)(i - (uint32_t)y * fv.width);
-        uint32_t nb[kSpatialSamples]; int count = 0;
+        // all five neighbour probes are issued before any is tested (5 independent 16-byte gathers in flight)
+        uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
 #pragma unroll
         for (uint32_t k = 0; k < kSpatialSamples; ++k) {
             const int ny = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + y;
             const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
-            if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
-            const uint32_t ni = (uint32_t)ny * fv.width + (uint32_t)nx;
-            Surface sn; surface_load_geom(fv.surf_cur, np, ni, sn);
-            if (sn.flags) continue;
-            if (similar(sn.t, sc.t, sn.normal, sc.normal)) nb[count++] = ni;
+            inside[k] = !(nx < 0 || nx >= W || ny < 0 || ny >= H);
+            ni[k] = inside[k] ? (uint32_t)ny * fv.width + (uint32_t)nx : i;
+            ng[k] = geom[ni[k]];
+        }
+        uint32_t nb[kSpatialSamples]; int count = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kSpatialSamples; ++k) {
+            const SurfGeom gn = surf_geom_unpack(ng[k]);
+            if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) nb[count++] = ni[k];
         }
         if (count > 1) {
-            Surface p0; surface_load(fv.surf_cur, np, nb[0], p0);      // resampled at the FIRST accepted neighbour
+            ResProbe cur = res_probe(in, np, nb[0]);
+            Surface p0; surface_load_shading(fv.surf_cur, np, nb[0], p0);      // resampled at the FIRST accepted neighbour
+            const BsdfCtx ctx = surface_ctx(p0);
             Reservoir acc = reservoir_zero(); int total = 0;
+#pragma unroll 1
             for (int k = 0; k < count; ++k) {
-                Reservoir q; reservoir_load(in, np, nb[k], q);
-                LightSample rs; resample(q.s, p0, rs);
-                reservoir_update(acc, rs, (float)q.count * q.weight * rs.pdf, seed);   // kernel-wide seed by value (hazard 14)
-                total += q.count;
+                ResProbe nxt = cur;
+                if (k + 1 < count) nxt = res_probe(in, np, nb[k + 1]);          // next neighbour's reservoir is in flight during this evaluation
+                LightSample q; q.position = f3(cur.b); q.area = cur.b.w; q.normal = f3(cur.c); q.radiance = f3(cur.d); q.pdf = cur.a.w;
+                // a geometrically rejected sample keeps its stored contribution, but it can only be selected when the acceptance draw is
+                // exactly 0, i.e. for the all-zero xorshift state: only then is plane 4 fetched
+                q.contribution = degenerate ? f3(in[4 * np + nb[k]]) : f3(0.f);
+                const int qcount = __float_as_int(cur.a.z); const float qweight = cur.a.y;
+                LightSample rs; resample(q, p0.pos, p0.normal, ctx, rs);
+                reservoir_update(acc, rs, (float)qcount * qweight * rs.pdf, seed);   // kernel-wide seed by value (hazard 14)
+                total += qcount;
+                cur = nxt;
             }
             acc.count = total; reservoir_update_weight(acc);
             reservoir_store(out, np, i, acc);
@@ -186,12 +298,12 @@ __global__ void __launch_bounds__(kBlock) k_spatial(FrameView fv, const float4* 
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_combine(FrameView fv, const float4* __restrict__ nbuf, uint32_t cseed) {
+__global__ void __launch_bounds__(kBlock, 2) k_combine(FrameView fv, const float4* __restrict__ nbuf, uint32_t cseed) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const size_t np = fv.npix;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
         if (surface_flags(fv.surf_cur, np, i)) continue;
-        Surface sc; surface_load(fv.surf_cur, np, i, sc);
+        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
         Reservoir a, b; reservoir_load(fv.res_cur, np, i, a); reservoir_load(nbuf, np, i, b);
         reservoir_store(fv.res_cur, np, i, combine_pair(a, b, sc, wang_hash(cseed + i)));
     }
@@ -211,13 +323,13 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS]); LB_LAUNCH_CHECK();
     if (a.temporal) {
         seed = wang_hash(seed);
-        k_temporal<<<grid, kBlock, 0, st>>>(fv, seed, shaded); LB_LAUNCH_CHECK();
+        k_temporal<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
     }
     if (a.spatial) {
         seed = wang_hash(seed);
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-            k_spatial<<<grid, kBlock, 0, st>>>(fv, from, to, seed); LB_LAUNCH_CHECK();
+            k_spatial<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
         k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS]); LB_LAUNCH_CHECK();

@@ -154,18 +154,31 @@ LB_D bool bounce_sample(const Surface& s, uint32_t pixel_index, uint32_t seed_in
     return true;
 }
 
-// Resample (ReSTIRKernels.cu:1259-1325): re-evaluate a light sample's unshadowed contribution at a pixel
-LB_D void resample(const LightSample& in, const Surface& px, LightSample& out) {
-    out = in;
-    float3 dir = in.position - px.pos; const float dist = length(dir); dir /= dist;
-    const float cos_in = fmaxf(dot(dir, px.normal), 0.f), cos_out = fmaxf(dot(in.normal, -dir), 0.f);
-    if (cos_in <= 0 || cos_out <= 0 || dist <= 0.01f) { out.pdf = 0; return; }
-    const float solid = (cos_out * in.area) / (dist * dist);
-    float pdf = 0.f; const float3 bsdf = bsdf_eval(px.mat, px.normal, px.tangent, -px.incoming, dir, pdf);
+// Resample (ReSTIRKernels.cu:1259-1325): re-evaluate a light sample's unshadowed contribution at a pixel.
+// Split in two so that a caller evaluating many samples against one pixel (RIS: 32, spatial reuse: up to 5) builds the BSDF
+// context once, and so that the cheap geometric rejection can run ahead of the expensive BSDF evaluation (k_ris).
+struct ResampleGeom { float3 dir; float solid, cos_in; };
+// false = rejected (light below the horizon / facing away / too close): the sample's pdf becomes 0, nothing else changes
+LB_D bool resample_geom(const float3& lpos, const float3& lnormal, float larea, const float3& ppos, const float3& pnormal, ResampleGeom& g) {
+    float3 dir = lpos - ppos; const float dist = length(dir); dir /= dist;
+    const float cos_in = fmaxf(dot(dir, pnormal), 0.f), cos_out = fmaxf(dot(lnormal, -dir), 0.f);
+    if (cos_in <= 0 || cos_out <= 0 || dist <= 0.01f) return false;
+    g.dir = dir; g.cos_in = cos_in; g.solid = (cos_out * larea) / (dist * dist);
+    return true;
+}
+LB_D void resample_shade(const BsdfCtx& ctx, const ResampleGeom& g, LightSample& out) {
+    float pdf = 0.f; const float3 bsdf = ctx.eval(g.dir, pdf);
     const float added = pdf + bsdf.x + bsdf.y + bsdf.z;
     if (pdf <= kBsdfEps || isnan(added) || isinf(added)) { out.contribution = f3(0.f); out.pdf = 0; return; }
-    const float3 c = (bsdf / pdf) * solid * cos_in * out.radiance;
+    const float3 c = (bsdf / pdf) * g.solid * g.cos_in * out.radiance;
     out.contribution = c; out.pdf = (c.x + c.y + c.z) / 3.f;
 }
+LB_D void resample(const LightSample& in, const float3& ppos, const float3& pnormal, const BsdfCtx& ctx, LightSample& out) {
+    out = in;
+    ResampleGeom g;
+    if (!resample_geom(in.position, in.normal, in.area, ppos, pnormal, g)) { out.pdf = 0; return; }
+    resample_shade(ctx, g, out);
+}
+LB_D BsdfCtx surface_ctx(const Surface& px) { return BsdfCtx(px.mat, px.normal, px.tangent, -px.incoming); }
 
 } // namespace lb
