@@ -12,6 +12,7 @@
 // resolved per wave, fp32 channels. There is no CPU fallback anywhere in this file.
 #include "../../include/lumen_b200.h"
 #include "lb_kernels.h"
+#include <cstdlib>
 #include "lb_bsdf.cuh"
 #include <vector>
 #include <string>
@@ -87,7 +88,14 @@ struct Renderer {
     std::thread render_thread; std::atomic<bool> stop_flag{false}; std::string thread_error;
 
     uint32_t npix() const { return st.width * st.height; }
-    LaunchCfg cfg() const { LaunchCfg c; c.sms = sms; c.stream = stream; return c; }
+    // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
+    static TraceTuning trace_tuning() {
+        TraceTuning t;
+        if (const char* e = getenv("LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
+        if (const char* e = getenv("LB_TRACE_TRI_QUARTER")) t.tri_quarter = atoi(e);
+        return t;
+    }
+    LaunchCfg cfg() const { static const TraceTuning tune = trace_tuning(); LaunchCfg c; c.sms = sms; c.stream = stream; c.trace = tune; return c; }
 
     ~Renderer() {
         stop_thread();

@@ -112,6 +112,9 @@ struct DevLight { float3 p0, p1, p2, normal, radiance; float area; };
 //  q2: qlo_x[0..7] | qlo_y[0..7]      q3: qlo_z[0..7] | qhi_x[0..7]      q4: qhi_y[0..7] | qhi_z[0..7]
 struct Bvh8Node { uint4 q0, q1, q2, q3, q4; };
 
+// warp scheduling of trace_queue (lb_trace.cuh): refill when >= refill_min lanes are idle; triangle round when pending * tri_quarter >= live
+struct TraceTuning { int refill_min = 12; int tri_quarter = 4; };
+
 struct BvhView {
     const Bvh8Node* nodes;
     const DevTri* tris;

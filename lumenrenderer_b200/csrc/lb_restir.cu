@@ -173,37 +173,33 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 }
 
 // visibility of the reservoir's sample + shading of the survivor into DIRECT, one kernel
-__global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhView bvh, uint32_t* ticket, float inv_shaded_count_denominator, unsigned long long* stat) {
-    const uint32_t n = fv.npix;
-    const size_t np = fv.npix;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t traced = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            float4 r0 = fv.res_cur[i];                         // weightSum, weight, count, pdf
-            float weight = r0.y;
-            const float4 sp = fv.surf_cur[i];                  // position, flags
-            if (!__float_as_uint(sp.w) && weight > 0.f) {
-                const float3 pos = f3(sp);
-                float3 d = f3(fv.res_cur[np + i]) - pos; const float l = length(d); d /= l;
-                ++traced;
-                HitInfo h;
-                if (bvh8_trace<true>(bvh, pos, d, 0.1f, l - 0.05f, h)) { weight = 0.f; r0.y = 0.f; fv.res_cur[i] = r0; }
-            }
-            if (weight > 0.f) {
-                const float3 c = f3(fv.res_cur[4 * np + i]) * (weight / inv_shaded_count_denominator);
-                float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
-            }
-        }
-        __syncwarp();
+struct VisibilityJob {
+    FrameView fv; float shaded; uint32_t traced;
+    float4 r0;                                                  // lane state between load and done: weightSum, weight, count, pdf
+    LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) {
+        const size_t np = fv.npix;
+        r0 = fv.res_cur[i];
+        const float4 sp = fv.surf_cur[i];                       // position, flags
+        if (__float_as_uint(sp.w) || !(r0.y > 0.f)) return false;
+        o = f3(sp);
+        d = f3(fv.res_cur[np + i]) - o; const float l = length(d); d /= l;
+        t0 = 0.1f; t1 = l - 0.05f;
+        ++traced;
+        return true;
     }
-    traced = __reduce_add_sync(0xFFFFFFFFu, traced);
-    if (lane == 0 && traced) atomicAdd(stat, (unsigned long long)traced);
+    LB_D void done(uint32_t i, bool occluded, const Tracer&) {
+        if (occluded) { r0.y = 0.f; fv.res_cur[i] = r0; return; }
+        if (r0.y > 0.f) {
+            const float3 c = f3(fv.res_cur[4 * (size_t)fv.npix + i]) * (r0.y / shaded);
+            float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
+        }
+    }
+};
+__global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhView bvh, uint32_t* ticket, float inv_shaded_count_denominator, unsigned long long* stat, TraceTuning tune) {
+    VisibilityJob job{fv, inv_shaded_count_denominator, 0u, make_float4(0.f, 0.f, 0.f, 0.f)};
+    trace_queue<true>(bvh, fv.npix, ticket, job, tune);
+    const uint32_t traced = __reduce_add_sync(0xFFFFFFFFu, job.traced);
+    if ((threadIdx.x & 31u) == 0u && traced) atomicAdd(stat, (unsigned long long)traced);
 }
 
 __global__ void __launch_bounds__(kBlock, 2) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
@@ -320,7 +316,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     seed = wang_hash(seed);
     k_ris<<<grid, kBlock, 0, st>>>(fv, sc, rb.bags, seed); LB_LAUNCH_CHECK();
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
-    k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS]); LB_LAUNCH_CHECK();
+    k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
     if (a.temporal) {
         seed = wang_hash(seed);
         k_temporal<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
@@ -332,7 +328,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
             k_spatial<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
-        k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS]); LB_LAUNCH_CHECK();
+        k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
         k_combine<<<grid, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
     }
 }

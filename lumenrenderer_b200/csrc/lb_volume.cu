@@ -23,26 +23,20 @@ __global__ void __launch_bounds__(kBlock) k_volume_extend(const float4* __restri
 }
 
 // volumetric shadow rays of the compat march: several per pixel and launch -> atomic adds (all carry the same constant radiance)
-__global__ void __launch_bounds__(kBlock) k_vol_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket, float4* channels, size_t npix, float tmin, unsigned long long* stat) {
-    const uint32_t n = *count;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 o = q.o[i], d = q.d[i];
-            HitInfo h;
-            if (!bvh8_trace<true>(bvh, f3(o), f3(d), tmin, o.w, h)) {
-                const float4 L = q.L[i];
-                float* dst = reinterpret_cast<float*>(&channels[(size_t)__float_as_int(L.w) * npix + __float_as_uint(d.w)]);
-                atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z);
-            }
-        }
-        __syncwarp();
+struct VolShadowJob {
+    ShadowQueue q; float4* channels; size_t npix; float tmin;
+    LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { const float4 o4 = q.o[i]; o = f3(o4); d = f3(q.d[i]); t0 = tmin; t1 = o4.w; return true; }
+    LB_D void done(uint32_t i, bool occluded, const Tracer&) const {
+        if (occluded) return;
+        const float4 L = q.L[i];
+        float* dst = reinterpret_cast<float*>(&channels[(size_t)__float_as_int(L.w) * npix + __float_as_uint(q.d[i].w)]);
+        atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z);
     }
+};
+__global__ void __launch_bounds__(kBlock) k_vol_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket, float4* channels, size_t npix, float tmin, unsigned long long* stat, TraceTuning tune) {
+    const uint32_t n = *count;
+    VolShadowJob job{q, channels, npix, tmin};
+    trace_queue<true>(bvh, n, ticket, job, tune);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
@@ -104,7 +98,7 @@ void launch_volume_extend(const LaunchCfg& cfg, const FrameView& fv, int queue, 
         volumes, num_volumes, tmin, tmax, fv.vol_hits); LB_LAUNCH_CHECK();
 }
 void launch_volume_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
-    k_vol_shadow<<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(bvh, fv.vol_shadow, &fv.counters[CNT_VOL_SHADOW], &fv.counters[CNT_TICKET0 + ticket], fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW]); LB_LAUNCH_CHECK();
+    k_vol_shadow<<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(bvh, fv.vol_shadow, &fv.counters[CNT_VOL_SHADOW], &fv.counters[CNT_TICKET0 + ticket], fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace); LB_LAUNCH_CHECK();
 }
 void launch_volume_delta(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, int queue, bool primary, const ShadeArgs& a) {
     if (primary) k_volume_delta<true><<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(fv, sc, queue, a);

@@ -46,28 +46,24 @@ __global__ void __launch_bounds__(kBlock) k_raygen(FrameView fv, CameraBasis cam
     if (blockIdx.x == 0 && threadIdx.x == 0) { fv.counters[CNT_RAYS_A] = fv.npix; fv.counters[CNT_RAYS_B] = 0u; }
 }
 
-// ------------------------------------------------------------------ K2 extend: persistent warps fetch 32 rays at a time
-__global__ void __launch_bounds__(kBlock) k_extend(BvhView bvh, const float4* __restrict__ ro, const float4* __restrict__ rd, const uint32_t* __restrict__ count,
-                                                    uint32_t* ticket, uint4* __restrict__ hits, float tmin, float tmax, unsigned long long* stat) {
-    const uint32_t n = *count;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 o = ro[i], d = rd[i];
-            HitInfo h; uint4 rec = make_uint4(0u, 0u, 0u, __float_as_uint(-1.f));
-            if (bvh8_trace<false>(bvh, f3(o), f3(d), tmin, tmax, h)) {
-                const __half2 b = __floats2half2_rn(h.u, h.v);            // fp16 barycentrics, WaveFrontShaders.cu:318-321
-                rec = make_uint4(h.inst, h.prim, *reinterpret_cast<const uint32_t*>(&b), __float_as_uint(h.t));
-            }
-            hits[i] = rec;
+// ------------------------------------------------------------------ K2 extend: persistent warps, per-lane ray refill (trace_queue)
+struct ExtendJob {
+    const float4* __restrict__ ro; const float4* __restrict__ rd; uint4* __restrict__ hits; float tmin, tmax;
+    LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { o = f3(ro[i]); d = f3(rd[i]); t0 = tmin; t1 = tmax; return true; }
+    LB_D void done(uint32_t i, bool hit, const Tracer& tr) const {
+        uint4 rec = make_uint4(0u, 0u, 0u, __float_as_uint(-1.f));
+        if (hit) {
+            const __half2 b = __floats2half2_rn(tr.bu, tr.bv);            // fp16 barycentrics, WaveFrontShaders.cu:318-321
+            rec = make_uint4(tr.bi, tr.bp, *reinterpret_cast<const uint32_t*>(&b), __float_as_uint(tr.best));
         }
-        __syncwarp();
+        hits[i] = rec;
     }
+};
+__global__ void __launch_bounds__(kBlock) k_extend(BvhView bvh, const float4* __restrict__ ro, const float4* __restrict__ rd, const uint32_t* __restrict__ count,
+                                                    uint32_t* ticket, uint4* __restrict__ hits, float tmin, float tmax, unsigned long long* stat, TraceTuning tune) {
+    const uint32_t n = *count;
+    ExtendJob job{ro, rd, hits, tmin, tmax};
+    trace_queue<false>(bvh, n, ticket, job, tune);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
@@ -165,27 +161,21 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
 // ------------------------------------------------------------------ K3 shadow rays: any-hit, unoccluded rays add their radiance
 // One shadow ray per pixel per launch (one NEE sample per wave), so the fp32 read-modify-write below is race free —
 // the reference's fp16 RMW is racy (SURVEY hazard 2).
-__global__ void __launch_bounds__(kBlock) k_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket,
-                                                    float4* channels, size_t npix, float tmin, unsigned long long* stat) {
-    const uint32_t n = *count;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 o = q.o[i], d = q.d[i];
-            HitInfo h;
-            if (!bvh8_trace<true>(bvh, f3(o), f3(d), tmin, o.w, h)) {
-                const float4 L = q.L[i];
-                float4* dst = &channels[(size_t)__float_as_int(L.w) * npix + __float_as_uint(d.w)];
-                float4 c = *dst; c.x += L.x; c.y += L.y; c.z += L.z; *dst = c;
-            }
-        }
-        __syncwarp();
+struct ShadowJob {
+    ShadowQueue q; float4* channels; size_t npix; float tmin;
+    LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { const float4 o4 = q.o[i]; o = f3(o4); d = f3(q.d[i]); t0 = tmin; t1 = o4.w; return true; }
+    LB_D void done(uint32_t i, bool occluded, const Tracer&) const {
+        if (occluded) return;
+        const float4 L = q.L[i];
+        float4* dst = &channels[(size_t)__float_as_int(L.w) * npix + __float_as_uint(q.d[i].w)];
+        float4 c = *dst; c.x += L.x; c.y += L.y; c.z += L.z; *dst = c;
     }
+};
+__global__ void __launch_bounds__(kBlock) k_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket,
+                                                    float4* channels, size_t npix, float tmin, unsigned long long* stat, TraceTuning tune) {
+    const uint32_t n = *count;
+    ShadowJob job{q, channels, npix, tmin};
+    trace_queue<true>(bvh, n, ticket, job, tune);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
@@ -299,7 +289,7 @@ void launch_raygen(const LaunchCfg& cfg, const FrameView& fv, const CameraBasis&
 }
 void launch_extend(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, int queue, uint32_t ticket, bool primary, float tmin, float tmax) {
     k_extend<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.rays[queue].o, fv.rays[queue].d, &fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A],
-        &fv.counters[CNT_TICKET0 + ticket], primary ? fv.primary_hits : fv.hits, tmin, tmax, &fv.stats[STAT_EXTEND]); LB_LAUNCH_CHECK();
+        &fv.counters[CNT_TICKET0 + ticket], primary ? fv.primary_hits : fv.hits, tmin, tmax, &fv.stats[STAT_EXTEND], cfg.trace); LB_LAUNCH_CHECK();
 }
 void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, int queue, const ShadeArgs& a) {
     if (a.depth == 0) k_shade<true><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
@@ -308,7 +298,7 @@ void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc
 }
 void launch_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
     k_shadow<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.shadow, &fv.counters[CNT_SHADOW], &fv.counters[CNT_TICKET0 + ticket],
-        fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW]); LB_LAUNCH_CHECK();
+        fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace); LB_LAUNCH_CHECK();
 }
 void launch_merge(const LaunchCfg& cfg, const FrameView& fv, int blend, uint32_t blend_count) {
     k_merge<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, blend, blend_count); LB_LAUNCH_CHECK();
