@@ -179,6 +179,7 @@ def run_gpu(args):
     r.synchronize()
     counters = r.frame_counters()
     tris, lights, bvh_bytes, launches = counters["triangles"], counters["lights"], counters["bvh_bytes"], counters["kernel_launches"]
+    bvh_build_ms = counters.get("bvh_build_us", 0) / 1e3
 
     # ---- timed region 1: device-resident throughput
     sampler = ClockSampler(local) if rank == 0 else None
@@ -254,7 +255,7 @@ def run_gpu(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_of(args, W, H, "gpu"),
                 "fps": args.steps / (ms * 1e-3), "samples_per_s": W * H * args.steps * world / (ms * 1e-3), "rays_per_frame": rays_per_frame,
-                "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes},
+                "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
                 "roofline": roofline, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}

@@ -202,7 +202,7 @@ LB_API int lb_read_motion_vectors(LbRenderer r, float* xy32f, size_t capacity_by
  * names are returned as a single ';'-separated string valid until the next call. */
 LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint32_t capacity, uint32_t* count);
 /* counters of the last frame: [0]=extend rays, [1]=shadow rays, [2]=ReSTIR visibility rays, [3]=kernel launches,
- * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes */
+ * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes, [8]=bvh build time (us), [9]=bvh levels, [10]=PLOC rounds */
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* values, uint32_t capacity, uint32_t* count);
 
 /* ---- multi-GPU / framework interop ---- */

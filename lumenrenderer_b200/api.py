@@ -444,10 +444,11 @@ class Renderer:
         return out
 
     def frame_counters(self) -> dict:
-        vals, n = np.zeros(8, np.uint64), C.c_uint32()
-        self.b.check(self.b.frame_counters(self._h, vals.ctypes.data, 8, C.byref(n)))
-        keys = ["extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes", "bvh_bytes"]
-        return {k: int(v) for k, v in zip(keys, vals)}
+        vals, n = np.zeros(12, np.uint64), C.c_uint32()
+        self.b.check(self.b.frame_counters(self._h, vals.ctypes.data, 12, C.byref(n)))
+        keys = ["extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes", "bvh_bytes",
+                "bvh_build_us", "bvh_levels", "bvh_build_rounds"]
+        return {k: int(v) for k, v in zip(keys, vals[: n.value])}
 
     def accum_buffer(self):
         p, nbytes, frames = C.c_void_p(), C.c_size_t(), C.c_uint32()

@@ -77,7 +77,7 @@ struct Renderer {
     DevBuf<float4> d_rays[2][3], d_shadow[3], d_surf[2], d_res[4], d_channels, d_combined, d_accum, d_vol_hits, d_vol_shadow[3];
     DevBuf<uint4> d_hits, d_primary_hits; DevBuf<float2> d_motion; DevBuf<uchar4> d_ldr;
     DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags;
-    uint64_t counters[8]{};
+    uint64_t counters[12]{};
 
     // ---- FrameStats (LumenRenderer.h:29-34): CUDA events instead of host wall clock around forced syncs
     struct Lap { const char* name; cudaEvent_t ev; };
@@ -244,7 +244,10 @@ struct Renderer {
         ScenePrepIn in{d_entries.p, (uint32_t)h_entries.size(), total_tris, d_indices.p, d_vtx_pos.p};
         d_flat.reserve(std::max<uint32_t>(total_tris, 1u));
         launch_flatten(cfg(), in, d_flat.p);
-        bvh_build(stream, d_flat.p, total_tris, bvh);
+        {   // LB_BVH_BUILDER=lbvh selects the fastest build (Karras radix tree); default is the SAH-quality PLOC hierarchy
+            const char* e = getenv("LB_BVH_BUILDER");
+            bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC);
+        }
         lights.num_lights = 0; lights.cdf_sum = 0.f;
         if (total_tris) build_lights(cfg(), scene_view(), in, d_prim_flags.p, lights);
         // volumes
@@ -263,6 +266,7 @@ struct Renderer {
         d_volumes.upload(dv.data(), dv.size(), stream);
         LB_CUDA(cudaStreamSynchronize(stream));
         counters[4] = lights.num_lights; counters[5] = total_tris; counters[6] = bvh.num_nodes; counters[7] = bvh.bytes();
+        counters[8] = (uint64_t)(bvh.build_ms * 1000.f); counters[9] = bvh.levels; counters[10] = bvh.ploc_rounds;
         scene_dirty = false;
     }
 
@@ -588,7 +592,7 @@ LB_API int lb_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* 
         LB_CUDA(cudaMemcpyAsync(s, R_->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R_->stream));
         LB_CUDA(cudaStreamSynchronize(R_->stream));
         R_->counters[0] = s[STAT_EXTEND]; R_->counters[1] = s[STAT_SHADOW]; R_->counters[2] = s[STAT_VIS]; R_->counters[3] = R_->launches_last_frame;
-        const uint32_t n = cap < 8 ? cap : 8; memcpy(v, R_->counters, n * 8); if (count) *count = n; return (int)LB_OK;
+        const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R_->counters, n * 8); if (count) *count = n; return (int)LB_OK;
     });
 }
 LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) {

@@ -46,16 +46,17 @@ struct DevBuf {
 
 struct DeviceBvh {
     DevBuf<Bvh8Node> nodes; DevBuf<DevTri> tris;
-    uint32_t num_nodes = 0, num_tris = 0, levels = 0;
+    uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0;
     float build_ms = 0.f;
     BvhView view() const { return BvhView{nodes.p, tris.p, num_tris}; }
     size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + (size_t)num_tris * sizeof(DevTri); }
 };
 
-// GPU LBVH (63-bit Morton, Karras 2012) -> bottom-up refit -> greedy surface-area collapse into compressed
-// 8-wide nodes. Replaces optixAccelBuild (LumenPT/src/Framework/OptixWrapper.cpp:46-131).
+// GPU build: 63-bit Morton order -> binary hierarchy by PLOC (SAH-quality, default) or LBVH (Karras 2012, fastest build)
+// -> greedy surface-area collapse into compressed 8-wide nodes. Replaces optixAccelBuild (LumenPT/src/Framework/OptixWrapper.cpp:46-131).
 // tris_in: world-space triangles in any order; the builder writes its own leaf-ordered copy into out.tris.
-void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out);
+enum class BvhBuilder { PLOC, LBVH };
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC);
 
 inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 
