@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __res
 //    (light above the pixel's horizon and facing it). A candidate that fails contributes weight +0: it changes nothing but
 //    the reservoir's sample count, so it needs no ordering and is accounted for by a popcount.
 //  * Phase B evaluates the survivors in candidate order, one per lane per round: the lanes re-align on the expensive BSDF
-//    evaluation, which the warp executes max-over-lanes(survivors) times instead of 32. The xorshift stream is replayed up
-//    to the candidate, so every random number is the one the sequential loop of the reference would have drawn.
+//    evaluation, which the warp executes max-over-lanes(survivors) times instead of 32. Phase A leaves the xorshift state in
+//    front of every candidate in shared memory, so every random number is the one the sequential loop of the reference
+//    would have drawn.
 struct BagCandidate { LightSample ls; float bag_pdf; };
 LB_D BagCandidate draw_candidate(const SceneView& sc, const uint2* __restrict__ picked, uint32_t& s) {
     BagCandidate c;
@@ -117,6 +118,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
     const uint32_t stride = gridDim.x * blockDim.x;            // a multiple of 32: the pixel loop is warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
     const size_t np = fv.npix;
+    // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
+    // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
+    __shared__ uint32_t s_state[kPrimarySamples][kBlock];
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < fv.npix; base += stride) {
         const uint32_t i = base + lane;
         bool valid = i < fv.npix;
@@ -136,11 +140,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
             uint32_t sa = s0;
 #pragma unroll 2
             for (uint32_t k = 0; k < kPrimarySamples; ++k) {
+                s_state[k][threadIdx.x] = sa;
                 const BagCandidate c = draw_candidate(sc, picked, sa);
                 ResampleGeom g;
                 const bool have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
-                // ordered unless the update is provably a pure count increment: weight exactly 0 and a non-zero acceptance draw
-                const bool ordered = have || !(0.f / c.bag_pdf == 0.f) || sa == 0u;
+                // ordered unless the update is provably a pure count increment: weight 0 / bag_pdf exactly 0 (bag_pdf neither 0 nor NaN)
+                // and a non-zero acceptance draw
+                const bool ordered = have || !(c.bag_pdf != 0.f && c.bag_pdf == c.bag_pdf) || sa == 0u;
                 mask |= (ordered ? 1u : 0u) << k;
             }
             fresh.count = (int)kPrimarySamples - __popc(mask);
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 
         // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation
         const BsdfCtx ctx = surface_ctx(px);
-        uint32_t sb = s0, kb = 0u;
+        uint32_t sb = s0;
         while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
             const bool active = mask != 0u;
             BagCandidate c; ResampleGeom g; bool have = false;
@@ -156,8 +162,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
             g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
             if (active) {
                 const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
-                for (; kb < k; ++kb) { rand_u32(sb); rand_u32(sb); rand_u32(sb); }      // replay the draws of the skipped candidates
-                c = draw_candidate(sc, picked, sb); ++kb;
+                sb = s_state[k][threadIdx.x];
+                c = draw_candidate(sc, picked, sb);
                 have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
             }
             __syncwarp();
