@@ -364,12 +364,12 @@ struct Renderer {
             lap("shade");
             if (depth == 0 && st.restir) {
                 RestirArgs ra{seed, (int)st.restir_temporal, (int)st.restir_spatial};
+                ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage); }; ra.lap_user = this;
                 RestirBuffers rb{d_bags.p};
                 const uint32_t t0 = ticket;
                 launch_restir(c, fv, sc, bv, rb, ra, ticket);
                 if (sc.num_lights) launches += 3u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
                 (void)t0;
-                lap("restir");
             }
             if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }

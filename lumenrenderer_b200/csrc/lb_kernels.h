@@ -50,7 +50,10 @@ struct ShadeArgs {
     int volume_mode;                  // LB_VOLUME_COMPAT: the reference's 5-step march; LB_VOLUME_DELTA: delta / ratio tracking
 };
 
-struct RestirArgs { uint32_t seed; int temporal, spatial; };
+struct RestirArgs {
+    uint32_t seed; int temporal, spatial;
+    void (*lap)(void* user, const char* stage) = nullptr; void* lap_user = nullptr;      // per-kernel timing marks (CUDA events of the renderer)
+};
 
 // ---- wavefront (lb_wavefront.cu)
 void launch_raygen(const LaunchCfg&, const FrameView&, const CameraBasis&, uint32_t frame_count);

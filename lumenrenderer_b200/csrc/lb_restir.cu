@@ -113,15 +113,20 @@ LB_D BagCandidate draw_candidate(const SceneView& sc, const uint2* __restrict__ 
     return c;
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t seed) {
+__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t* ticket, uint32_t seed) {
     static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
-    const uint32_t stride = gridDim.x * blockDim.x;            // a multiple of 32: the pixel loop is warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
     const size_t np = fv.npix;
     // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
     // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
     __shared__ uint32_t s_state[kPrimarySamples][kBlock];
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < fv.npix; base += stride) {
+    for (;;) {
+        // 32 pixels per warp and turn, handed out by a device ticket: the work per pixel varies (sky / emissive pixels cost
+        // nothing), a static split would leave SMs idle at the end
+        uint32_t base = 0u;
+        if (lane == 0u) base = atomicAdd(ticket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= fv.npix) break;
         const uint32_t i = base + lane;
         bool valid = i < fv.npix;
         Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
@@ -317,25 +322,32 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     if (sc.num_lights == 0u) return;
     cudaStream_t st = cfg.stream;
     const int grid = cfg.sms * 4;
+    auto lap = [&](const char* stage) { if (a.lap) a.lap(a.lap_user, stage); };
     uint32_t seed = wang_hash(a.seed);
     k_fill_bags<<<grid_for(kNumBags * kLightsPerBag, kBlock), kBlock, 0, st>>>(sc, rb.bags, a.seed); LB_LAUNCH_CHECK();
     seed = wang_hash(seed);
-    k_ris<<<grid, kBlock, 0, st>>>(fv, sc, rb.bags, seed); LB_LAUNCH_CHECK();
+    k_ris<<<cfg.sms * 2, kBlock, 0, st>>>(fv, sc, rb.bags, &fv.counters[CNT_TICKET0 + ticket++], seed); LB_LAUNCH_CHECK();
+    lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
     k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
+    lap("restir_visibility");
     if (a.temporal) {
         seed = wang_hash(seed);
-        k_temporal<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
+        k_temporal<<<cfg.sms * 2, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
+        lap("restir_temporal");
     }
     if (a.spatial) {
         seed = wang_hash(seed);
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-            k_spatial<<<grid, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
+            k_spatial<<<cfg.sms * 2, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
+        lap("restir_spatial");
         k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
-        k_combine<<<grid, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
+        lap("restir_visibility");
+        k_combine<<<cfg.sms * 2, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
+        lap("restir_combine");
     }
 }
 

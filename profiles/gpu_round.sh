@@ -9,6 +9,6 @@ python bench.py --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/$
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 if [ -n "$FULL" ]; then
   # skip scene build + 4 frames, then capture one frame's worth of launches
-  ncu --set full --clock-control none --import-source on -k regex:'k_(raygen|extend|shade|shadow|ris|visibility_shade|temporal|spatial|combine|merge)' --launch-skip 84 -c 21 -f -o gpurun_out/${TAG}_full python bench.py --steps 2 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'k_(raygen|extend|shade|shadow|fill_bags|ris|visibility_shade|temporal|spatial|combine|merge)' --launch-skip 84 -c 21 -f -o gpurun_out/${TAG}_full python bench.py --steps 2 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 fi
 cat gpurun_out/${TAG}_pytest.log gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err

@@ -9,6 +9,7 @@ import csv
 import io
 import re
 import subprocess
+import os
 
 METRICS = [("gpu__time_duration.sum", "time"), ("launch__registers_per_thread", "regs"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("smsp__warps_eligible.avg.per_cycle_active", "elig warps"),
@@ -52,6 +53,33 @@ def rep_table(path):
     return "\n".join(out)
 
 
+def launches_per_frame(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    names = [re.sub(r"<\d>", "", short(r["Kernel Name"])) for r in csv.DictReader(lines)]
+    starts = [i for i, n in enumerate(names) if n == "k_raygen"]
+    return collections.Counter(names[starts[-2]:starts[-1]]) if len(starts) >= 2 else None
+
+
+def traffic_json(path, out, note, launches_csv=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per kernel, summed over the launches of the captured frame (bench.py reads this for `traffic`)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    agg, launches = collections.OrderedDict(), collections.Counter()
+    for r in data:
+        k = re.sub(r"<\d>", "", short(r[col["Kernel Name"]]))
+        b = sum(to_bytes(r[col[m]].replace(",", ""), units[col[m]]) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        agg[k] = agg.get(k, 0.0) + b; launches[k] += 1
+    per_frame = launches_per_frame(launches_csv) if launches_csv else None
+    if per_frame:       # the capture window need not be aligned to a frame: average per launch, times the launches one frame makes
+        agg = collections.OrderedDict((k, v / launches[k] * per_frame.get(k, launches[k])) for k, v in agg.items())
+        launches = per_frame
+    json.dump({"source": os.path.basename(path), "note": note, "launches_per_frame": dict(launches), "dram_bytes_per_frame": agg}, open(out, "w"), indent=1)
+    print("wrote", out)
+
+
 def launches_table(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
@@ -75,8 +103,10 @@ def launches_table(path):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rep"); ap.add_argument("--launches"); ap.add_argument("--out", required=True); ap.add_argument("--title", default="ncu summary"); ap.add_argument("--notes", default="")
+    ap.add_argument("--rep"); ap.add_argument("--launches"); ap.add_argument("--out", required=True); ap.add_argument("--title", default="ncu summary"); ap.add_argument("--notes", default=""); ap.add_argument("--traffic-json")
     a = ap.parse_args()
+    if a.traffic_json and a.rep:
+        traffic_json(a.rep, a.traffic_json, a.title, a.launches)
     parts = [f"# {a.title}", ""]
     if a.notes:
         parts += [a.notes, ""]
