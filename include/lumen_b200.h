@@ -194,6 +194,11 @@ LB_API int lb_stop_rendering(LbRenderer r);
 
 /* ---- output: GetOutputTexturePixels, PT/Framework/WaveFrontRenderer.cpp:1379-1394 (+ fp32 HDR, north_star) ---- */
 LB_API int lb_read_hdr(LbRenderer r, float* rgba32f, size_t capacity_bytes);      /* width*height*4 floats, merged/blended image */
+/* The same read-back without blocking the caller (no reference counterpart: GetOutputTexturePixels, WaveFrontRenderer.cpp:1379-1394, is
+ * synchronous). The copy of the frame just rendered runs on a copy engine while the next frame renders; `rgba32f` should be pinned host
+ * memory and must not be touched until lb_readback_wait() returns. One read-back can be pending per renderer. */
+LB_API int lb_read_hdr_async(LbRenderer r, float* rgba32f, size_t capacity_bytes);
+LB_API int lb_readback_wait(LbRenderer r);
 LB_API int lb_read_ldr(LbRenderer r, uint8_t* rgba8, size_t capacity_bytes);      /* clamp + sRGB OETF + 8 bit, GPUShadingKernels.cu:28-56 */
 LB_API int lb_read_channel(LbRenderer r, int channel, float* rgba32f, size_t capacity_bytes);
 LB_API int lb_read_motion_vectors(LbRenderer r, float* xy32f, size_t capacity_bytes); /* MotionVectors.cu:8-55 (fp16-rounded values) */

@@ -161,6 +161,8 @@ _SIGS = {
     "start_rendering": [C.c_void_p],
     "stop_rendering": [C.c_void_p],
     "read_hdr": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "read_hdr_async": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "readback_wait": [C.c_void_p],
     "read_ldr": [C.c_void_p, C.c_void_p, C.c_size_t],
     "read_channel": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
     "read_motion_vectors": [C.c_void_p, C.c_void_p, C.c_size_t],
@@ -417,6 +419,13 @@ class Renderer:
     def read_hdr_into(self, ptr: int, nbytes: int):
         """Read-back into caller-owned (e.g. pinned) host memory."""
         self.b.check(self.b.read_hdr(self._h, ptr, nbytes))
+
+    def read_hdr_async(self, ptr: int, nbytes: int):
+        """Enqueue the read-back of the frame just rendered into (pinned) host memory; it overlaps the next frame. Pair with readback_wait()."""
+        self.b.check(self.b.read_hdr_async(self._h, ptr, nbytes))
+
+    def readback_wait(self):
+        self.b.check(self.b.readback_wait(self._h))
 
     def read_ldr(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), np.uint8)

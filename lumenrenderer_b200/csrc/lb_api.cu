@@ -49,6 +49,8 @@ struct Renderer {
     LbSettings st{};
     int device = 0; int sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // asynchronous read-back (lb_read_hdr_async): a copy stream + two events; the next frame's merge waits for a pending copy
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered = nullptr, ev_copied = nullptr; bool copy_pending = false;
     std::mutex mu;
 
     // ---- host-side scene (the reference keeps the same tables in PTScene / SceneDataTable)
@@ -102,6 +104,9 @@ struct Renderer {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (ev_rendered) cudaEventDestroy(ev_rendered);
+        if (ev_copied) cudaEventDestroy(ev_copied);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
     void stop_thread() {
@@ -120,6 +125,8 @@ struct Renderer {
         sms = prop.multiProcessorCount;
         LB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
         stream = own_stream;
+        LB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        LB_CUDA(cudaEventCreateWithFlags(&ev_rendered, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));
         // sRGB decode table, computed in double exactly like the oracle does per texel
         float lut[256];
         for (int b = 0; b < 256; ++b) { const double c = b / 255.0; lut[b] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4)); }
@@ -375,6 +382,7 @@ struct Renderer {
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
+        if (copy_pending) LB_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));      // an asynchronous read-back still owns the combined buffer
         launch_merge(c, fv, (int)st.blend_output, blend_count); ++launches;
         lap("merge");
         if (st.blend_output) ++blend_count; else blend_count = 1;
@@ -567,6 +575,21 @@ static int read_back(lb::Renderer* R, const void* src, size_t bytes, void* dst, 
     return LB_OK;
 }
 LB_API int lb_read_hdr(LbRenderer r, float* out, size_t cap) { return guarded(R_, [&]() { return read_back(R_, R_->d_combined.p, (size_t)R_->npix() * 16, out, cap); }); }
+LB_API int lb_read_hdr_async(LbRenderer r, float* out, size_t cap) {
+    return guarded(R_, [&]() {
+        const size_t bytes = (size_t)R_->npix() * 16;
+        if (!out || cap < bytes) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small");
+        LB_CUDA(cudaEventRecord(R_->ev_rendered, R_->stream));
+        LB_CUDA(cudaStreamWaitEvent(R_->copy_stream, R_->ev_rendered, 0));
+        LB_CUDA(cudaMemcpyAsync(out, R_->d_combined.p, bytes, cudaMemcpyDeviceToHost, R_->copy_stream));
+        LB_CUDA(cudaEventRecord(R_->ev_copied, R_->copy_stream));
+        R_->copy_pending = true;
+        return (int)LB_OK;
+    });
+}
+LB_API int lb_readback_wait(LbRenderer r) {
+    return guarded(R_, [&]() { if (R_->copy_pending) { LB_CUDA(cudaEventSynchronize(R_->ev_copied)); R_->copy_pending = false; } return (int)LB_OK; });
+}
 LB_API int lb_read_ldr(LbRenderer r, uint8_t* out, size_t cap) { return guarded(R_, [&]() { return read_back(R_, R_->d_ldr.p, (size_t)R_->npix() * 4, out, cap); }); }
 LB_API int lb_read_channel(LbRenderer r, int c, float* out, size_t cap) {
     return guarded(R_, [&]() { if (c < 0 || c >= LB_NUM_CHANNELS) return fail(LB_ERR_INVALID_ARGUMENT, "channel"); return read_back(R_, R_->d_channels.p + (size_t)c * R_->npix(), (size_t)R_->npix() * 16, out, cap); });
@@ -599,7 +622,7 @@ LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* fram
     return guarded(R_, [&]() { *p = R_->d_accum.p; *bytes = (size_t)R_->npix() * 16; *frames = R_->blend_count; return (int)LB_OK; });
 }
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
-    return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
+    return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
 }
 LB_API int lb_set_stream(LbRenderer r, void* s) {
     return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->stream = s ? (cudaStream_t)s : R_->own_stream; return (int)LB_OK; });

@@ -916,6 +916,9 @@ LB_API int lo_stop_rendering(LbRenderer) { return fail(LB_ERR_UNSUPPORTED, "orac
 
 static int copy_out(const void* src, size_t bytes, void* dst, size_t cap) { if (!dst || cap < bytes) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small"); memcpy(dst, src, bytes); return LB_OK; }
 LB_API int lo_read_hdr(LbRenderer r, float* out, size_t cap) { CHECK_R; return copy_out(R_->combined.data(), R_->combined.size() * 16, out, cap); }
+// the CPU restatement has nothing to overlap: the asynchronous read-back is the synchronous one, the wait a no-op
+LB_API int lo_read_hdr_async(LbRenderer r, float* out, size_t cap) { return lo_read_hdr(r, out, cap); }
+LB_API int lo_readback_wait(LbRenderer r) { CHECK_R; return LB_OK; }
 LB_API int lo_read_ldr(LbRenderer r, uint8_t* out, size_t cap) { CHECK_R; return copy_out(R_->ldr.data(), R_->ldr.size(), out, cap); }
 LB_API int lo_read_channel(LbRenderer r, int c, float* out, size_t cap) { CHECK_R; if (c < 0 || c >= 4) return fail(LB_ERR_INVALID_ARGUMENT, "channel"); return copy_out(R_->channel[c].data(), R_->channel[c].size() * 16, out, cap); }
 LB_API int lo_read_motion_vectors(LbRenderer r, float* out, size_t cap) { CHECK_R; return copy_out(R_->motion.data(), R_->motion.size() * 8, out, cap); }

@@ -109,3 +109,23 @@ def test_fog_room_volumes(oracle, mode, restir):
     cg, cc = g.frame_counters(), c.frame_counters()
     assert abs(cg["shadow_rays"] - cc["shadow_rays"]) <= max(4, cc["shadow_rays"] // 2000)
     g.close(); c.close()
+
+
+def test_async_readback_equals_blocking_readback():
+    """lb_read_hdr_async + lb_readback_wait deliver the same frame as lb_read_hdr, also while the next frame is being rendered."""
+    g = lr.Renderer(lr.Settings(width=128, height=96, depth=3, restir=True))
+    g.load_scene(scenes.cornell_box())
+    bufs = [np.zeros((96, 128, 4), np.float32) for _ in range(2)]
+    want = []
+    for k in range(4):
+        g.render_frames(1)
+        g.readback_wait()
+        if k:
+            assert np.array_equal(bufs[(k - 1) % 2], want[k - 1]), f"frame {k - 1} arrived altered"
+        g.read_hdr_async(bufs[k % 2].ctypes.data, bufs[k % 2].nbytes)
+        want.append(None)
+        # the blocking read of the same frame (the pending copy and this one read the same buffer)
+        want[k] = g.read_hdr().copy()
+    g.readback_wait()
+    assert np.array_equal(bufs[3 % 2], want[3])
+    g.close()
