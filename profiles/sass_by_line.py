@@ -32,14 +32,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rep", required=True); ap.add_argument("--obj", required=True); ap.add_argument("--kernel", required=True)
     ap.add_argument("--instance", type=int, default=0); ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--symbol", help="substring of the mangled function name in the object (defaults to --kernel); needed for template instances")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", "--kernel-name", f"regex:{a.kernel}", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
     st = starts[a.instance]; en = starts[a.instance + 1] if a.instance + 1 < len(starts) else len(rows)
     hdr, data = rows[st + 1], rows[st + 2:en]
-    ia, it, isamp = hdr.index("Instructions Executed"), hdr.index("Avg. Threads Executed"), hdr.index("# Samples")
-    lines = sass_lines(a.obj, a.kernel)
+    ia, it, isamp = hdr.index("Instructions Executed"), hdr.index("Avg. Predicated-On Threads Executed"), hdr.index("# Samples")
+    lines = sass_lines(a.obj, a.symbol or a.kernel)
     if len(lines) != len(data):
         print(f"warning: {len(lines)} SASS instructions in the object vs {len(data)} in the report")
     agg = collections.defaultdict(lambda: [0, 0.0, 0])
