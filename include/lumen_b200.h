@@ -174,6 +174,8 @@ LB_API int lb_scene_clear(LbRenderer r);
 /* position + rotation quaternion (w,x,y,z); fovY is the reference's hard-coded 90 degrees (Camera.h:63) unless overridden. */
 LB_API int lb_camera_set_pose(LbRenderer r, const float* position3, const float* rotation_wxyz);
 LB_API int lb_camera_set_fov_y(LbRenderer r, float degrees);
+/* Camera::SetMinMaxRenderDistance, LM/Renderer/Camera.h:36-37,60 (default 0.1, 1000): normalisation range of the depth side output */
+LB_API int lb_camera_set_min_max_distance(LbRenderer r, float min_distance, float max_distance);
 
 /* ---- frame settings: LumenRenderer::Set/GetRenderResolution, SetBlendMode, LM/Renderer/LumenRenderer.h:178-196 ---- */
 LB_API int lb_set_render_resolution(LbRenderer r, uint32_t width, uint32_t height);
@@ -202,6 +204,15 @@ LB_API int lb_readback_wait(LbRenderer r);
 LB_API int lb_read_ldr(LbRenderer r, uint8_t* rgba8, size_t capacity_bytes);      /* clamp + sRGB OETF + 8 bit, GPUShadingKernels.cu:28-56 */
 LB_API int lb_read_channel(LbRenderer r, int channel, float* rgba32f, size_t capacity_bytes);
 LB_API int lb_read_motion_vectors(LbRenderer r, float* xy32f, size_t capacity_bytes); /* MotionVectors.cu:8-55 (fp16-rounded values) */
+
+/* G-buffer side outputs of the frame just rendered, for a denoiser / upscaler behind the path (any pointer may be NULL):
+ *   depth             float[N]   ExtractDepthDataGpu / ExtractNRD_DLSSdataGpu, PT/CUDAKernels/WaveFrontKernels/GPUExtractDepthData.cu:6-72,
+ *                                GPUExtractNRD_DLSSdata.cu:6-89: (t - min(minD, t)) / (max(maxD, t) - min(minD, t)), 0 where t < 0
+ *   normal_roughness  float4[N]  shading normal + MaterialData::GetRoughness(); the reference writes a half4 surface, values are rounded
+ *                                through fp16 accordingly (GPUExtractNRD_DLSSdata.cu:77-86)
+ *   albedo            float4[N]  m_MaterialData.m_Color (PrepareOptixDenoisingGPU, GPUPostProcessingEffects.cu:13-50)
+ * Motion vectors: lb_read_motion_vectors. */
+LB_API int lb_read_gbuffer(LbRenderer r, float* depth, float* normal_roughness4, float* albedo4, size_t pixel_capacity);
 
 /* FrameStats, LM/Renderer/LumenRenderer.h:29-34: per-stage device time (CUDA events) of the last frame, microseconds.
  * names are returned as a single ';'-separated string valid until the next call. */

@@ -162,6 +162,8 @@ _SIGS = {
     "stop_rendering": [C.c_void_p],
     "read_hdr": [C.c_void_p, C.c_void_p, C.c_size_t],
     "read_hdr_async": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "read_gbuffer": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
+    "camera_set_min_max_distance": [C.c_void_p, C.c_float, C.c_float],
     "readback_wait": [C.c_void_p],
     "read_ldr": [C.c_void_p, C.c_void_p, C.c_size_t],
     "read_channel": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
@@ -426,6 +428,17 @@ class Renderer:
 
     def readback_wait(self):
         self.b.check(self.b.readback_wait(self._h))
+
+    def read_gbuffer(self):
+        """(depth [H, W], normal_roughness [H, W, 4], albedo [H, W, 4]) of the frame just rendered."""
+        n = self.width * self.height
+        depth = np.empty((self.height, self.width), np.float32)
+        nr = np.empty((self.height, self.width, 4), np.float32); al = np.empty_like(nr)
+        self.b.check(self.b.read_gbuffer(self._h, depth.ctypes.data, nr.ctypes.data, al.ctypes.data, n))
+        return depth, nr, al
+
+    def set_camera_min_max_distance(self, min_distance: float, max_distance: float):
+        self.b.check(self.b.camera_set_min_max_distance(self._h, min_distance, max_distance))
 
     def read_ldr(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), np.uint8)

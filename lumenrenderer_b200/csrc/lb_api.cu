@@ -49,6 +49,8 @@ struct Renderer {
     LbSettings st{};
     int device = 0; int sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    float cam_min_d = 0.1f, cam_max_d = 1000.f;           // Camera::m_MinMaxRenderDistance, Camera.h:60
+    DevBuf<float> d_gbuffer;
     // asynchronous read-back (lb_read_hdr_async): a copy stream + two events; the next frame's merge waits for a pending copy
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered = nullptr, ev_copied = nullptr; bool copy_pending = false;
     std::mutex mu;
@@ -529,6 +531,9 @@ LB_API int lb_camera_set_pose(LbRenderer r, const float* p, const float* q) {
 LB_API int lb_camera_set_fov_y(LbRenderer r, float deg) {
     return guarded(R_, [&]() { if (!(deg > 0.f && deg < 180.f)) return fail(LB_ERR_INVALID_ARGUMENT, "fov"); R_->fov_y = deg; return (int)LB_OK; });
 }
+LB_API int lb_camera_set_min_max_distance(LbRenderer r, float mn, float mx) {
+    return guarded(R_, [&]() { if (!(mx > mn)) return fail(LB_ERR_INVALID_ARGUMENT, "min/max distance"); R_->cam_min_d = mn; R_->cam_max_d = mx; return (int)LB_OK; });
+}
 LB_API int lb_set_render_resolution(LbRenderer r, uint32_t w, uint32_t h) {
     return guarded(R_, [&]() { if (!w || !h) return fail(LB_ERR_INVALID_ARGUMENT, "resolution"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->st.width = w; R_->st.height = h; R_->resize(); return (int)LB_OK; });
 }
@@ -589,6 +594,20 @@ LB_API int lb_read_hdr_async(LbRenderer r, float* out, size_t cap) {
 }
 LB_API int lb_readback_wait(LbRenderer r) {
     return guarded(R_, [&]() { if (R_->copy_pending) { LB_CUDA(cudaEventSynchronize(R_->ev_copied)); R_->copy_pending = false; } return (int)LB_OK; });
+}
+LB_API int lb_read_gbuffer(LbRenderer r, float* depth, float* normal_rough, float* albedo, size_t pixel_capacity) {
+    return guarded(R_, [&]() {
+        const size_t n = R_->npix();
+        if (pixel_capacity < n) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small");
+        R_->d_gbuffer.reserve(n * 9);                                                   // depth | normal+roughness (4) | albedo (4)
+        float* d_depth = R_->d_gbuffer.p; float4* d_nr = reinterpret_cast<float4*>(R_->d_gbuffer.p + n); float4* d_al = d_nr + n;
+        launch_gbuffer(R_->cfg(), R_->d_surf[R_->surf_cur ^ 1u].p, (uint32_t)n, R_->cam_min_d, R_->cam_max_d, depth ? d_depth : nullptr, normal_rough ? d_nr : nullptr, albedo ? d_al : nullptr);
+        if (depth) LB_CUDA(cudaMemcpyAsync(depth, d_depth, n * 4, cudaMemcpyDeviceToHost, R_->stream));
+        if (normal_rough) LB_CUDA(cudaMemcpyAsync(normal_rough, d_nr, n * 16, cudaMemcpyDeviceToHost, R_->stream));
+        if (albedo) LB_CUDA(cudaMemcpyAsync(albedo, d_al, n * 16, cudaMemcpyDeviceToHost, R_->stream));
+        LB_CUDA(cudaStreamSynchronize(R_->stream));
+        return (int)LB_OK;
+    });
 }
 LB_API int lb_read_ldr(LbRenderer r, uint8_t* out, size_t cap) { return guarded(R_, [&]() { return read_back(R_, R_->d_ldr.p, (size_t)R_->npix() * 4, out, cap); }); }
 LB_API int lb_read_channel(LbRenderer r, int c, float* out, size_t cap) {

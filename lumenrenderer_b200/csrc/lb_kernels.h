@@ -66,6 +66,7 @@ void launch_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t 
 void launch_volume_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
 void launch_merge(const LaunchCfg&, const FrameView&, int blend, uint32_t blend_count);
 void launch_resolve(const LaunchCfg&, const FrameView&, float inv_frames);
+void launch_gbuffer(const LaunchCfg&, const float4* surf_planes, uint32_t npix, float min_d, float max_d, float* depth, float4* normal_rough, float4* albedo);
 void launch_debug_trace(const LaunchCfg&, const BvhView&, const float* rays6, const float* tmax_per_ray, uint32_t n, float tmin, float tmax, void* hits20, uint8_t* occluded);
 void launch_debug_bsdf(const LaunchCfg&, const float* mat24, const float* v12, uint32_t n, float* out, bool sample);
 void launch_debug_surface(const LaunchCfg&, const float4* planes, uint32_t npix, float* out24);

@@ -216,6 +216,26 @@ __global__ void __launch_bounds__(kBlock) k_resolve(FrameView fv, float inv) {
     }
 }
 
+// ------------------------------------------------------------------ G-buffer side outputs for a denoiser / upscaler behind the path
+// depth: ExtractDepthDataGpu / ExtractNRD_DLSSdataGpu (GPUExtractDepthData.cu:6-72, GPUExtractNRD_DLSSdata.cu:6-89): t normalised by the
+// camera's min/max render distance, 0 where t < 0. normal + roughness: the reference writes a half4 surface -> values rounded through
+// fp16. albedo: m_MaterialData.m_Color (PrepareOptixDenoisingGPU, GPUPostProcessingEffects.cu:13-50).
+__global__ void __launch_bounds__(kBlock) k_gbuffer(const float4* __restrict__ surf, uint32_t npix, float min_d, float max_d,
+                                                     float* __restrict__ depth, float4* __restrict__ normal_rough, float4* __restrict__ albedo) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const size_t np = npix;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const float4 g = surf[np + i];                                  // normal, signed depth
+        float t = fabsf(g.w);
+        if (depth) depth[i] = t < 0.f ? 0.f : (t - fminf(min_d, t)) / (fmaxf(max_d, t) - fminf(min_d, t));
+        if (normal_rough) {
+            const float roughness = unpack8(__float_as_uint(surf[8 * np + i].x), 24);
+            normal_rough[i] = make_float4(half_round(g.x), half_round(g.y), half_round(g.z), half_round(roughness));
+        }
+        if (albedo) albedo[i] = surf[5 * np + i];
+    }
+}
+
 // ------------------------------------------------------------------ debug taps (parity tests)
 struct Hit20 { uint32_t inst, prim; float u, v, t; };
 
@@ -302,6 +322,9 @@ void launch_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh
 }
 void launch_merge(const LaunchCfg& cfg, const FrameView& fv, int blend, uint32_t blend_count) {
     k_merge<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, blend, blend_count); LB_LAUNCH_CHECK();
+}
+void launch_gbuffer(const LaunchCfg& cfg, const float4* surf, uint32_t npix, float min_d, float max_d, float* depth, float4* normal_rough, float4* albedo) {
+    k_gbuffer<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(surf, npix, min_d, max_d, depth, normal_rough, albedo); LB_LAUNCH_CHECK();
 }
 void launch_resolve(const LaunchCfg& cfg, const FrameView& fv, float inv_frames) {
     k_resolve<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, inv_frames); LB_LAUNCH_CHECK();

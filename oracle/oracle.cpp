@@ -73,6 +73,7 @@ struct Renderer {
     std::vector<Tri> tris; Bvh2 bvh; std::vector<LightTri> lights; std::vector<float> cdf; float cdf_sum = 0;
     // frame state
     uint32_t frame_index = 0, surf_cur = 0, res_cur = 0, blend_count = 0;
+    float cam_min_d = 0.1f, cam_max_d = 1000.f;           // Camera::m_MinMaxRenderDistance, Camera.h:60
     std::vector<Surface> surface[3]; std::vector<Reservoir> reservoirs[4];
     std::vector<V4> channel[4], combined, accum; std::vector<V2> motion; std::vector<HitRec> primary_hits; std::vector<uint8_t> ldr;
     std::vector<VolumeHit> volhits;
@@ -903,6 +904,20 @@ LB_API int lo_scene_add_volume_instance(LbRenderer r, LbHandle vol, const float*
 LB_API int lo_scene_clear(LbRenderer r) { CHECK_R; R_->instances.clear(); R_->vinstances.clear(); R_->scene_dirty = true; return LB_OK; }
 LB_API int lo_camera_set_pose(LbRenderer r, const float* p, const float* q) { CHECK_R; if (!p || !q) return fail(LB_ERR_INVALID_ARGUMENT, "null"); R_->cam_pos = {p[0], p[1], p[2]}; memcpy(R_->cam_q, q, 16); return LB_OK; }
 LB_API int lo_camera_set_fov_y(LbRenderer r, float deg) { CHECK_R; if (!(deg > 0.f && deg < 180.f)) return fail(LB_ERR_INVALID_ARGUMENT, "fov"); R_->fov_y = deg; return LB_OK; }
+LB_API int lo_camera_set_min_max_distance(LbRenderer r, float mn, float mx) { CHECK_R; if (!(mx > mn)) return fail(LB_ERR_INVALID_ARGUMENT, "min/max distance"); R_->cam_min_d = mn; R_->cam_max_d = mx; return LB_OK; }
+// G-buffer side outputs: GPUExtractDepthData.cu:6-72, GPUExtractNRD_DLSSdata.cu:6-89 (half4 normal+roughness), GPUPostProcessingEffects.cu:13-50 (albedo)
+LB_API int lo_read_gbuffer(LbRenderer r, float* depth, float* nr, float* albedo, size_t pixel_capacity) {
+    CHECK_R; const auto& S = R_->surface[R_->surf_cur == 1 ? 0 : 1];
+    if (pixel_capacity < S.size()) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small");
+    const float mn = R_->cam_min_d, mx = R_->cam_max_d;
+    for (size_t i = 0; i < S.size(); ++i) {
+        const Surface& s = S[i]; const float t = s.t;
+        if (depth) depth[i] = t < 0.f ? 0.f : (t - fminf(mn, t)) / (fmaxf(mx, t) - fminf(mn, t));
+        if (nr) { nr[4 * i] = half_round(s.normal.x); nr[4 * i + 1] = half_round(s.normal.y); nr[4 * i + 2] = half_round(s.normal.z); nr[4 * i + 3] = half_round(unpack8(s.mat.params[0], 24)); }
+        if (albedo) { albedo[4 * i] = s.mat.color.x; albedo[4 * i + 1] = s.mat.color.y; albedo[4 * i + 2] = s.mat.color.z; albedo[4 * i + 3] = s.mat.color.w; }
+    }
+    return LB_OK;
+}
 LB_API int lo_set_render_resolution(LbRenderer r, uint32_t w, uint32_t h) { CHECK_R; if (!w || !h) return fail(LB_ERR_INVALID_ARGUMENT, "resolution"); R_->st.width = w; R_->st.height = h; R_->resize(); return LB_OK; }
 LB_API int lo_get_render_resolution(LbRenderer r, uint32_t* w, uint32_t* h) { CHECK_R; *w = R_->st.width; *h = R_->st.height; return LB_OK; }
 LB_API int lo_set_depth(LbRenderer r, uint32_t d) { CHECK_R; if (!d) return fail(LB_ERR_INVALID_ARGUMENT, "depth"); R_->st.depth = d; return LB_OK; }

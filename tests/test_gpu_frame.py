@@ -129,3 +129,16 @@ def test_async_readback_equals_blocking_readback():
     g.readback_wait()
     assert np.array_equal(bufs[3 % 2], want[3])
     g.close()
+
+
+def test_gbuffer_side_outputs_bit_exact(oracle):
+    """Depth / normal+roughness / albedo side outputs against the oracle's restatement of GPUExtractNRD_DLSSdata.cu."""
+    g, c = _pair(oracle, scenes.material_gallery(), width=160, height=96, depth=2, restir=False)
+    for r in (g, c):
+        r.set_camera_min_max_distance(0.5, 40.0)
+        r.render_frames(1)
+    (dg, ng, ag), (dc, nc, ac) = g.read_gbuffer(), c.read_gbuffer()
+    assert np.array_equal(dg, dc) and dg.max() > 0 and dg.max() <= 1.0
+    assert np.array_equal(ng, nc) and np.array_equal(ag, ac)
+    assert np.abs(np.linalg.norm(ng[..., :3], axis=-1)[dg > 0] - 1).max() < 2e-3       # fp16-rounded unit normals
+    g.close(); c.close()
