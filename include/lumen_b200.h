@@ -221,6 +221,17 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
  * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes, [8]=bvh build time (us), [9]=bvh levels, [10]=PLOC rounds */
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* values, uint32_t capacity, uint32_t* count);
 
+/* ---- output stage behind the path ---- */
+/* Screenshot: the 8-bit output image (lb_read_ldr) as a PNG file — colour type 6, 8 bit, rows top to bottom. Replaces
+ * OutputLayer::MakeScreenshot = GetOutputTexturePixels + stbi_write_png(w, h, 4, pixels, 0) (Sandbox/src/OutputLayer.cpp:882-896).
+ * LB_ERR_INVALID_ARGUMENT when the file cannot be written. */
+LB_API int lb_save_png(LbRenderer r, const char* path);
+/* FrameStats export (LM/Renderer/LumenRenderer.h:29-34, consumed by the profiler pane Sandbox/src/OutputLayer.cpp:377-420) as one
+ * JSON object: {"frame_id", "resolution", "times_us": {stage: microseconds, ...}, "counters": {name: value, ...}}. Writes at most
+ * `capacity` bytes including the terminating 0; `*needed` (may be NULL) receives the full length + 1. LB_ERR_INVALID_ARGUMENT when the
+ * buffer is too small (nothing is written then). */
+LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t capacity, size_t* needed);
+
 /* ---- multi-GPU / framework interop ---- */
 /* Device pointer of the fp32 RGBA accumulation buffer (sum over blended frames) and its frame count, for an
  * external NCCL reduce; lb_resolve_accum divides by `total_frames` and refreshes HDR/LDR. */

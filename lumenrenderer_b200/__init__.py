@@ -18,7 +18,8 @@ from .api import (MaterialData, Settings, SceneDescription, LumenError, Bindings
                   VOLUME_COMPAT, VOLUME_DELTA, SURF_EMISSIVE, SURF_ALPHA, SURF_MISS, pack_material24)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "liblumen_b200.so")
+# LUMEN_B200_LIB selects another build of the same library (A/B experiments of compile flags); never the oracle.
+LIB_PATH = os.environ.get("LUMEN_B200_LIB") or os.path.join(_PKG_DIR, "liblumen_b200.so")
 _bindings = None
 
 

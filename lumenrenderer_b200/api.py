@@ -13,6 +13,7 @@ through the very same code; the product only ever instantiates it with its own C
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -170,6 +171,8 @@ _SIGS = {
     "read_motion_vectors": [C.c_void_p, C.c_void_p, C.c_size_t],
     "frame_stats": [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)],
     "frame_counters": [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)],
+    "save_png": [C.c_void_p, C.c_char_p],
+    "frame_stats_json": [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
     "accum_buffer": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)],
     "resolve_accum": [C.c_void_p, C.c_uint32],
     "set_stream": [C.c_void_p, C.c_void_p],
@@ -471,6 +474,19 @@ class Renderer:
         keys = ["extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes", "bvh_bytes",
                 "bvh_build_us", "bvh_levels", "bvh_build_rounds"]
         return {k: int(v) for k, v in zip(keys, vals[: n.value])}
+
+    def save_png(self, path: str):
+        """Screenshot of the 8-bit output (OutputLayer::MakeScreenshot, Sandbox/src/OutputLayer.cpp:882-896)."""
+        self.b.check(self.b.save_png(self._h, os.fsencode(path)))
+
+    def frame_stats_json(self) -> dict:
+        """FrameStats of the last frame as parsed JSON (times in microseconds per stage + counters)."""
+        import json
+        need = C.c_size_t(0)
+        self.b.frame_stats_json(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        self.b.check(self.b.frame_stats_json(self._h, buf, need.value, None))
+        return json.loads(buf.value.decode())
 
     def accum_buffer(self):
         p, nbytes, frames = C.c_void_p(), C.c_size_t(), C.c_uint32()

@@ -637,6 +637,43 @@ LB_API int lb_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* 
         const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R_->counters, n * 8); if (count) *count = n; return (int)LB_OK;
     });
 }
+// ---- output stage: screenshot + FrameStats export
+LB_API int lb_save_png(LbRenderer r, const char* path) {
+    return guarded(R_, [&]() {
+        if (!path || !*path) return fail(LB_ERR_INVALID_ARGUMENT, "path");
+        std::vector<uint8_t> px((size_t)R_->npix() * 4);
+        const int rc = read_back(R_, R_->d_ldr.p, px.size(), px.data(), px.size());
+        if (rc) return rc;
+        if (!png::write_file(path, png::encode_rgba8(px.data(), R_->st.width, R_->st.height))) return fail(LB_ERR_INVALID_ARGUMENT, std::string("cannot write ") + path);
+        return (int)LB_OK;
+    });
+}
+LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* needed) {
+    return guarded(R_, [&]() {
+        static const char* kCounterNames[11] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
+                                                "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds"};
+        uint64_t cnt[12]; uint32_t n = 0;
+        int rc = lb_frame_counters(r, cnt, 12, &n); if (rc) return rc;
+        LB_CUDA(cudaStreamSynchronize(R_->stream));
+        // stages that run several times per frame (extend, shade, shadow per wave) are summed, as FrameStats::m_Times does with its map
+        std::vector<std::pair<std::string, double>> times;
+        for (size_t i = 1; i < R_->laps.size(); ++i) {
+            float ms = 0.f; LB_CUDA(cudaEventElapsedTime(&ms, R_->laps[i - 1].ev, R_->laps[i].ev));
+            auto it = std::find_if(times.begin(), times.end(), [&](const std::pair<std::string, double>& t) { return t.first == R_->laps[i].name; });
+            if (it == times.end()) times.emplace_back(R_->laps[i].name, (double)ms * 1000.0); else it->second += (double)ms * 1000.0;
+        }
+        char num[64];
+        std::string o = "{\"frame_id\": " + std::to_string(R_->frame_id) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
+        for (size_t i = 0; i < times.size(); ++i) { snprintf(num, sizeof num, "%.3f", times[i].second); o += (i ? ", \"" : "\"") + times[i].first + "\": " + num; }
+        o += "}, \"counters\": {";
+        for (uint32_t i = 0; i < n && i < 11; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);
+        o += "}}";
+        if (needed) *needed = o.size() + 1;
+        if (!json || cap < o.size() + 1) return (json || cap) ? fail(LB_ERR_INVALID_ARGUMENT, "buffer too small") : (needed ? (int)LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "null"));
+        memcpy(json, o.c_str(), o.size() + 1);
+        return (int)LB_OK;
+    });
+}
 LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) {
     return guarded(R_, [&]() { *p = R_->d_accum.p; *bytes = (size_t)R_->npix() * 16; *frames = R_->blend_count; return (int)LB_OK; });
 }

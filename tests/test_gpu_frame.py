@@ -142,3 +142,37 @@ def test_gbuffer_side_outputs_bit_exact(oracle):
     assert np.array_equal(ng, nc) and np.array_equal(ag, ac)
     assert np.abs(np.linalg.norm(ng[..., :3], axis=-1)[dg > 0] - 1).max() < 2e-3       # fp16-rounded unit normals
     g.close(); c.close()
+
+
+def test_dynamic_scene_moving_camera_and_instance(oracle):
+    """SURVEY 8f-4 (dynamic scenes): the camera dollies and turns and one mesh instance moves between frames. The scene commit
+    (flattening, BVH, light list) is redone on the device, motion vectors are non-zero, and temporal reuse reprojects into the
+    previous frame's reservoirs (ReSTIRKernels.cu:1044-1048) — all against the oracle, frame by frame."""
+    scene = scenes.cornell_box()
+    g, c = _pair(oracle, scene, width=160, height=120, depth=3, restir=True)
+    cam = scene.camera
+    p0 = np.asarray(cam["position"], np.float64)
+    moved = len(scene.instances) - 1
+    base = np.asarray(scene.instances[moved].get("transform", np.eye(4)), np.float32).reshape(4, 4).copy()
+    nonzero_mv = 0
+    for frame in range(4):
+        ang = 0.03 * frame
+        w0, x0, y0, z0 = cam.get("rotation", (1.0, 0.0, 0.0, 0.0)); w1, y1 = float(np.cos(ang / 2)), float(np.sin(ang / 2))   # base * yaw
+        rot = (w0 * w1 - y0 * y1, x0 * w1 - z0 * y1, y0 * w1 + w0 * y1, z0 * w1 + x0 * y1)
+        m = base.copy(); m[:3, 3] += np.float32(0.02 * frame) * np.array([1, 0.5, -0.25], np.float32)
+        for r in (g, c):
+            r.set_camera(p0 + np.array([0.02, 0.01, -0.03]) * frame, rot, cam.get("fov_y"))
+            if frame:
+                r.set_instance_transform(moved, m)
+            r.render_frames(1)
+        _check_hits(g, c)
+        assert np.array_equal(g.read_surface(), c.read_surface())
+        mg, mc = g.read_motion_vectors(), c.read_motion_vectors()
+        assert np.array_equal(mg, mc)
+        nonzero_mv += int((mg != 0).any())
+        err = rel_l1(g.read_hdr()[..., :3], c.read_hdr()[..., :3])
+        assert err < RADIANCE_TOL, f"frame {frame}: {err}"
+    assert nonzero_mv >= 3
+    rg, rc = g.read_reservoirs(), c.read_reservoirs()
+    assert (rg[..., 2] != rc[..., 2]).mean() < 1e-3
+    g.close(); c.close()
