@@ -232,6 +232,34 @@ LB_API int lb_save_png(LbRenderer r, const char* path);
  * buffer is too small (nothing is written then). */
 LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t capacity, size_t* needed);
 
+/* ---- asset ingest in front of the path: glTF 2.0 (.gltf + .bin / data URIs, .glb) ----
+ * Restates LumenPTModelConverter (PT/Tools/LumenPTModelConverter.cpp): material mapping :347-531, accessor extraction :1027-1059,
+ * tangent generation :734-900, node hierarchy :953-1025 + :275-317. Host-only: lb_gltf_open needs no renderer and no GPU, the
+ * parsed document can be inspected (what the parity tests do) and uploaded any number of times. */
+typedef struct LbGltfOpaque* LbGltf;
+/* Decoder for image formats other than PNG (the reference links stb_image, LumenPTModelConverter.cpp:121). Returns 0 on success with
+ * *rgba8 = malloc()ed width*height*4 bytes, which the library frees. */
+typedef int (*LbImageDecodeFn)(const uint8_t* bytes, size_t size, uint8_t** rgba8, uint32_t* width, uint32_t* height, void* user);
+typedef struct LbGltfInfo {
+    uint32_t images, undecoded_images;   /* undecoded images become the renderer's 1x1 default texture */
+    uint32_t materials, meshes, primitives, instances, triangles, vertices;
+} LbGltfInfo;
+LB_API int lb_gltf_open(const char* path, LbImageDecodeFn decoder /* may be NULL */, void* user, LbGltf* out);
+LB_API int lb_gltf_close(LbGltf g);
+LB_API const char* lb_gltf_last_error(void);
+LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out);
+/* Inspection; returned pointers stay valid until lb_gltf_close. Texture members of the material are IMAGE indices of this document
+ * (LB_NO_HANDLE = none), `material` of the primitive is a glTF material index (-1 = glTF default material). Indices are 32 bit. */
+LB_API int lb_gltf_image(LbGltf g, uint32_t image, const uint8_t** rgba8, uint32_t* width, uint32_t* height, int* srgb, int* decoded);
+LB_API int lb_gltf_material(LbGltf g, uint32_t material, LbMaterialDesc* out);
+LB_API int lb_gltf_mesh_primitive_count(LbGltf g, uint32_t mesh, uint32_t* count);
+LB_API int lb_gltf_primitive(LbGltf g, uint32_t mesh, uint32_t primitive, LbPrimitiveDesc* out);
+LB_API int lb_gltf_instance(LbGltf g, uint32_t instance, uint32_t* mesh, float* transform16 /* row-major world matrix */);
+/* CreateTexture / CreateMaterial / CreatePrimitive / CreateMesh / AddMesh for the whole document, in the order
+ * LumenPTModelConverter::LoadFile issues them (:105-268). root_transform16 (row-major, may be NULL) is applied on the left of
+ * every instance transform (SceneManager::LoadGLTF's a_TransformMat, LM/ModelLoading/SceneManager.cpp:41). */
+LB_API int lb_gltf_upload(LbRenderer r, LbGltf g, const float* root_transform16, LbHandle* first_instance, uint32_t* instance_count);
+
 /* ---- multi-GPU / framework interop ---- */
 /* Device pointer of the fp32 RGBA accumulation buffer (sum over blended frames) and its frame count, for an
  * external NCCL reduce; lb_resolve_accum divides by `total_frames` and refreshes HDR/LDR. */

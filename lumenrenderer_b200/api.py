@@ -185,6 +185,24 @@ _SIGS = {
     "debug_eval_bsdf": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
     "debug_sample_bsdf": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
 }
+# Host-only entry points (asset ingest): no renderer, no device work, nothing for the oracle to mirror.
+class LbGltfInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("images", "undecoded_images", "materials", "meshes", "primitives", "instances", "triangles", "vertices")]
+
+
+IMAGE_DECODE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p)
+_HOST_SIGS = {
+    "gltf_open": [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
+    "gltf_close": [C.c_void_p],
+    "gltf_info": [C.c_void_p, C.POINTER(LbGltfInfo)],
+    "gltf_image": [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "gltf_material": [C.c_void_p, C.c_uint32, C.POINTER(LbMaterialDesc)],
+    "gltf_mesh_primitive_count": [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)],
+    "gltf_primitive": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(LbPrimitiveDesc)],
+    "gltf_instance": [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p],
+    "gltf_upload": [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)],
+}
+HOST_ONLY_SYMBOLS = tuple(_HOST_SIGS) + ("gltf_last_error",)
 C_ABI_SYMBOLS = tuple(_SIGS) + ("last_error", "version")
 
 HIT_DTYPE = np.dtype([("instance", np.uint32), ("primitive", np.uint32), ("u", np.float32), ("v", np.float32), ("t", np.float32)])
@@ -203,6 +221,13 @@ class Bindings:
         self.last_error.restype = C.c_char_p
         self.version = getattr(lib, prefix + "version")
         self.version.restype = C.c_char_p
+        if prefix == "lb_":                                   # the product library also carries the host-only asset ingest
+            for name, args in _HOST_SIGS.items():
+                fn = getattr(lib, prefix + name)
+                fn.argtypes, fn.restype = args, C.c_int
+                setattr(self, name, fn)
+            self.gltf_last_error = lib.lb_gltf_last_error
+            self.gltf_last_error.restype = C.c_char_p
 
     def check(self, code: int):
         if code != LB_OK:

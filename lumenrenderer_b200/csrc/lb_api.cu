@@ -14,6 +14,7 @@
 #include "lb_kernels.h"
 #include <cstdlib>
 #include "lb_bsdf.cuh"
+#include "lb_png.h"
 #include <vector>
 #include <string>
 #include <memory>
@@ -628,14 +629,15 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
         return (int)LB_OK;
     });
 }
+static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uint32_t* count) {     // caller holds R->mu
+    unsigned long long s[kNumStats];
+    LB_CUDA(cudaMemcpyAsync(s, R->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R->stream));
+    LB_CUDA(cudaStreamSynchronize(R->stream));
+    R->counters[0] = s[STAT_EXTEND]; R->counters[1] = s[STAT_SHADOW]; R->counters[2] = s[STAT_VIS]; R->counters[3] = R->launches_last_frame;
+    const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
+}
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* count) {
-    return guarded(R_, [&]() {
-        unsigned long long s[kNumStats];
-        LB_CUDA(cudaMemcpyAsync(s, R_->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R_->stream));
-        LB_CUDA(cudaStreamSynchronize(R_->stream));
-        R_->counters[0] = s[STAT_EXTEND]; R_->counters[1] = s[STAT_SHADOW]; R_->counters[2] = s[STAT_VIS]; R_->counters[3] = R_->launches_last_frame;
-        const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R_->counters, n * 8); if (count) *count = n; return (int)LB_OK;
-    });
+    return guarded(R_, [&]() { return frame_counters_locked(R_, v, cap, count); });
 }
 // ---- output stage: screenshot + FrameStats export
 LB_API int lb_save_png(LbRenderer r, const char* path) {
@@ -653,7 +655,7 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
         static const char* kCounterNames[11] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
                                                 "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds"};
         uint64_t cnt[12]; uint32_t n = 0;
-        int rc = lb_frame_counters(r, cnt, 12, &n); if (rc) return rc;
+        int rc = frame_counters_locked(R_, cnt, 12, &n); if (rc) return rc;
         LB_CUDA(cudaStreamSynchronize(R_->stream));
         // stages that run several times per frame (extend, shade, shadow per wave) are summed, as FrameStats::m_Times does with its map
         std::vector<std::pair<std::string, double>> times;
@@ -663,7 +665,7 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
             if (it == times.end()) times.emplace_back(R_->laps[i].name, (double)ms * 1000.0); else it->second += (double)ms * 1000.0;
         }
         char num[64];
-        std::string o = "{\"frame_id\": " + std::to_string(R_->frame_id) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
+        std::string o = "{\"frame_id\": " + std::to_string(R_->frame_index) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
         for (size_t i = 0; i < times.size(); ++i) { snprintf(num, sizeof num, "%.3f", times[i].second); o += (i ? ", \"" : "\"") + times[i].first + "\": " + num; }
         o += "}, \"counters\": {";
         for (uint32_t i = 0; i < n && i < 11; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);

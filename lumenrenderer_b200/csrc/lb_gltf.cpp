@@ -1,0 +1,475 @@
+// lb_gltf.cpp — glTF 2.0 ingest in front of the path: file -> vertex streams, Disney material parameters, textures
+// and mesh instances, handed to the renderer through the same C ABI an application would use. Host code only.
+//
+// Restates what the reference does between a .gltf/.glb file and LumenRenderer::CreateTexture/CreateMaterial/CreatePrimitive/
+// CreateMesh/AddMesh (paths under /root/reference/Lumen_Engine/):
+//   material mapping        LumenPT/src/Tools/LumenPTModelConverter.cpp:347-531  (pbrMetallicRoughness + KHR_materials_transmission /
+//                           sheen / ior / clearcoat / specular -> Disney parameters; roughness >= 0.01; luminance 1, transmittance 0)
+//   texture typing          :358-398 (image = textures[i].source), :121-135 (RGBA8, green >= 1 for metal-roughness images, sRGB only
+//                           for diffuse and emissive images)
+//   accessor extraction     :1027-1059 LoadBinary
+//   tangent generation      :734-900 GenerateTangentBinary (default UVs, per-vertex Gram-Schmidt against the vertex normal, w = 1,
+//                           the LAST triangle that references a vertex wins)
+//   node hierarchy          :953-1025 LoadNode/LoadNodeTransform (matrix, else T*R*S), :275-317 (mesh nodes become mesh instances whose
+//                           parent is the parent node's transform), Lumen/src/Lumen/ModelLoading/Transform.cpp:264-307 (world = parent * local)
+// The intermediate .ollad cache file (ConvertGLTF/OutputToFile) is a serialisation of exactly this content and is not reproduced.
+//
+// Canonical choices where the reference is undefined or lossy (DESIGN.md "glTF ingest"):
+//   * node transforms are used as written (the reference round-trips every matrix through glm::decompose);
+//   * a primitive without NORMAL gets flat face normals (the reference reads an empty buffer);
+//   * tangents are stored per VERTEX (the reference sizes the buffer by the index count and indexes it by vertex);
+//   * 8-bit indices are widened (CreatePrimitive takes 2- or 4-byte indices); strided accessors are read with their stride
+//     (LoadBinary advances source and destination by the same stride, which is only right for tightly packed views);
+//   * the quirk that the children of a MESH node do not inherit that node's ancestors (:296-306) is reproduced.
+// Images: PNG is decoded here (lb_png.h); any other format goes through the caller's decoder callback (the reference links
+// stb_image); without one the image becomes the 1x1 default and is counted in LbGltfInfo::undecoded_images.
+#include "../../include/lumen_b200.h"
+#include "lb_json.h"
+#include "lb_png.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+int gfail(int code, const std::string& msg) { g_error = msg; return code; }
+
+struct Vec3 { float x, y, z; };
+inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 operator*(Vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline Vec3 operator*(float s, Vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline Vec3 operator/(Vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }                 // glm: component-wise division
+inline float dot3(Vec3 a, Vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }               // glm::dot: tmp.x + tmp.y + tmp.z
+inline Vec3 normalize3(Vec3 v) { const float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }  // glm::normalize = v * inversesqrt(dot)
+inline Vec3 cross3(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+
+// column-major 4x4 (glm::mat4 layout): m[col * 4 + row]
+struct Mat4 { float m[16]; };
+Mat4 mat_identity() { Mat4 r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.f; return r; }
+bool mat_is_identity(const Mat4& a) { const Mat4 i = mat_identity(); return memcmp(a.m, i.m, sizeof a.m) == 0; }
+// glm operator*(mat4, mat4): Result[j] = ((A[0]*B[j][0] + A[1]*B[j][1]) + A[2]*B[j][2]) + A[3]*B[j][3]
+Mat4 mat_mul(const Mat4& a, const Mat4& b) {
+    Mat4 r;
+    for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i)
+        r.m[j * 4 + i] = ((a.m[0 * 4 + i] * b.m[j * 4 + 0] + a.m[1 * 4 + i] * b.m[j * 4 + 1]) + a.m[2 * 4 + i] * b.m[j * 4 + 2]) + a.m[3 * 4 + i] * b.m[j * 4 + 3];
+    return r;
+}
+// Transform::UpdateLocalMatrix (Transform.cpp:264-280): translate(I, t) * mat4_cast(q) scaled per column
+Mat4 mat_trs(const float t[3], const float q[4] /* x y z w */, const float s[3]) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+    Mat4 r{};
+    r.m[0] = (1.f - 2.f * (qyy + qzz)) * s[0]; r.m[1] = (2.f * (qxy + qwz)) * s[0]; r.m[2] = (2.f * (qxz - qwy)) * s[0];
+    r.m[4] = (2.f * (qxy - qwz)) * s[1]; r.m[5] = (1.f - 2.f * (qxx + qzz)) * s[1]; r.m[6] = (2.f * (qyz + qwx)) * s[1];
+    r.m[8] = (2.f * (qxz + qwy)) * s[2]; r.m[9] = (2.f * (qyz - qwx)) * s[2]; r.m[10] = (1.f - 2.f * (qxx + qyy)) * s[2];
+    r.m[12] = t[0]; r.m[13] = t[1]; r.m[14] = t[2]; r.m[15] = 1.f;
+    return r;
+}
+
+struct Image { std::vector<uint8_t> px; uint32_t w = 1, h = 1; bool decoded = false, srgb = false, metal_rough = false; };
+struct Primitive { std::vector<float> pos, uv, nrm, tan; std::vector<uint32_t> idx; int32_t material = -1; };
+struct Mesh { std::vector<Primitive> prims; };
+struct Instance { uint32_t mesh; float m[16]; /* row-major */ };
+
+bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const bool ok = out.empty() || fread(out.data(), 1, out.size(), f) == out.size();
+    fclose(f);
+    return ok;
+}
+bool base64_decode(const char* s, size_t n, std::vector<uint8_t>& out) {
+    uint32_t acc = 0; int bits = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const char c = s[i]; int v;
+        if (c >= 'A' && c <= 'Z') v = c - 'A'; else if (c >= 'a' && c <= 'z') v = c - 'a' + 26; else if (c >= '0' && c <= '9') v = c - '0' + 52;
+        else if (c == '+' || c == '-') v = 62; else if (c == '/' || c == '_') v = 63; else if (c == '=' || c == '\n' || c == '\r') continue; else return false;
+        acc = (acc << 6) | (uint32_t)v; bits += 6;
+        if (bits >= 8) { bits -= 8; out.push_back((uint8_t)(acc >> bits)); }
+    }
+    return true;
+}
+std::string uri_unescape(const std::string& s) {
+    std::string o;
+    for (size_t i = 0; i < s.size(); ++i) {
+        if (s[i] == '%' && i + 2 < s.size() + 0 && isxdigit((unsigned char)s[i + 1]) && isxdigit((unsigned char)s[i + 2])) { o += (char)strtol(s.substr(i + 1, 2).c_str(), nullptr, 16); i += 2; }
+        else o += s[i];
+    }
+    return o;
+}
+
+} // namespace
+
+struct LbGltfOpaque {
+    std::vector<Image> images; std::vector<LbMaterialDesc> materials; std::vector<Mesh> meshes; std::vector<Instance> instances;
+    LbGltfInfo info{};
+};
+
+namespace {
+
+using lb::json::Value;
+
+struct Loader {
+    LbGltfOpaque& g; const Value& doc; std::string dir; std::vector<std::vector<uint8_t>> buffers; std::vector<uint8_t> glb_bin;
+    LbImageDecodeFn decoder; void* user;
+
+    [[noreturn]] void bad(const std::string& what) const { throw std::runtime_error("glTF: " + what); }
+
+    bool load_uri(const std::string& uri, std::vector<uint8_t>& out) const {
+        if (uri.compare(0, 5, "data:") == 0) {
+            const size_t comma = uri.find(',');
+            if (comma == std::string::npos || uri.find(";base64") == std::string::npos) return false;
+            return base64_decode(uri.c_str() + comma + 1, uri.size() - comma - 1, out);
+        }
+        return read_file(dir + uri_unescape(uri), out);
+    }
+    void load_buffers() {
+        const Value& bs = doc["buffers"];
+        for (size_t i = 0; i < bs.size(); ++i) {
+            std::vector<uint8_t> data;
+            if (bs[i].has("uri")) { if (!load_uri(bs[i]["uri"].string(), data)) bad("cannot read buffer " + std::to_string(i)); }
+            else if (i == 0 && !glb_bin.empty()) data = glb_bin;
+            else bad("buffer " + std::to_string(i) + " has no data");
+            if ((int64_t)data.size() < bs[i]["byteLength"].integer(0)) bad("buffer " + std::to_string(i) + " is shorter than its byteLength");
+            buffers.push_back(std::move(data));
+        }
+    }
+    static uint32_t component_size(int64_t t) { return (t == 5120 || t == 5121) ? 1u : (t == 5122 || t == 5123) ? 2u : (t == 5125 || t == 5126) ? 4u : 0u; }
+    static uint32_t component_count(const std::string& t) { return t == "SCALAR" ? 1u : t == "VEC2" ? 2u : t == "VEC3" ? 3u : t == "VEC4" ? 4u : t == "MAT2" ? 4u : t == "MAT3" ? 9u : t == "MAT4" ? 16u : 0u; }
+    // LoadBinary (:1027-1059): tightly packed copy of the accessor's elements
+    std::vector<uint8_t> accessor_bytes(int64_t index, uint32_t& comp_size, uint32_t& comp_count, int64_t& comp_type) const {
+        const Value& acc = doc["accessors"][(size_t)index];
+        if (index < 0 || acc.is_null()) bad("accessor index out of range");
+        if (acc.has("sparse")) bad("sparse accessors are not supported");
+        comp_type = acc["componentType"].integer(0); comp_size = component_size(comp_type); comp_count = component_count(acc["type"].string());
+        if (!comp_size || !comp_count) bad("accessor with unknown component type");
+        const size_t count = (size_t)acc["count"].integer(0), elem = (size_t)comp_size * comp_count;
+        std::vector<uint8_t> out(count * elem, 0);
+        if (!acc.has("bufferView")) return out;
+        const Value& view = doc["bufferViews"][(size_t)acc["bufferView"].integer(-1)];
+        if (view.is_null()) bad("bufferView index out of range");
+        const size_t buf = (size_t)view["buffer"].integer(0);
+        if (buf >= buffers.size()) bad("buffer index out of range");
+        const size_t stride = std::max<size_t>(elem, (size_t)view["byteStride"].integer(0));
+        const size_t base = (size_t)view["byteOffset"].integer(0) + (size_t)acc["byteOffset"].integer(0);
+        if (count && base + (count - 1) * stride + elem > buffers[buf].size()) bad("accessor reads past the end of its buffer");
+        for (size_t i = 0; i < count; ++i) memcpy(out.data() + i * elem, buffers[buf].data() + base + i * stride, elem);
+        return out;
+    }
+    std::vector<float> float_attribute(int64_t index, uint32_t want_count, const char* name) const {
+        uint32_t cs, cc; int64_t ct;
+        const std::vector<uint8_t> raw = accessor_bytes(index, cs, cc, ct);
+        if (ct != 5126 || cc != want_count) bad(std::string(name) + " must be a float accessor of the expected width");
+        std::vector<float> out(raw.size() / 4);
+        memcpy(out.data(), raw.data(), out.size() * 4);
+        return out;
+    }
+
+    void load_images() {
+        const Value& imgs = doc["images"];
+        g.images.resize(imgs.size());
+        for (size_t i = 0; i < imgs.size(); ++i) {
+            std::vector<uint8_t> bytes; bool have = false;
+            if (imgs[i].has("uri")) have = load_uri(imgs[i]["uri"].string(), bytes);
+            else if (imgs[i].has("bufferView")) {
+                const Value& view = doc["bufferViews"][(size_t)imgs[i]["bufferView"].integer(-1)];
+                const size_t buf = (size_t)view["buffer"].integer(0), off = (size_t)view["byteOffset"].integer(0), len = (size_t)view["byteLength"].integer(0);
+                if (!view.is_null() && buf < buffers.size() && off + len <= buffers[buf].size()) { bytes.assign(buffers[buf].begin() + off, buffers[buf].begin() + off + len); have = true; }
+            }
+            Image& im = g.images[i];
+            if (have && lb::png::decode_rgba8(bytes.data(), bytes.size(), im.px, im.w, im.h)) im.decoded = true;
+            else if (have && decoder) {
+                uint8_t* px = nullptr; uint32_t w = 0, h = 0;
+                if (decoder(bytes.data(), bytes.size(), &px, &w, &h, user) == 0 && px && w && h) { im.px.assign(px, px + (size_t)w * h * 4); im.w = w; im.h = h; im.decoded = true; }
+                free(px);
+            }
+            if (!im.decoded) { im.px = {255, 255, 255, 255}; im.w = im.h = 1; ++g.info.undecoded_images; }
+        }
+        g.info.images = (uint32_t)g.images.size();
+    }
+    // glTF texture index -> image index (textures[i].source), -1 when absent
+    int32_t texture_image(const Value& tex_info) const {
+        if (!tex_info.is_object() || !tex_info.has("index")) return LB_NO_HANDLE;
+        const Value& t = doc["textures"][(size_t)tex_info["index"].integer(-1)];
+        const int64_t src = t.is_null() ? -1 : t["source"].integer(-1);
+        return (src >= 0 && src < (int64_t)g.images.size()) ? (int32_t)src : LB_NO_HANDLE;
+    }
+    // JsonGetOrDefault<uint32_t>(json, "xTexture", -1) reads the member as a plain number (:428); glTF stores a textureInfo
+    // object there. Both spellings are accepted.
+    int32_t extension_texture(const Value& ext, const char* key) const {
+        const Value& v = ext[key];
+        if (v.kind == Value::Number) { const Value& t = doc["textures"][(size_t)v.integer(-1)]; const int64_t src = t.is_null() ? -1 : t["source"].integer(-1); return (src >= 0 && src < (int64_t)g.images.size()) ? (int32_t)src : LB_NO_HANDLE; }
+        return texture_image(v);
+    }
+    void load_materials() {
+        const Value& mats = doc["materials"];
+        for (size_t i = 0; i < mats.size(); ++i) {
+            const Value& m = mats[i]; const Value& pbr = m["pbrMetallicRoughness"];
+            LbMaterialDesc d{};
+            for (int k = 0; k < 4; ++k) d.diffuse_color[k] = (float)pbr["baseColorFactor"][(size_t)k].number(1.0);
+            for (int k = 0; k < 3; ++k) d.emission[k] = (float)m["emissiveFactor"][(size_t)k].number(0.0);
+            d.diffuse_texture = texture_image(pbr["baseColorTexture"]);
+            d.normal_texture = texture_image(m["normalTexture"]);
+            d.metallic_roughness_texture = texture_image(pbr["metallicRoughnessTexture"]);
+            d.emissive_texture = texture_image(m["emissiveTexture"]);
+            if (d.diffuse_texture >= 0) g.images[d.diffuse_texture].srgb = true;
+            if (d.emissive_texture >= 0) g.images[d.emissive_texture].srgb = true;
+            if (d.metallic_roughness_texture >= 0) g.images[d.metallic_roughness_texture].metal_rough = true;
+            d.metallic_factor = (float)pbr["metallicFactor"].number(1.0);
+            d.roughness_factor = fmaxf(0.01f, (float)pbr["roughnessFactor"].number(1.0));
+            d.luminance = 1.f; d.subsurface_factor = 0.f; d.anisotropic = 0.f;
+            d.tint_factor[0] = d.tint_factor[1] = d.tint_factor[2] = 0.f;      // HeaderMaterial::m_TintFactor is never written by the converter (zero-initialised)
+            const Value& ext = m["extensions"];
+            const Value& tr = ext["KHR_materials_transmission"];
+            d.transmission_factor = tr.is_object() ? (float)tr["transmissionFactor"].number(0.0) : 0.f;
+            d.transmission_texture = tr.is_object() ? extension_texture(tr, "transmissionTexture") : LB_NO_HANDLE;
+            const Value& sh = ext["KHR_materials_sheen"];
+            d.sheen_factor = sh.is_object() ? (float)sh["sheenRoughnessFactor"].number(0.0) : 0.f;
+            d.sheen_tint_factor = sh.is_object() ? 1.f : 0.f;
+            const Value& ior = ext["KHR_materials_ior"];
+            d.index_of_refraction = ior.is_object() ? (float)ior["ior"].number(1.0) : 1.f;
+            const Value& cc = ext["KHR_materials_clearcoat"];
+            d.clear_coat_factor = cc.is_object() ? (float)cc["clearcoatFactor"].number(0.0) : 0.f;
+            d.clear_coat_roughness_factor = cc.is_object() ? (float)cc["clearcoatRoughnessFactor"].number(0.0) : 0.f;
+            d.clear_coat_texture = cc.is_object() ? extension_texture(cc, "clearcoatTexture") : LB_NO_HANDLE;
+            d.clear_coat_roughness_texture = cc.is_object() ? extension_texture(cc, "clearcoatRoughnessTexture") : LB_NO_HANDLE;
+            const Value& sp = ext["KHR_materials_specular"];
+            d.specular_factor = sp.is_object() ? (float)sp["specularFactor"].number(0.0) : 0.f;
+            d.specular_tint_factor = sp.is_object() ? 1.f : 0.f;
+            d.tint_texture = sp.is_object() ? extension_texture(sp, "specularColorTexture") : LB_NO_HANDLE;
+            g.materials.push_back(d);
+        }
+        // :127-134 metal-roughness images: green (roughness) is at least 1/255
+        for (Image& im : g.images) if (im.metal_rough) for (size_t p = 0; p < im.px.size(); p += 4) if (im.px[p + 1] < 1) im.px[p + 1] = 1;
+        g.info.materials = (uint32_t)g.materials.size();
+    }
+
+    // GenerateTangentBinary, :734-900
+    static void generate_tangents(Primitive& p) {
+        const size_t nv = p.pos.size() / 3;
+        p.tan.assign(nv * 4, 0.f);
+        const Vec3* pos = reinterpret_cast<const Vec3*>(p.pos.data()); const Vec3* nrm = reinterpret_cast<const Vec3*>(p.nrm.data());
+        const bool have_uv = !p.uv.empty();
+        const float default_uv[3][2] = {{1.f, 1.f}, {0.f, 1.f}, {1.f, 0.f}};
+        for (size_t t = 0; t + 2 < p.idx.size(); t += 3) {
+            const uint32_t ix[3] = {p.idx[t], p.idx[t + 1], p.idx[t + 2]};
+            float uv[3][2];
+            for (int k = 0; k < 3; ++k) { uv[k][0] = have_uv ? p.uv[2 * ix[k]] : default_uv[k][0]; uv[k][1] = have_uv ? p.uv[2 * ix[k] + 1] : default_uv[k][1]; }
+            auto len2 = [](const float* a, const float* b) { const float dx = a[0] - b[0], dy = a[1] - b[1]; return sqrtf(dx * dx + dy * dy); };
+            const float eps = 1.1920928955078125e-07f;
+            if (len2(uv[0], uv[1]) < eps || len2(uv[0], uv[2]) < eps || len2(uv[2], uv[1]) < eps) memcpy(uv, default_uv, sizeof uv);
+            const Vec3 dp1 = pos[ix[1]] - pos[ix[0]], dp2 = pos[ix[2]] - pos[ix[0]];
+            float du1[2] = {uv[1][0] - uv[0][0], uv[1][1] - uv[0][1]}, du2[2] = {uv[2][0] - uv[0][0], uv[2][1] - uv[0][1]};
+            const float cross = du1[0] * du2[1] - du1[1] * du2[0];
+            if (cross == 0.f) { du1[0] = default_uv[1][0] - default_uv[0][0]; du1[1] = default_uv[1][1] - default_uv[0][1]; du2[0] = default_uv[2][0] - default_uv[0][0]; du2[1] = default_uv[2][1] - default_uv[0][1]; }
+            const Vec3 tg = (du2[1] * dp1 - du1[1] * dp2) / (du1[0] * du2[1] - du2[0] * du1[1]);
+            for (int k = 0; k < 3; ++k) {
+                const Vec3 ng = normalize3(nrm[ix[k]]);
+                const Vec3 tangent = normalize3(tg - ng * dot3(ng, tg));
+                float* o = &p.tan[4 * (size_t)ix[k]]; o[0] = tangent.x; o[1] = tangent.y; o[2] = tangent.z; o[3] = 1.f;
+            }
+        }
+    }
+    static void flat_normals(Primitive& p) {
+        const size_t nv = p.pos.size() / 3;
+        p.nrm.assign(nv * 3, 0.f);
+        const Vec3* pos = reinterpret_cast<const Vec3*>(p.pos.data()); Vec3* nrm = reinterpret_cast<Vec3*>(p.nrm.data());
+        for (size_t t = 0; t + 2 < p.idx.size(); t += 3) {
+            const Vec3 n = cross3(pos[p.idx[t + 1]] - pos[p.idx[t]], pos[p.idx[t + 2]] - pos[p.idx[t]]);
+            for (int k = 0; k < 3; ++k) { Vec3& d = nrm[p.idx[t + k]]; d = {d.x + n.x, d.y + n.y, d.z + n.z}; }
+        }
+        for (size_t v = 0; v < nv; ++v) { const float l = sqrtf(dot3(nrm[v], nrm[v])); nrm[v] = l > 0.f ? nrm[v] * (1.0f / l) : Vec3{0.f, 0.f, 1.f}; }
+    }
+    void load_meshes() {
+        const Value& meshes = doc["meshes"];
+        for (size_t mi = 0; mi < meshes.size(); ++mi) {
+            Mesh mesh;
+            const Value& prims = meshes[mi]["primitives"];
+            for (size_t pi = 0; pi < prims.size(); ++pi) {
+                const Value& fp = prims[pi]; const Value& at = fp["attributes"];
+                if (fp["mode"].integer(4) != 4) bad("only triangle lists (mode 4) are supported");
+                if (!at.has("POSITION")) bad("primitive without POSITION");
+                Primitive p;
+                p.pos = float_attribute(at["POSITION"].integer(-1), 3, "POSITION");
+                const size_t nv = p.pos.size() / 3;
+                if (at.has("TEXCOORD_0")) p.uv = float_attribute(at["TEXCOORD_0"].integer(-1), 2, "TEXCOORD_0");
+                if (at.has("NORMAL")) p.nrm = float_attribute(at["NORMAL"].integer(-1), 3, "NORMAL");
+                if (at.has("TANGENT")) p.tan = float_attribute(at["TANGENT"].integer(-1), 4, "TANGENT");
+                if ((!p.uv.empty() && p.uv.size() != nv * 2) || (!p.nrm.empty() && p.nrm.size() != nv * 3) || (!p.tan.empty() && p.tan.size() != nv * 4)) bad("attribute counts differ within a primitive");
+                if (fp.has("indices")) {
+                    uint32_t cs, cc; int64_t ct;
+                    const std::vector<uint8_t> raw = accessor_bytes(fp["indices"].integer(-1), cs, cc, ct);
+                    if (cc != 1 || ct == 5126) bad("indices must be scalar integers");
+                    p.idx.resize(raw.size() / cs);
+                    for (size_t k = 0; k < p.idx.size(); ++k) p.idx[k] = cs == 1 ? raw[k] : cs == 2 ? (uint32_t)(raw[2 * k] | (raw[2 * k + 1] << 8)) : (uint32_t)(raw[4 * k] | (raw[4 * k + 1] << 8) | (raw[4 * k + 2] << 16) | ((uint32_t)raw[4 * k + 3] << 24));
+                } else { p.idx.resize(nv); for (size_t k = 0; k < nv; ++k) p.idx[k] = (uint32_t)k; }
+                p.idx.resize(p.idx.size() / 3 * 3);
+                for (uint32_t v : p.idx) if (v >= nv) bad("index out of range");
+                if (p.nrm.empty()) flat_normals(p);
+                if (p.tan.empty()) generate_tangents(p);
+                if (p.uv.empty()) p.uv.assign(nv * 2, 0.f);                    // InterleaveVertexBuffers leaves a missing stream zero (:902-928)
+                p.material = (int32_t)fp["material"].integer(-1);
+                if (p.material >= (int32_t)g.materials.size()) bad("material index out of range");
+                g.info.triangles += (uint32_t)(p.idx.size() / 3); g.info.vertices += (uint32_t)nv; ++g.info.primitives;
+                mesh.prims.push_back(std::move(p));
+            }
+            g.meshes.push_back(std::move(mesh));
+        }
+        g.info.meshes = (uint32_t)g.meshes.size();
+    }
+
+    Mat4 node_local(const Value& n) const {
+        Mat4 m = mat_identity();
+        if (n["matrix"].size() == 16) for (int k = 0; k < 16; ++k) m.m[k] = (float)n["matrix"][(size_t)k].number(0.0);
+        if (!mat_is_identity(m)) return m;                                     // LoadNodeTransform :994-1025
+        float t[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, s[3] = {1, 1, 1};
+        for (int k = 0; k < 3; ++k) { t[k] = (float)n["translation"][(size_t)k].number(0.0); s[k] = (float)n["scale"][(size_t)k].number(1.0); }
+        for (int k = 0; k < 4; ++k) q[k] = (float)n["rotation"][(size_t)k].number(k == 3 ? 1.0 : 0.0);
+        return mat_trs(t, q, s);
+    }
+    // `parent_world`: world matrix of the parent NODE's transform object; null for root nodes
+    void load_node(int64_t index, const Mat4* parent_world, int depth) {
+        const Value& n = doc["nodes"][(size_t)index];
+        if (index < 0 || n.is_null()) bad("node index out of range");
+        if (depth > 512) bad("node hierarchy too deep (cycle?)");
+        const Mat4 local = node_local(n);
+        const Mat4 with_parent = parent_world ? mat_mul(*parent_world, local) : local;
+        const int64_t mesh = n["mesh"].integer(-1);
+        Mat4 own_world;                                                        // world matrix of node->m_Transform as its children see it
+        if (mesh >= 0) {
+            if (mesh >= (int64_t)g.meshes.size()) bad("mesh index out of range");
+            Instance in; in.mesh = (uint32_t)mesh;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) in.m[r * 4 + c] = with_parent.m[c * 4 + r];
+            g.instances.push_back(in);
+            own_world = local;                                                 // :296-306: only the mesh instance's transform is parented
+        } else own_world = with_parent;
+        const Value& ch = n["children"];
+        for (size_t k = 0; k < ch.size(); ++k) load_node(ch[k].integer(-1), &own_world, depth + 1);
+    }
+    void load_scenes() {
+        const Value& scenes = doc["scenes"];
+        for (size_t s = 0; s < scenes.size(); ++s) { const Value& roots = scenes[s]["nodes"]; for (size_t k = 0; k < roots.size(); ++k) load_node(roots[k].integer(-1), nullptr, 0); }
+        g.info.instances = (uint32_t)g.instances.size();
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+LB_API const char* lb_gltf_last_error(void) { return g_error.c_str(); }
+
+LB_API int lb_gltf_open(const char* path, LbImageDecodeFn decoder, void* user, LbGltf* out) {
+    if (!path || !out) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    try {
+        std::vector<uint8_t> file;
+        if (!read_file(path, file)) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("cannot read ") + path);
+        const std::string p(path); const size_t slash = p.find_last_of("/\\");
+        std::vector<uint8_t> bin; const char* text = reinterpret_cast<const char*>(file.data()); size_t text_len = file.size();
+        if (file.size() >= 12 && memcmp(file.data(), "glTF", 4) == 0) {             // GLB container: header, JSON chunk, optional BIN chunk
+            auto le = [&](size_t at) { return (uint32_t)file[at] | ((uint32_t)file[at + 1] << 8) | ((uint32_t)file[at + 2] << 16) | ((uint32_t)file[at + 3] << 24); };
+            size_t pos = 12; text = nullptr;
+            while (pos + 8 <= file.size()) {
+                const uint32_t len = le(pos), type = le(pos + 4);
+                if (pos + 8 + (size_t)len > file.size()) return gfail(LB_ERR_INVALID_ARGUMENT, "GLB chunk runs past the end of the file");
+                if (type == 0x4E4F534Au && !text) { text = reinterpret_cast<const char*>(file.data() + pos + 8); text_len = len; }
+                else if (type == 0x004E4942u && bin.empty()) bin.assign(file.begin() + pos + 8, file.begin() + pos + 8 + len);
+                pos += 8 + (size_t)len;
+            }
+            if (!text) return gfail(LB_ERR_INVALID_ARGUMENT, "GLB without a JSON chunk");
+        }
+        const Value doc = lb::json::parse(text, text_len);
+        if (!doc.is_object() || !doc.has("asset")) return gfail(LB_ERR_INVALID_ARGUMENT, "not a glTF document");
+        std::unique_ptr<LbGltfOpaque> g(new LbGltfOpaque());
+        Loader L{*g, doc, slash == std::string::npos ? std::string() : p.substr(0, slash + 1), {}, std::move(bin), decoder, user};
+        L.load_buffers(); L.load_images(); L.load_materials(); L.load_meshes(); L.load_scenes();
+        *out = g.release();
+        return LB_OK;
+    } catch (const std::exception& e) { return gfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
+}
+LB_API int lb_gltf_close(LbGltf g) { delete g; return LB_OK; }
+LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out) { if (!g || !out) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument"); *out = g->info; return LB_OK; }
+LB_API int lb_gltf_image(LbGltf g, uint32_t i, const uint8_t** rgba8, uint32_t* w, uint32_t* h, int* srgb, int* decoded) {
+    if (!g || i >= g->images.size()) return gfail(LB_ERR_INVALID_HANDLE, "image");
+    const Image& im = g->images[i];
+    if (rgba8) *rgba8 = im.px.data(); if (w) *w = im.w; if (h) *h = im.h; if (srgb) *srgb = im.srgb ? 1 : 0; if (decoded) *decoded = im.decoded ? 1 : 0;
+    return LB_OK;
+}
+LB_API int lb_gltf_material(LbGltf g, uint32_t i, LbMaterialDesc* out) {
+    if (!g || !out || i >= g->materials.size()) return gfail(LB_ERR_INVALID_HANDLE, "material");
+    *out = g->materials[i]; return LB_OK;
+}
+LB_API int lb_gltf_mesh_primitive_count(LbGltf g, uint32_t mesh, uint32_t* count) {
+    if (!g || !count || mesh >= g->meshes.size()) return gfail(LB_ERR_INVALID_HANDLE, "mesh");
+    *count = (uint32_t)g->meshes[mesh].prims.size(); return LB_OK;
+}
+LB_API int lb_gltf_primitive(LbGltf g, uint32_t mesh, uint32_t prim, LbPrimitiveDesc* out) {
+    if (!g || !out || mesh >= g->meshes.size() || prim >= g->meshes[mesh].prims.size()) return gfail(LB_ERR_INVALID_HANDLE, "primitive");
+    const Primitive& p = g->meshes[mesh].prims[prim];
+    LbPrimitiveDesc d{};
+    d.positions = p.pos.data(); d.position_stride = 12; d.uvs = p.uv.data(); d.uv_stride = 8; d.normals = p.nrm.data(); d.normal_stride = 12;
+    d.tangents = p.tan.data(); d.tangent_stride = 16; d.vertex_count = (uint32_t)(p.pos.size() / 3);
+    d.indices = p.idx.data(); d.index_size = 4; d.index_count = (uint32_t)p.idx.size(); d.material = p.material;
+    *out = d; return LB_OK;
+}
+LB_API int lb_gltf_instance(LbGltf g, uint32_t i, uint32_t* mesh, float* transform16) {
+    if (!g || i >= g->instances.size()) return gfail(LB_ERR_INVALID_HANDLE, "instance");
+    if (mesh) *mesh = g->instances[i].mesh; if (transform16) memcpy(transform16, g->instances[i].m, 64);
+    return LB_OK;
+}
+
+// CreateTexture / CreateMaterial / CreatePrimitive / CreateMesh / AddMesh in the order LumenPTModelConverter::LoadFile issues them (:105-268)
+LB_API int lb_gltf_upload(LbRenderer r, LbGltf g, const float* root16, LbHandle* first_instance, uint32_t* instance_count) {
+    if (!r || !g) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument");
+    auto check = [&](int rc) { if (rc != LB_OK) { g_error = lb_last_error(); throw rc; } };
+    try {
+        std::vector<LbHandle> tex(g->images.size(), LB_NO_HANDLE), mats(g->materials.size(), LB_NO_HANDLE), meshes(g->meshes.size(), LB_NO_HANDLE);
+        for (size_t i = 0; i < g->images.size(); ++i) { const Image& im = g->images[i]; if (im.decoded) check(lb_texture_create(r, im.px.data(), im.w, im.h, im.srgb ? 1 : 0, &tex[i])); }
+        auto map_tex = [&](LbHandle& h) { h = h >= 0 ? tex[(size_t)h] : LB_NO_HANDLE; };
+        for (size_t i = 0; i < g->materials.size(); ++i) {
+            LbMaterialDesc d = g->materials[i];
+            map_tex(d.diffuse_texture); map_tex(d.normal_texture); map_tex(d.metallic_roughness_texture); map_tex(d.emissive_texture);
+            map_tex(d.transmission_texture); map_tex(d.clear_coat_texture); map_tex(d.clear_coat_roughness_texture); map_tex(d.tint_texture);
+            check(lb_material_create(r, &d, &mats[i]));
+        }
+        LbHandle default_material = LB_NO_HANDLE;
+        for (size_t m = 0; m < g->meshes.size(); ++m) {
+            std::vector<LbHandle> prims;
+            for (uint32_t p = 0; p < g->meshes[m].prims.size(); ++p) {
+                LbPrimitiveDesc d; lb_gltf_primitive(g, (uint32_t)m, p, &d);
+                if (d.material >= 0) d.material = mats[(size_t)d.material];
+                else {                                                           // glTF default material (the reference indexes the pool with -1)
+                    if (default_material == LB_NO_HANDLE) {
+                        LbMaterialDesc dm{}; dm.diffuse_color[0] = dm.diffuse_color[1] = dm.diffuse_color[2] = dm.diffuse_color[3] = 1.f; dm.metallic_factor = 1.f; dm.roughness_factor = 1.f; dm.luminance = 1.f; dm.index_of_refraction = 1.f;
+                        dm.diffuse_texture = dm.normal_texture = dm.metallic_roughness_texture = dm.emissive_texture = dm.transmission_texture = dm.clear_coat_texture = dm.clear_coat_roughness_texture = dm.tint_texture = LB_NO_HANDLE;
+                        check(lb_material_create(r, &dm, &default_material));
+                    }
+                    d.material = default_material;
+                }
+                LbHandle h; check(lb_primitive_create(r, &d, &h)); prims.push_back(h);
+            }
+            check(lb_mesh_create(r, prims.data(), (uint32_t)prims.size(), &meshes[m]));
+        }
+        Mat4 root = mat_identity();
+        if (root16) for (int rr = 0; rr < 4; ++rr) for (int c = 0; c < 4; ++c) root.m[c * 4 + rr] = root16[rr * 4 + c];
+        LbHandle first = LB_NO_HANDLE;
+        for (const Instance& in : g->instances) {
+            float m16[16]; memcpy(m16, in.m, 64);
+            if (root16) { Mat4 w; for (int rr = 0; rr < 4; ++rr) for (int c = 0; c < 4; ++c) w.m[c * 4 + rr] = in.m[rr * 4 + c]; const Mat4 t = mat_mul(root, w); for (int rr = 0; rr < 4; ++rr) for (int c = 0; c < 4; ++c) m16[rr * 4 + c] = t.m[c * 4 + rr]; }
+            LbHandle h; check(lb_scene_add_mesh_instance(r, meshes[in.mesh], m16, nullptr, LB_NO_HANDLE, &h));
+            if (first == LB_NO_HANDLE) first = h;
+        }
+        if (first_instance) *first_instance = first;
+        if (instance_count) *instance_count = (uint32_t)g->instances.size();
+        return LB_OK;
+    } catch (int rc) { return rc; }
+}
+
+} // extern "C"

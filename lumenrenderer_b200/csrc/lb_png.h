@@ -1,4 +1,4 @@
-// lb_png.h — 8-bit RGBA PNG encoder for the output stage (host only, no dependencies).
+// lb_png.h — 8-bit RGBA PNG encoder for the output stage and PNG decoder for the glTF ingest (host only, no dependencies).
 //
 // Replaces the screenshot path of the reference: WaveFrontRenderer::GetOutputTexturePixels (LumenPT/src/Framework/
 // WaveFrontRenderer.cpp:1379-1394) feeding stbi_write_png(w, h, 4, pixels, 0) in Sandbox/src/OutputLayer.cpp:882-896.
@@ -115,6 +115,151 @@ inline std::vector<uint8_t> encode_rgba8(const uint8_t* rgba8, uint32_t w, uint3
     uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 6, 0, 0, 0};
     put_chunk(f, "IHDR", ihdr, 13); put_chunk(f, "IDAT", z.data(), z.size()); put_chunk(f, "IEND", nullptr, 0);
     return f;
+}
+
+
+// ---------------------------------------------------------------- decoding (glTF ingest: the reference decodes with stbi_load_from_memory(..., 4),
+// LumenPT/src/Tools/LumenPTModelConverter.cpp:121). Non-interlaced PNG of bit depth 8 or 16, every colour type; output RGBA8.
+struct BitReader {
+    const uint8_t* p; size_t n, pos = 0; uint64_t acc = 0; int bits = 0;
+    BitReader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
+    uint32_t get(int k) { while (bits < k) { acc |= (uint64_t)(pos < n ? p[pos] : 0) << bits; ++pos; bits += 8; } const uint32_t v = (uint32_t)(acc & ((1ull << k) - 1)); acc >>= k; bits -= k; return v; }
+    void align() { acc >>= (bits & 7); bits -= (bits & 7); }
+};
+struct Huffman {
+    uint16_t count[16] = {0}; uint16_t symbol[288];
+    void build(const uint8_t* lengths, int n) {
+        for (int i = 0; i < 16; ++i) count[i] = 0;
+        for (int i = 0; i < n; ++i) ++count[lengths[i]];
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < n; ++i) if (lengths[i]) symbol[offs[lengths[i]]++] = (uint16_t)i;
+    }
+    int decode(BitReader& br) const {                      // canonical code, one bit at a time (textures are decoded once per load)
+        int code = 0, first = 0, index = 0;
+        for (int len = 1; len <= 15; ++len) {
+            code |= (int)br.get(1);
+            const int c = count[len];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+    if (n < 6) return false;
+    BitReader br(src + 2, n - 2);                           // zlib header: CMF, FLG
+    static const uint16_t lbase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+    static const uint8_t lextra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+    static const uint16_t dbase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+    static const uint8_t dextra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+    for (;;) {
+        const uint32_t final = br.get(1), type = br.get(2);
+        if (type == 0) {
+            br.align();
+            const uint32_t len = br.get(16), nlen = br.get(16);
+            if ((len ^ 0xFFFFu) != nlen) return false;
+            for (uint32_t i = 0; i < len; ++i) out.push_back((uint8_t)br.get(8));
+        } else if (type == 1 || type == 2) {
+            Huffman lit, dist; uint8_t lengths[320];
+            if (type == 1) {
+                for (int i = 0; i < 288; ++i) lengths[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                lit.build(lengths, 288);
+                for (int i = 0; i < 30; ++i) lengths[i] = 5;
+                dist.build(lengths, 30);
+            } else {
+                const int hlit = (int)br.get(5) + 257, hdist = (int)br.get(5) + 1, hclen = (int)br.get(4) + 4;
+                static const uint8_t order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < hclen; ++i) cl[order[i]] = (uint8_t)br.get(3);
+                Huffman clh; clh.build(cl, 19);
+                int i = 0;
+                while (i < hlit + hdist) {
+                    const int sym = clh.decode(br);
+                    if (sym < 0) return false;
+                    if (sym < 16) lengths[i++] = (uint8_t)sym;
+                    else {
+                        uint8_t prev = 0; int rep;
+                        if (sym == 16) { if (i == 0) return false; prev = lengths[i - 1]; rep = 3 + (int)br.get(2); }
+                        else if (sym == 17) rep = 3 + (int)br.get(3);
+                        else rep = 11 + (int)br.get(7);
+                        if (i + rep > hlit + hdist) return false;
+                        while (rep--) lengths[i++] = prev;
+                    }
+                }
+                lit.build(lengths, hlit); dist.build(lengths + hlit, hdist);
+            }
+            for (;;) {
+                const int sym = lit.decode(br);
+                if (sym < 0) return false;
+                if (sym < 256) out.push_back((uint8_t)sym);
+                else if (sym == 256) break;
+                else {
+                    if (sym > 285) return false;
+                    const uint32_t len = lbase[sym - 257] + br.get(lextra[sym - 257]);
+                    const int ds = dist.decode(br);
+                    if (ds < 0 || ds > 29) return false;
+                    const uint32_t d = dbase[ds] + br.get(dextra[ds]);
+                    if (d > out.size()) return false;
+                    const size_t from = out.size() - d;
+                    for (uint32_t k = 0; k < len; ++k) out.push_back(out[from + k]);
+                }
+            }
+        } else return false;
+        if (final) break;
+        if (br.pos > br.n + 8) return false;
+    }
+    return true;
+}
+inline bool is_png(const uint8_t* p, size_t n) { static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A}; return n >= 8 && memcmp(p, sig, 8) == 0; }
+// false = not a PNG this decoder handles (interlaced, bit depth < 8, damaged)
+inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rgba, uint32_t& w, uint32_t& h) {
+    if (!is_png(file, n)) return false;
+    size_t pos = 8; std::vector<uint8_t> idat, plte, trns; int depth = 0, colour = 0, lace = 0; w = h = 0;
+    auto be = [&](size_t at) { return ((uint32_t)file[at] << 24) | ((uint32_t)file[at + 1] << 16) | ((uint32_t)file[at + 2] << 8) | file[at + 3]; };
+    while (pos + 12 <= n) {
+        const uint32_t len = be(pos); const uint8_t* type = file + pos + 4; const uint8_t* body = file + pos + 8;
+        if (pos + 12 + (size_t)len > n) return false;
+        if (!memcmp(type, "IHDR", 4) && len >= 13) { w = be(pos + 8); h = be(pos + 12); depth = body[8]; colour = body[9]; lace = body[12]; }
+        else if (!memcmp(type, "PLTE", 4)) plte.assign(body, body + len);
+        else if (!memcmp(type, "tRNS", 4)) trns.assign(body, body + len);
+        else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+        else if (!memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (!w || !h || lace || (depth != 8 && depth != 16)) return false;
+    const int channels = colour == 0 ? 1 : colour == 2 ? 3 : colour == 3 ? 1 : colour == 4 ? 2 : colour == 6 ? 4 : 0;
+    if (!channels || (colour == 3 && depth != 8)) return false;
+    const size_t bpp = (size_t)channels * (depth / 8), stride = bpp * w;
+    std::vector<uint8_t> raw; raw.reserve((stride + 1) * h);
+    if (!inflate(idat.data(), idat.size(), raw) || raw.size() < (stride + 1) * h) return false;
+    std::vector<uint8_t> img(stride * h);
+    for (uint32_t y = 0; y < h; ++y) {
+        const uint8_t* in = raw.data() + (size_t)y * (stride + 1); const int f = in[0]; ++in;
+        uint8_t* row = img.data() + (size_t)y * stride; const uint8_t* up = y ? row - stride : nullptr;
+        for (size_t x = 0; x < stride; ++x) {
+            const int a = x >= bpp ? row[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+            int pred = 0;
+            if (f == 1) pred = a; else if (f == 2) pred = b; else if (f == 3) pred = (a + b) >> 1;
+            else if (f == 4) { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            else if (f != 0) return false;
+            row[x] = (uint8_t)(in[x] + pred);
+        }
+    }
+    rgba.resize((size_t)w * h * 4);
+    const size_t step = depth / 8;                            // 16-bit samples: the high byte (what stb's 8-bit interface returns)
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        const uint8_t* s = img.data() + i * bpp; uint8_t* d = rgba.data() + i * 4;
+        switch (colour) {
+            case 0: d[0] = d[1] = d[2] = s[0]; d[3] = 255; break;
+            case 2: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = 255; break;
+            case 3: { const size_t k = s[0]; d[0] = 3 * k + 2 < plte.size() ? plte[3 * k] : 0; d[1] = 3 * k + 2 < plte.size() ? plte[3 * k + 1] : 0; d[2] = 3 * k + 2 < plte.size() ? plte[3 * k + 2] : 0; d[3] = k < trns.size() ? trns[k] : 255; break; }
+            case 4: d[0] = d[1] = d[2] = s[0]; d[3] = s[step]; break;
+            default: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = s[3 * step]; break;
+        }
+    }
+    return true;
 }
 
 inline bool write_file(const char* path, const std::vector<uint8_t>& bytes) {

@@ -943,6 +943,49 @@ LB_API int lo_frame_stats(LbRenderer r, const char** names, float* micros, uint3
     if (names) *names = R_->stats_names.c_str(); if (count) *count = n; return LB_OK;
 }
 LB_API int lo_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* count) { CHECK_R; const uint32_t n = cap < 8 ? cap : 8; memcpy(v, R_->counters, n * 8); if (count) *count = n; return LB_OK; }
+// ---- output stage mirror (test infrastructure): PNG with STORED deflate blocks — an encoder independent of the product's, so that the
+// decoded pixels of both files can be compared; FrameStats JSON in the same shape.
+static uint32_t crc32_bytes(const uint8_t* p, size_t n) { uint32_t c = ~0u; for (size_t i = 0; i < n; ++i) { c ^= p[i]; for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u))); } return ~c; }
+static void be32(std::vector<uint8_t>& f, uint32_t v) { f.push_back(v >> 24); f.push_back(v >> 16); f.push_back(v >> 8); f.push_back(v); }
+static void chunk(std::vector<uint8_t>& f, const char* type, const std::vector<uint8_t>& d) {
+    be32(f, (uint32_t)d.size()); const size_t at = f.size(); f.insert(f.end(), type, type + 4); f.insert(f.end(), d.begin(), d.end()); be32(f, crc32_bytes(f.data() + at, d.size() + 4));
+}
+LB_API int lo_save_png(LbRenderer r, const char* path) {
+    CHECK_R; if (!path || !*path) return fail(LB_ERR_INVALID_ARGUMENT, "path");
+    const uint32_t w = R_->st.width, h = R_->st.height; const size_t stride = (size_t)w * 4;
+    std::vector<uint8_t> raw; raw.reserve((stride + 1) * h);
+    for (uint32_t y = 0; y < h; ++y) { raw.push_back(0); raw.insert(raw.end(), R_->ldr.begin() + (size_t)y * stride, R_->ldr.begin() + (size_t)(y + 1) * stride); }
+    std::vector<uint8_t> z = {0x78, 0x01}; uint32_t a = 1, b = 0;
+    for (size_t at = 0; at < raw.size() || at == 0; at += 65535) {
+        const size_t n = std::min<size_t>(65535, raw.size() - at); const bool last = at + n >= raw.size();
+        z.push_back(last ? 1 : 0); z.push_back(n & 255); z.push_back(n >> 8); z.push_back(~n & 255); z.push_back((~n >> 8) & 255);
+        z.insert(z.end(), raw.begin() + at, raw.begin() + at + n);
+        if (last) break;
+    }
+    for (uint8_t v : raw) { a = (a + v) % 65521u; b = (b + a) % 65521u; }
+    be32(z, (b << 16) | a);
+    std::vector<uint8_t> f = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A}, ihdr;
+    be32(ihdr, w); be32(ihdr, h); ihdr.insert(ihdr.end(), {8, 6, 0, 0, 0});
+    chunk(f, "IHDR", ihdr); chunk(f, "IDAT", z); chunk(f, "IEND", {});
+    FILE* fp = fopen(path, "wb"); if (!fp) return fail(LB_ERR_INVALID_ARGUMENT, "cannot write file");
+    const bool ok = fwrite(f.data(), 1, f.size(), fp) == f.size(); fclose(fp);
+    return ok ? LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "short write");
+}
+LB_API int lo_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* needed) {
+    CHECK_R;
+    static const char* names[8] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes", "bvh_bytes"};
+    std::vector<std::pair<std::string, double>> times;
+    for (auto& s : R_->stats) { bool found = false; for (auto& t : times) if (t.first == s.first) { t.second += s.second; found = true; } if (!found) times.push_back({s.first, s.second}); }
+    char num[64];
+    std::string o = "{\"frame_id\": " + std::to_string(R_->frame_index) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
+    for (size_t i = 0; i < times.size(); ++i) { snprintf(num, sizeof num, "%.3f", times[i].second); o += std::string(i ? ", \"" : "\"") + times[i].first + "\": " + num; }
+    o += "}, \"counters\": {";
+    for (int i = 0; i < 8; ++i) o += std::string(i ? ", \"" : "\"") + names[i] + "\": " + std::to_string(R_->counters[i]);
+    o += "}}";
+    if (needed) *needed = o.size() + 1;
+    if (!json || cap < o.size() + 1) return (json || cap) ? fail(LB_ERR_INVALID_ARGUMENT, "buffer too small") : (needed ? (int)LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "null"));
+    memcpy(json, o.c_str(), o.size() + 1); return LB_OK;
+}
 LB_API int lo_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) { CHECK_R; *p = R_->accum.data(); *bytes = R_->accum.size() * 16; *frames = R_->blend_count; return LB_OK; }
 LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); const float inv = 1.0f / (float)total;
     for (size_t i = 0; i < R_->accum.size(); ++i) R_->combined[i] = {R_->accum[i].x * inv, R_->accum[i].y * inv, R_->accum[i].z * inv, R_->accum[i].w * inv}; R_->write_ldr(); return LB_OK; }
