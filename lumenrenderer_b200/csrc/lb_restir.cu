@@ -100,42 +100,73 @@ __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __res
 //    evaluation, which the warp executes max-over-lanes(survivors) times instead of 32. Phase A leaves the xorshift state in
 //    front of every candidate in shared memory, so every random number is the one the sequential loop of the reference
 //    would have drawn.
+//  * All 256 pixels of a block share one light bag (canonical choice of hazard 1: bag = WangHash(seed + pixel / 256)). The block takes
+//    256-pixel groups from a device ticket and first stages the group's bag — 1000 entries, each the full light record + its bag
+//    pdf, 72 KB — in shared memory. A candidate fetch is then 4-5 shared-memory reads instead of a dependent chain of random
+//    global gathers (bag entry -> 64-byte light record): ncu showed the first version bound by the L1 data pipe
+//    (l1tex__data_pipe_lsu_wavefronts 77 % of peak, ~8.5 wavefronts per request, profiles/r01_m_frame.md), not by instruction issue.
+struct BagSmem {
+    float4* g0;     // p0.xyz, p1.x
+    float4* g1;     // p1.yz, p2.xy
+    float4* g2;     // p2.z, normal.xyz
+    float4* rad;    // radiance.xyz, -
+    float2* pa;     // bag pdf, area
+};
+constexpr size_t kRisBagBytes = (size_t)kLightsPerBag * (4 * sizeof(float4) + sizeof(float2));
+constexpr size_t kRisSmemBytes = kRisBagBytes + (size_t)kPrimarySamples * kBlock * sizeof(uint32_t);
+
 struct BagCandidate { LightSample ls; float bag_pdf; };
-LB_D BagCandidate draw_candidate(const SceneView& sc, const uint2* __restrict__ picked, uint32_t& s) {
-    BagCandidate c;
+// geometry of the next candidate of stream `s` (position on the light, normal, area, bag pdf) + its bag slot
+LB_D uint32_t draw_candidate_geom(const BagSmem& b, uint32_t& s, BagCandidate& c) {
     const float r = rand_f(s);
-    const uint2 be = __ldg(&picked[(int)roundf((float)(kLightsPerBag - 1u) * r)]);
-    const DevLight l = load_light(sc, be.x);
+    const uint32_t slot = (uint32_t)(int)roundf((float)(kLightsPerBag - 1u) * r);
+    const float4 a = b.g0[slot], bb = b.g1[slot], cc = b.g2[slot]; const float2 pa = b.pa[slot];
     const float u = rand_f(s), v = rand_f(s) * (1.f - u);
-    c.ls.radiance = l.radiance; c.ls.normal = l.normal; c.ls.area = l.area; c.ls.contribution = f3(0.f); c.ls.pdf = 0.f;
-    c.ls.position = l.p0 + ((l.p1 - l.p0) * u) + ((l.p2 - l.p0) * v);
-    c.bag_pdf = __uint_as_float(be.y);
-    return c;
+    const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(a.w, bb.x, bb.y), p2 = f3(bb.z, bb.w, cc.x);
+    c.ls.normal = f3(cc.y, cc.z, cc.w); c.ls.area = pa.y; c.ls.contribution = f3(0.f); c.ls.pdf = 0.f;
+    c.ls.position = p0 + ((p1 - p0) * u) + ((p2 - p0) * v);
+    c.bag_pdf = pa.x;
+    return slot;
 }
+
+extern __shared__ __align__(16) unsigned char ris_smem[];
 
 __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t* ticket, uint32_t seed) {
     static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
-    const uint32_t lane = threadIdx.x & 31u;
+    static_assert(kBlock == 256, "one block = one 256-pixel bag group");
     const size_t np = fv.npix;
+    BagSmem bag;
+    bag.g0 = reinterpret_cast<float4*>(ris_smem); bag.g1 = bag.g0 + kLightsPerBag; bag.g2 = bag.g1 + kLightsPerBag; bag.rad = bag.g2 + kLightsPerBag;
+    bag.pa = reinterpret_cast<float2*>(bag.rad + kLightsPerBag);
     // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
     // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
-    __shared__ uint32_t s_state[kPrimarySamples][kBlock];
+    uint32_t (*s_state)[kBlock] = reinterpret_cast<uint32_t (*)[kBlock]>(ris_smem + kRisBagBytes);
+    __shared__ uint32_t s_base;
     for (;;) {
-        // 32 pixels per warp and turn, handed out by a device ticket: the work per pixel varies (sky / emissive pixels cost
+        // 256 pixels per block and turn, handed out by a device ticket: the work per pixel varies (sky / emissive pixels cost
         // nothing), a static split would leave SMs idle at the end
-        uint32_t base = 0u;
-        if (lane == 0u) base = atomicAdd(ticket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        __syncthreads();                                    // the previous group's bag is no longer read
+        if (threadIdx.x == 0u) s_base = atomicAdd(ticket, (uint32_t)kBlock);
+        __syncthreads();
+        const uint32_t base = s_base;
         if (base >= fv.npix) break;
-        const uint32_t i = base + lane;
+        uint32_t bag_seed = wang_hash(seed + base / 256u);
+        const int bag_index = (int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
+        const uint2* picked = bags + (size_t)bag_index * kLightsPerBag;
+        for (uint32_t e = threadIdx.x; e < kLightsPerBag; e += kBlock) {
+            const uint2 be = __ldg(&picked[e]);
+            const float4* lp = reinterpret_cast<const float4*>(sc.lights + be.x);
+            const float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d = __ldg(lp + 3);
+            bag.g0[e] = a; bag.g1[e] = b; bag.g2[e] = c; bag.rad[e] = make_float4(d.x, d.y, d.z, 0.f); bag.pa[e] = make_float2(__uint_as_float(be.y), d.w);
+        }
+        __syncthreads();
+
+        const uint32_t i = base + threadIdx.x;
         bool valid = i < fv.npix;
         Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
         px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
         if (valid && surface_flags(fv.surf_cur, np, i)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); valid = false; }
         if (valid) surface_load_shading(fv.surf_cur, np, i, px);
-        uint32_t bag_seed = wang_hash(seed + i / 256u);
-        const int bag = (int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
-        const uint2* picked = bags + (size_t)bag * kLightsPerBag;
         const uint32_t s0 = wang_hash(seed + wang_hash(i));
         Reservoir fresh = reservoir_zero();
 
@@ -146,7 +177,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 #pragma unroll 2
             for (uint32_t k = 0; k < kPrimarySamples; ++k) {
                 s_state[k][threadIdx.x] = sa;
-                const BagCandidate c = draw_candidate(sc, picked, sa);
+                BagCandidate c; draw_candidate_geom(bag, sa, c);
                 ResampleGeom g;
                 const bool have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
                 // ordered unless the update is provably a pure count increment: weight 0 / bag_pdf exactly 0 (bag_pdf neither 0 nor NaN)
@@ -168,7 +199,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
             if (active) {
                 const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
                 sb = s_state[k][threadIdx.x];
-                c = draw_candidate(sc, picked, sb);
+                const uint32_t slot = draw_candidate_geom(bag, sb, c);
+                c.ls.radiance = f3(bag.rad[slot]);
                 have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
             }
             __syncwarp();
@@ -326,7 +358,8 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     uint32_t seed = wang_hash(a.seed);
     k_fill_bags<<<grid_for(kNumBags * kLightsPerBag, kBlock), kBlock, 0, st>>>(sc, rb.bags, a.seed); LB_LAUNCH_CHECK();
     seed = wang_hash(seed);
-    k_ris<<<cfg.sms * 2, kBlock, 0, st>>>(fv, sc, rb.bags, &fv.counters[CNT_TICKET0 + ticket++], seed); LB_LAUNCH_CHECK();
+    LB_CUDA(cudaFuncSetAttribute(k_ris, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRisSmemBytes));      // per device; a host-side setting, no launch
+    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, &fv.counters[CNT_TICKET0 + ticket++], seed); LB_LAUNCH_CHECK();
     lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
     k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
