@@ -173,6 +173,10 @@ LB_API int lb_scene_clear(LbRenderer r);
 /* ---- camera: Camera::GetVectorData, LM/Renderer/Camera.cpp:79-93,122-140 ---- */
 /* position + rotation quaternion (w,x,y,z); fovY is the reference's hard-coded 90 degrees (Camera.h:63) unless overridden. */
 LB_API int lb_camera_set_pose(LbRenderer r, const float* position3, const float* rotation_wxyz);
+/* The camera's world matrix as the reference keeps it (Camera::GetMatrixData's current matrix, LM/Renderer/Camera.cpp:95-104,128-140:
+ * columns right / up / forward / position), given ROW-major (= glm::transpose of it), float precision preserved. Replaces the pose
+ * until the next lb_camera_set_pose. This is what an adapter holding only a `Camera` object passes (it has no rotation getter). */
+LB_API int lb_camera_set_matrix(LbRenderer r, const float* world16_row_major);
 LB_API int lb_camera_set_fov_y(LbRenderer r, float degrees);
 /* Camera::SetMinMaxRenderDistance, LM/Renderer/Camera.h:36-37,60 (default 0.1, 1000): normalisation range of the depth side output */
 LB_API int lb_camera_set_min_max_distance(LbRenderer r, float min_distance, float max_distance);

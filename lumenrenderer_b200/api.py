@@ -150,6 +150,7 @@ _SIGS = {
     "scene_add_volume_instance": [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.POINTER(C.c_int32)],
     "scene_clear": [C.c_void_p],
     "camera_set_pose": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "camera_set_matrix": [C.c_void_p, C.c_void_p],
     "camera_set_fov_y": [C.c_void_p, C.c_float],
     "set_render_resolution": [C.c_void_p, C.c_uint32, C.c_uint32],
     "get_render_resolution": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
@@ -402,6 +403,11 @@ class Renderer:
         self.b.check(self.b.camera_set_pose(self._h, p.ctypes.data, q.ctypes.data))
         if fov_y is not None:
             self.b.check(self.b.camera_set_fov_y(self._h, fov_y))
+
+    def set_camera_matrix(self, world_row_major):
+        """Camera world matrix (columns right / up / forward / position), row-major: Camera::GetMatrixData, Camera.cpp:95-104."""
+        m = _f32(world_row_major, (16,))
+        self.b.check(self.b.camera_set_matrix(self._h, m.ctypes.data))
 
     def set_render_resolution(self, width: int, height: int):
         self.b.check(self.b.set_render_resolution(self._h, width, height))

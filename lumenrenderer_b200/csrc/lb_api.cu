@@ -74,6 +74,7 @@ struct Renderer {
 
     // ---- frame state
     float3 cam_pos = f3(0.f); float cam_q[4] = {1, 0, 0, 0}; float fov_y = 90.f;
+    bool cam_from_matrix = false; float cam_m[16];        // lb_camera_set_matrix: the caller's float matrix, used as is
     double prev_cam[16]; bool have_prev_cam = false;
     uint32_t frame_index = 0, surf_cur = 0, res_cur = 0, blend_count = 0;
     uint32_t launches_last_frame = 0;
@@ -282,6 +283,7 @@ struct Renderer {
 
     // ---- camera (Camera.cpp:79-93,122-140): row-major world matrix, columns right/up/forward/position
     void camera_matrix(double m[16]) const {
+        if (cam_from_matrix) { for (int k = 0; k < 16; ++k) m[k] = cam_m[k]; return; }
         const double w = cam_q[0], x = cam_q[1], y = cam_q[2], z = cam_q[3];
         const double c0[3] = {1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y)};
         const double c1[3] = {2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x)};
@@ -527,7 +529,10 @@ LB_API int lb_scene_add_volume_instance(LbRenderer r, LbHandle vol, const float*
 }
 LB_API int lb_scene_clear(LbRenderer r) { return guarded(R_, [&]() { R_->instances.clear(); R_->vinstances.clear(); R_->scene_dirty = true; return (int)LB_OK; }); }
 LB_API int lb_camera_set_pose(LbRenderer r, const float* p, const float* q) {
-    return guarded(R_, [&]() { if (!p || !q) return fail(LB_ERR_INVALID_ARGUMENT, "null"); R_->cam_pos = f3(p[0], p[1], p[2]); memcpy(R_->cam_q, q, 16); return (int)LB_OK; });
+    return guarded(R_, [&]() { if (!p || !q) return fail(LB_ERR_INVALID_ARGUMENT, "null"); R_->cam_pos = f3(p[0], p[1], p[2]); memcpy(R_->cam_q, q, 16); R_->cam_from_matrix = false; return (int)LB_OK; });
+}
+LB_API int lb_camera_set_matrix(LbRenderer r, const float* m) {
+    return guarded(R_, [&]() { if (!m) return fail(LB_ERR_INVALID_ARGUMENT, "null"); memcpy(R_->cam_m, m, 64); R_->cam_pos = f3(m[3], m[7], m[11]); R_->cam_from_matrix = true; return (int)LB_OK; });
 }
 LB_API int lb_camera_set_fov_y(LbRenderer r, float deg) {
     return guarded(R_, [&]() { if (!(deg > 0.f && deg < 180.f)) return fail(LB_ERR_INVALID_ARGUMENT, "fov"); R_->fov_y = deg; return (int)LB_OK; });

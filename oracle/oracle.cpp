@@ -67,6 +67,7 @@ struct Renderer {
     std::vector<Texture> textures; std::vector<Material> materials; std::vector<Primitive> prims; std::vector<Mesh> meshes;
     std::vector<Instance> instances; std::vector<Entry> entries; std::vector<Volume> volumes; std::vector<VolumeInstance> vinstances;
     V3 cam_pos{0, 0, 0}; float cam_q[4]{1, 0, 0, 0}; float fov_y = 90.f;
+    bool cam_from_matrix = false; float cam_m[16];
     double prev_cam[16]; bool have_prev_cam = false;
     bool scene_dirty = true;
     // derived scene
@@ -238,6 +239,7 @@ struct Renderer {
 
     // ------------------------------------------------------------------ camera (LM/Renderer/Camera.cpp:79-93,122-140)
     void camera_matrix(double m[16]) const {   // row-major world matrix (columns right, up, forward, position)
+        if (cam_from_matrix) { for (int k = 0; k < 16; ++k) m[k] = cam_m[k]; return; }
         const double w = cam_q[0], x = cam_q[1], y = cam_q[2], z = cam_q[3];
         const double c0[3] = {1 - 2 * (y * y + z * z), 2 * (x * y + w * z), 2 * (x * z - w * y)};
         const double c1[3] = {2 * (x * y - w * z), 1 - 2 * (x * x + z * z), 2 * (y * z + w * x)};
@@ -902,7 +904,8 @@ LB_API int lo_scene_add_volume_instance(LbRenderer r, LbHandle vol, const float*
     R_->vinstances.push_back(vi); if (out) *out = (LbHandle)R_->vinstances.size() - 1; return LB_OK;
 }
 LB_API int lo_scene_clear(LbRenderer r) { CHECK_R; R_->instances.clear(); R_->vinstances.clear(); R_->scene_dirty = true; return LB_OK; }
-LB_API int lo_camera_set_pose(LbRenderer r, const float* p, const float* q) { CHECK_R; if (!p || !q) return fail(LB_ERR_INVALID_ARGUMENT, "null"); R_->cam_pos = {p[0], p[1], p[2]}; memcpy(R_->cam_q, q, 16); return LB_OK; }
+LB_API int lo_camera_set_pose(LbRenderer r, const float* p, const float* q) { CHECK_R; if (!p || !q) return fail(LB_ERR_INVALID_ARGUMENT, "null"); R_->cam_pos = {p[0], p[1], p[2]}; memcpy(R_->cam_q, q, 16); R_->cam_from_matrix = false; return LB_OK; }
+LB_API int lo_camera_set_matrix(LbRenderer r, const float* m) { CHECK_R; if (!m) return fail(LB_ERR_INVALID_ARGUMENT, "null"); memcpy(R_->cam_m, m, 64); R_->cam_pos = {m[3], m[7], m[11]}; R_->cam_from_matrix = true; return LB_OK; }
 LB_API int lo_camera_set_fov_y(LbRenderer r, float deg) { CHECK_R; if (!(deg > 0.f && deg < 180.f)) return fail(LB_ERR_INVALID_ARGUMENT, "fov"); R_->fov_y = deg; return LB_OK; }
 LB_API int lo_camera_set_min_max_distance(LbRenderer r, float mn, float mx) { CHECK_R; if (!(mx > mn)) return fail(LB_ERR_INVALID_ARGUMENT, "min/max distance"); R_->cam_min_d = mn; R_->cam_max_d = mx; return LB_OK; }
 // G-buffer side outputs: GPUExtractDepthData.cu:6-72, GPUExtractNRD_DLSSdata.cu:6-89 (half4 normal+roughness), GPUPostProcessingEffects.cu:13-50 (albedo)
