@@ -316,6 +316,69 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_bands(args):
+    """--mode bands: ONE frame split into row bands across the ranks (single-frame latency; strong scaling). Every rank
+    renders its rows + a 60-row ReSTIR halo, then the owned rows are gathered on rank 0 device to device (NCCL point-to-point on
+    the renderer's stream) inside the timed region. A step = one complete 2560x1440 frame assembled on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import lumenrenderer_b200 as lr
+    from lumenrenderer_b200 import sharding
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = args.width, args.height
+    st, (y0, y1, h0, h1) = sharding.band_settings(settings(args, W, H), rank, world)
+    st.device = local
+    bands = sharding.band_partition(H, world, width=W)
+    scene = workload_scene(args)
+    r = lr.Renderer(st)
+    r.load_scene(scene)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); r.set_stream(stream.cuda_stream)
+    ptr, nbytes = r.hdr_buffer()
+    rows = torch.as_tensor(DevPtr(ptr, nbytes // 4), device=torch.device("cuda", local)).view(h1 - h0, W, 4)
+    full = torch.zeros((H, W, 4), device="cuda") if rank == 0 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r.render_frames(1); sharding.gather_bands(rows, full, bands, rank)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time(); e0.record(stream)
+    for _ in range(args.steps):
+        r.render_frames(1)
+        sharding.gather_bands(rows, full, bands, rank)
+    e1.record(stream)
+    barrier(); t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    fc = r.frame_counters()
+    rays = float(rays_of(fc)) * args.steps
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+        t = torch.tensor([rays], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM); rays = float(t[0])
+    if rank == 0:
+        finite = bool(torch.isfinite(full).all()) and float(full[..., :3].sum()) > 0
+        rendered_rows = sum(b[3] - b[2] for b in bands)
+        line = {"metric": METRIC, "mode": "bands", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "fps": args.steps / (ms * 1e-3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config_of(args, W, H, "gpu"), parallelism=f"row bands x{world} with a {sharding.RESTIR_HALO}-row ReSTIR halo, gather on rank 0"),
+                "bands": [list(b) for b in bands], "rows_rendered_over_rows_owned": rendered_rows / H, "gather_bytes_per_step": (H - (y1 - y0)) * W * 16,
+                "gpu_launches": fc["kernel_launches"] * args.steps, "clocks": clocks, "output_finite": finite}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,9 +391,13 @@ def main():
     ap.add_argument("--detail", type=float, default=0.78)
     ap.add_argument("--texture-size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="samples", choices=["samples", "bands"],
+                    help="multi-GPU partitioning: independent sample streams + one reduce (default, weak scaling) or row bands of one frame + one gather (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "bands":
+        run_bands(args)
     else:
         run_gpu(args)
 

@@ -72,7 +72,14 @@ typedef struct LbSettings {
     uint32_t first_frame_count;/* value of the reference's static frameCount for the first frame minus 1 (0 = reference);
                                   sample sharding sets 2*rank so that streams do not overlap */
     uint32_t frame_count_stride;/* frameCount advance per frame; 0 means the reference's 2 (SURVEY hazard 10) */
-    uint32_t reserved[5];
+    /* Row band of a larger frame (image-tile sharding across GPUs): this renderer produces rows
+     * [band_row0, band_row0 + height) of a frame that is band_full_height rows tall (0 = not a band: the frame is `height` rows).
+     * Camera, jitter, motion vectors and every per-pixel random stream use the pixel's position in the FULL frame, so a band
+     * pixel whose ReSTIR neighbourhood lies inside the band equals the same pixel of the full-frame render bit for bit.
+     * band_row0 * width must be a multiple of 256 (the RIS light-bag group, ReSTIRKernels.cu:423). */
+    uint32_t band_row0;
+    uint32_t band_full_height;
+    uint32_t reserved[3];
 } LbSettings;
 
 /* LumenRenderer::MaterialData, LM/Renderer/LumenRenderer.h:64-112 (defaults :66-82).
@@ -267,6 +274,9 @@ LB_API int lb_gltf_upload(LbRenderer r, LbGltf g, const float* root_transform16,
 /* ---- multi-GPU / framework interop ---- */
 /* Device pointer of the fp32 RGBA accumulation buffer (sum over blended frames) and its frame count, for an
  * external NCCL reduce; lb_resolve_accum divides by `total_frames` and refreshes HDR/LDR. */
+/* Device pointer of the merged fp32 RGBA frame (what lb_read_hdr copies): lets a multi-GPU host gather row bands device to device
+ * (NCCL) on the renderer's stream. Valid until the resolution changes. The oracle returns its host buffer. */
+LB_API int lb_hdr_buffer(LbRenderer r, void** device_ptr, size_t* bytes);
 LB_API int lb_accum_buffer(LbRenderer r, void** device_ptr, size_t* bytes, uint32_t* frames);
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
 /* Run all work on an externally owned CUDA stream (e.g. torch's current stream); 0/NULL = the renderer's own. */

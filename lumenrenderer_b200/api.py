@@ -30,7 +30,7 @@ class LbSettings(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("blend_output", C.c_uint32),
                 ("restir", C.c_uint32), ("restir_temporal", C.c_uint32), ("restir_spatial", C.c_uint32),
                 ("device", C.c_int32), ("volume_mode", C.c_uint32), ("first_frame_count", C.c_uint32),
-                ("frame_count_stride", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("frame_count_stride", C.c_uint32), ("band_row0", C.c_uint32), ("band_full_height", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class LbMaterialDesc(C.Structure):
@@ -119,6 +119,8 @@ class Settings:
     volume_mode: int = VOLUME_COMPAT
     first_frame_count: int = 0
     frame_count_stride: int = 0
+    band_row0: int = 0
+    band_full_height: int = 0
 
     def to_c(self) -> LbSettings:
         s = LbSettings()
@@ -151,6 +153,7 @@ _SIGS = {
     "scene_clear": [C.c_void_p],
     "camera_set_pose": [C.c_void_p, C.c_void_p, C.c_void_p],
     "camera_set_matrix": [C.c_void_p, C.c_void_p],
+    "hdr_buffer": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
     "camera_set_fov_y": [C.c_void_p, C.c_float],
     "set_render_resolution": [C.c_void_p, C.c_uint32, C.c_uint32],
     "get_render_resolution": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
@@ -518,6 +521,12 @@ class Renderer:
         buf = C.create_string_buffer(need.value)
         self.b.check(self.b.frame_stats_json(self._h, buf, need.value, None))
         return json.loads(buf.value.decode())
+
+    def hdr_buffer(self):
+        """(pointer, bytes) of the merged fp32 RGBA frame — a device pointer for the CUDA library, host memory for the oracle."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self.b.check(self.b.hdr_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def accum_buffer(self):
         p, nbytes, frames = C.c_void_p(), C.c_size_t(), C.c_uint32()

@@ -94,6 +94,7 @@ struct Renderer {
     std::thread render_thread; std::atomic<bool> stop_flag{false}; std::string thread_error;
 
     uint32_t npix() const { return st.width * st.height; }
+    uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
     static TraceTuning trace_tuning() {
         TraceTuning t;
@@ -294,7 +295,7 @@ struct Renderer {
     CameraBasis camera_basis() const {
         double m[16]; camera_matrix(m);
         const float half_y = 1.0f * tanf((fov_y * 0.01745329251994329576923690768489f) * 0.5f);
-        const float half_x = half_y * ((float)st.width / (float)st.height);
+        const float half_x = half_y * ((float)st.width / (float)full_height());
         CameraBasis c;
         c.eye = cam_pos;
         c.U = f3((float)m[0], (float)m[4], (float)m[8]) * half_x;
@@ -309,7 +310,7 @@ struct Renderer {
         double view[16];
         for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) view[r * 4 + k] = c[k * 4 + r]; view[r * 4 + 3] = -(c[0 * 4 + r] * c[3] + c[1 * 4 + r] * c[7] + c[2 * 4 + r] * c[11]); }
         view[12] = view[13] = view[14] = 0; view[15] = 1;
-        const double aspect = (double)st.width / (double)st.height, zn = 0.5, zf = 10000.0, th = tan((fov_y * 0.01745329251994329576923690768489) / 2.0);
+        const double aspect = (double)st.width / (double)full_height(), zn = 0.5, zf = 10000.0, th = tan((fov_y * 0.01745329251994329576923690768489) / 2.0);
         double P[16] = {1.0 / (aspect * th), 0, 0, 0, 0, 1.0 / th, 0, 0, 0, 0, -(zf + zn) / (zf - zn), -(2.0 * zf * zn) / (zf - zn), 0, 0, -1, 0};
         for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) { double s = 0; for (int j = 0; j < 4; ++j) s += P[r * 4 + j] * view[j * 4 + k]; out[r * 4 + k] = (float)s; }
     }
@@ -317,6 +318,7 @@ struct Renderer {
     FrameView frame_view() {
         FrameView fv;
         fv.width = st.width; fv.height = st.height; fv.npix = npix();
+        fv.row0 = st.band_row0; fv.full_height = full_height(); fv.pix0 = st.band_row0 * st.width;
         for (int q = 0; q < 2; ++q) fv.rays[q] = RayQueue{d_rays[q][0].p, d_rays[q][1].p, d_rays[q][2].p};
         fv.hits = d_hits.p; fv.primary_hits = d_primary_hits.p;
         fv.shadow = ShadowQueue{d_shadow[0].p, d_shadow[1].p, d_shadow[2].p};
@@ -423,6 +425,9 @@ extern "C" {
 LB_API int lb_create(const LbSettings* s, LbRenderer* out) {
     if (!s || !out || !s->width || !s->height || !s->depth) return fail(LB_ERR_INVALID_ARGUMENT, "bad settings");
     if (s->depth > 24) return fail(LB_ERR_INVALID_ARGUMENT, "depth > 24 is not supported");
+    if (s->band_full_height && (s->band_row0 + s->height > s->band_full_height || ((uint64_t)s->band_row0 * s->width) % 256u))
+        return fail(LB_ERR_INVALID_ARGUMENT, "row band: band_row0 + height must fit band_full_height and band_row0 * width must be a multiple of 256");
+    if (!s->band_full_height && s->band_row0) return fail(LB_ERR_INVALID_ARGUMENT, "band_row0 without band_full_height");
     std::unique_ptr<lb::Renderer> r(new lb::Renderer());
     r->st = *s;
     try { r->init(); }
@@ -680,6 +685,9 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
         memcpy(json, o.c_str(), o.size() + 1);
         return (int)LB_OK;
     });
+}
+LB_API int lb_hdr_buffer(LbRenderer r, void** p, size_t* bytes) {
+    return guarded(R_, [&]() { if (!p || !bytes) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *p = R_->d_combined.p; *bytes = (size_t)R_->npix() * 16; return (int)LB_OK; });
 }
 LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) {
     return guarded(R_, [&]() { *p = R_->d_accum.p; *bytes = (size_t)R_->npix() * 16; *frames = R_->blend_count; return (int)LB_OK; });

@@ -21,6 +21,8 @@ struct LaunchCfg { int sms = 148; cudaStream_t stream = nullptr; TraceTuning tra
 
 struct FrameView {
     uint32_t width = 0, height = 0, npix = 0;
+    // row band of a larger frame (LbSettings::band_*): first row, rows of the full frame, index of the band's first pixel in the full frame
+    uint32_t row0 = 0, full_height = 0, pix0 = 0;
     RayQueue rays[2];
     uint4* hits = nullptr;            // per queue slot (depth > 0)
     uint4* primary_hits = nullptr;    // per pixel == per queue slot at depth 0

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
         __syncthreads();
         const uint32_t base = s_base;
         if (base >= fv.npix) break;
-        uint32_t bag_seed = wang_hash(seed + base / 256u);
+        uint32_t bag_seed = wang_hash(seed + (base + fv.pix0) / 256u);        // full-frame group index (pix0 is a multiple of 256)
         const int bag_index = (int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
         const uint2* picked = bags + (size_t)bag_index * kLightsPerBag;
         for (uint32_t e = threadIdx.x; e < kLightsPerBag; e += kBlock) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
         px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
         if (valid && surface_flags(fv.surf_cur, np, i)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); valid = false; }
         if (valid) surface_load_shading(fv.surf_cur, np, i, px);
-        const uint32_t s0 = wang_hash(seed + wang_hash(i));
+        const uint32_t s0 = wang_hash(seed + wang_hash(i + fv.pix0));
         Reservoir fresh = reservoir_zero();
 
         // ---- phase A: which candidates need the ordered path
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_temporal(FrameView fv, uint32_t* 
         if (!tw.pixel(fv, tile, cx, cy)) continue;
         const uint32_t i = (uint32_t)cy * fv.width + (uint32_t)cx;
         const float2 mvec = fv.motion[i];
-        const int mx = (int)roundf((float)W * mvec.x), my = (int)roundf((float)H * mvec.y);
+        const int mx = (int)roundf((float)W * mvec.x), my = (int)roundf((float)fv.full_height * mvec.y);
         const int ty = cy + my, tx = cx + mx; uint32_t ti = i;
         if (ty >= 0 && ty < H && tx >= 0 && tx < W) ti = (uint32_t)ty * fv.width + (uint32_t)tx;
         const SurfGeom gp = surface_geom(fv.surf_prev, np, ti);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_temporal(FrameView fv, uint32_t* 
             float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
         }
         prev.count = min(prev.count, cur.count * 20);
-        reservoir_store(fv.res_cur, np, i, combine_pair(prev, cur, sc, wang_hash(seed + i)));
+        reservoir_store(fv.res_cur, np, i, combine_pair(prev, cur, sc, wang_hash(seed + i + fv.pix0)));
     }
 }
 
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_spatial(FrameView fv, uint32_t* t
         const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
         const SurfGeom gc = surf_geom_unpack(geom[i]);
         if (gc.flagged) continue;
-        uint32_t s = wang_hash(seed + i);
+        uint32_t s = wang_hash(seed + i + fv.pix0);
         // all five neighbour probes are issued before any is tested (5 independent 16-byte gathers in flight)
         uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
 #pragma unroll
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_combine(FrameView fv, const float
         if (surface_flags(fv.surf_cur, np, i)) continue;
         Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
         Reservoir a, b; reservoir_load(fv.res_cur, np, i, a); reservoir_load(nbuf, np, i, b);
-        reservoir_store(fv.res_cur, np, i, combine_pair(a, b, sc, wang_hash(cseed + i)));
+        reservoir_store(fv.res_cur, np, i, combine_pair(a, b, sc, wang_hash(cseed + i + fv.pix0)));
     }
 }
 

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kBlock) k_volume_delta(FrameView fv, SceneView
         if (vinst < 0) continue;
         const float4 o4 = in.o[i], d4 = in.d[i];
         const uint32_t pixel = __float_as_uint(d4.w);
-        uint32_t seed = wang_hash((a.seed ^ 0x9e3779b9u) + pixel);
+        uint32_t seed = wang_hash((a.seed ^ 0x9e3779b9u) + pixel + fv.pix0);
         float ts;
         if (!delta_track(a.volumes[vinst], f3(o4), f3(d4), vh.x, vh.y, seed, ts)) continue;
         hits[i].w = __float_as_uint(-2.f);                       // consumed by the medium: the surface shader sees a miss

@@ -33,8 +33,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(FrameView fv, CameraBasis cam
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
         const uint32_t sy = i / fv.width, sx = i - sy * fv.width;
-        const float jx = halton(frame_count + i, 2), jy = halton(frame_count + i, 3);
-        float dx = ((float)sx + jx) / (float)fv.width, dy = ((float)sy + jy) / (float)fv.height;
+        const uint32_t gi = i + fv.pix0;                    // the pixel's index in the full frame (== i unless this renderer is a row band)
+        const float jx = halton(frame_count + gi, 2), jy = halton(frame_count + gi, 3);
+        float dx = ((float)sx + jx) / (float)fv.width, dy = ((float)(sy + fv.row0) + jy) / (float)fv.full_height;
         dx = -(dx * 2.0f - 1.0f); dy = -(dy * 2.0f - 1.0f);
         const float3 d = f3(fmaf(dx, cam.U.x, fmaf(dy, cam.V.x, cam.W.x)), fmaf(dx, cam.U.y, fmaf(dy, cam.V.y, cam.W.y)), fmaf(dx, cam.U.z, fmaf(dy, cam.V.z, cam.W.z)));
         const float len2 = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
         const float4 o4 = in.o[i], d4 = in.d[i], T4 = in.T[i];
         const uint4 hr = hits[i];
         const uint32_t pixel = __float_as_uint(d4.w);
+        const uint32_t gpixel = pixel + fv.pix0;            // full-frame index: what every random stream is keyed on
         const __half2 hb = *reinterpret_cast<const __half2*>(&hr.z);
         const Surface s = extract_surface(sc, f3(o4), f3(d4), f3(T4), hr.x, hr.y, __low2float(hb), __high2float(hb), __uint_as_float(hr.w));
 
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
             float2 mv = make_float2(0.f, 0.f);
             if (s.t > 0.f) {
                 const uint32_t y = pixel / fv.width, x = pixel - y * fv.width;
-                const float cx = ((float)x + 0.5f) / (float)fv.width, cy = ((float)y + 0.5f) / (float)fv.height;
+                const float cx = ((float)x + 0.5f) / (float)fv.width, cy = ((float)(y + fv.row0) + 0.5f) / (float)fv.full_height;
                 const float* M = a.prev_view_proj;
                 const float px = fmaf(M[0], s.pos.x, fmaf(M[1], s.pos.y, fmaf(M[2], s.pos.z, M[3])));
                 const float py = fmaf(M[4], s.pos.x, fmaf(M[5], s.pos.y, fmaf(M[6], s.pos.z, M[7])));
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
         }
 
         if (a.do_nee) {
-            uint32_t seed = wang_hash(a.seed + pixel);
+            uint32_t seed = wang_hash(a.seed + gpixel);
             if (a.num_volumes && a.volume_mode == 0 /* LB_VOLUME_COMPAT */ && sc.num_lights) {
                 // VolumetricShadeDirect (GPUVolumetricShadeDirect.cu:8-101): 5 fixed steps, constant density per unit length, the grid is
                 // never sampled; every step spawns a shadow ray of constant radiance 0.01; accumulated density becomes the alpha
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
             ShadowRayOut sr;
             bool ok = nee_sample(sc, s, seed, sr);
             if (ok && a.num_volumes && a.volume_mode == 1 /* LB_VOLUME_DELTA */) {
-                uint32_t vseed = wang_hash((a.seed ^ 0x85ebca6bu) + pixel);
+                uint32_t vseed = wang_hash((a.seed ^ 0x85ebca6bu) + gpixel);
                 const float tr = ratio_transmittance(a.volumes, a.num_volumes, sr.o, sr.d, 0.01f, sr.tmax, vseed);
                 sr.radiance *= tr;
             }
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, in
         }
         if (a.do_bounce) {
             BounceOut b;
-            const bool ok = bounce_sample(s, pixel, wang_hash(a.seed), b);
+            const bool ok = bounce_sample(s, gpixel, wang_hash(a.seed), b);
             if (ok) {
                 const uint32_t slot = queue_append_slot(out_count);
                 out.o[slot] = f4(b.o, 0.f);

@@ -6,7 +6,8 @@ rank g renders frameCount = 1 + 2*(g + k*G), k = 0, 1, ... Each rank accumulates
 and ONE collective — a sum-reduce of the W*H*4 float accumulation buffer — produces the image. There is no other exchange.
 
 Alternative for single-frame latency: IMAGE BANDS with a 60-pixel halo (ReSTIR spatial radius 30 x 2 iterations), rendered
-redundantly so no halo exchange is needed; `band_partition` computes the bands, the gather is one collective at the end.
+redundantly so no halo exchange is needed: `band_settings` turns a renderer into the producer of one row band of the full frame
+(LbSettings::band_row0 / band_full_height), `gather_bands` collects the owned rows on one rank at the end of the frame.
 
 torch.distributed is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU tests); nothing here touches pixels except
 through the reduce.
@@ -37,14 +38,52 @@ def split_frames(total_frames: int, world: int) -> List[int]:
     return [base + (1 if r < rem else 0) for r in range(world)]
 
 
-def band_partition(height: int, world: int, halo: int = RESTIR_HALO) -> List[Tuple[int, int, int, int]]:
+def band_partition(height: int, world: int, halo: int = RESTIR_HALO, width: int = 0) -> List[Tuple[int, int, int, int]]:
     """Row bands (y0, y1) owned by each rank and the rows (h0, h1) it must render so that ReSTIR reuse inside its band never
-    reads a pixel it did not compute."""
+    reads a pixel it did not compute. With `width` given, h0 is lowered until h0 * width is a multiple of 256 (the RIS light-bag
+    group is 256 consecutive pixels of the FULL frame, LbSettings::band_row0)."""
+    from math import gcd
+    step = 256 // gcd(width, 256) if width else 1
     out = []
     for r in range(world):
         y0, y1 = height * r // world, height * (r + 1) // world
-        out.append((y0, y1, max(0, y0 - halo), min(height, y1 + halo)))
+        h0 = max(0, y0 - halo)
+        out.append((y0, y1, h0 - h0 % step, min(height, y1 + halo)))
     return out
+
+
+def band_settings(settings, rank: int, world: int, halo: int = RESTIR_HALO):
+    """Settings of the renderer that produces rank `rank`'s band (+ halo) of the frame described by `settings`, and the band
+    (y0, y1, h0, h1). Camera, jitter, motion vectors and random streams stay keyed on full-frame pixel positions, so the pixels of
+    rows y0..y1 are the ones a single renderer would produce (bit for bit while the ReSTIR history they depend on lies inside the halo:
+    the first two frames after a history reset; afterwards the outer `halo` rows of a band reuse a slightly different neighbourhood)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    y0, y1, h0, h1 = band_partition(settings.height, world, halo, settings.width)[rank]
+    return replace(settings, height=h1 - h0, band_row0=h0, band_full_height=settings.height), (y0, y1, h0, h1)
+
+
+def gather_bands(band_rows, full_frame, bands, rank: int, dst: int = 0, group=None):
+    """The one collective of the band scheme: every rank sends the rows it owns to `dst`. `band_rows` is this rank's rendered frame
+    as an (h1-h0, W, 4) tensor, `full_frame` the (H, W, 4) tensor on `dst` (ignored elsewhere), `bands` = band_partition(...).
+    Point-to-point sends, because the bands differ in size when H is not a multiple of the world size."""
+    import torch.distributed as dist
+    y0, y1, h0, _ = bands[rank]
+    own = band_rows[y0 - h0:y1 - h0]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        full_frame[y0:y1].copy_(own)
+        return full_frame
+    ops = []
+    if rank == dst:
+        full_frame[y0:y1].copy_(own)
+        for r, (a, b, _, _) in enumerate(bands):
+            if r != dst:
+                ops.append(dist.P2POp(dist.irecv, full_frame[a:b], r, group))
+    else:
+        ops.append(dist.P2POp(dist.isend, own.contiguous(), dst, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return full_frame
 
 
 def reduce_accumulation(accum, dst: int = 0, group=None):

@@ -83,6 +83,9 @@ struct Renderer {
     std::vector<std::pair<std::string, float>> stats; std::string stats_names;
 
     uint32_t npix() const { return st.width * st.height; }
+    // row band of a larger frame (LbSettings::band_*): random streams, camera and motion vectors are keyed on the full-frame position
+    uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
+    uint32_t pix0() const { return st.band_row0 * st.width; }
     void resize() {
         const size_t n = npix();
         for (auto& s : surface) s.assign(n, Surface{});
@@ -250,7 +253,7 @@ struct Renderer {
     void camera_vectors(V3& eye, V3& U, V3& V, V3& W) const {
         double m[16]; camera_matrix(m);
         const float half_y = 1.0f * tanf((fov_y * 0.01745329251994329576923690768489f) * 0.5f);
-        const float half_x = half_y * ((float)st.width / (float)st.height);
+        const float half_x = half_y * ((float)st.width / (float)full_height());
         eye = cam_pos;
         U = v3((float)m[0], (float)m[4], (float)m[8]) * half_x;
         V = v3((float)m[1], (float)m[5], (float)m[9]) * half_y;
@@ -263,7 +266,7 @@ struct Renderer {
         double view[16];   // inverse of rigid transform
         for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) view[r * 4 + k] = c[k * 4 + r]; view[r * 4 + 3] = -(c[0 * 4 + r] * c[3] + c[1 * 4 + r] * c[7] + c[2 * 4 + r] * c[11]); }
         view[12] = view[13] = view[14] = 0; view[15] = 1;
-        const double aspect = (double)st.width / (double)st.height, zn = 0.5, zf = 10000.0, th = tan((fov_y * 0.01745329251994329576923690768489) / 2.0);
+        const double aspect = (double)st.width / (double)full_height(), zn = 0.5, zf = 10000.0, th = tan((fov_y * 0.01745329251994329576923690768489) / 2.0);
         double P[16] = {1.0 / (aspect * th), 0, 0, 0, 0, 1.0 / th, 0, 0, 0, 0, -(zf + zn) / (zf - zn), -(2.0 * zf * zn) / (zf - zn), 0, 0, -1, 0};
         for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) { double s = 0; for (int j = 0; j < 4; ++j) s += P[r * 4 + j] * view[j * 4 + k]; out[r * 4 + k] = (float)s; }
     }
@@ -280,8 +283,9 @@ struct Renderer {
         #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < (int64_t)npix(); ++i) {
             const int sy = (int)(i / st.width), sx = (int)(i - (int64_t)sy * st.width);
-            const float jx = halton(frame_count + (uint32_t)i, 2), jy = halton(frame_count + (uint32_t)i, 3);
-            float dx = ((float)sx + jx) / (float)st.width, dy = ((float)sy + jy) / (float)st.height;
+            const uint32_t gi = (uint32_t)i + pix0();
+            const float jx = halton(frame_count + gi, 2), jy = halton(frame_count + gi, 3);
+            float dx = ((float)sx + jx) / (float)st.width, dy = ((float)((uint32_t)sy + st.band_row0) + jy) / (float)full_height();
             dx = -(dx * 2.0f - 1.0f); dy = -(dy * 2.0f - 1.0f);
             // canonical fused order (identical on the GPU): dx*U + (dy*V + W)
             const V3 d = v3(fmaf(dx, U.x, fmaf(dy, V.x, W.x)), fmaf(dx, U.y, fmaf(dy, V.y, W.y)), fmaf(dx, U.z, fmaf(dy, V.z, W.z)));
@@ -380,7 +384,7 @@ struct Renderer {
             const uint32_t y = (uint32_t)(i / st.width), x = (uint32_t)(i - (int64_t)y * st.width);
             V2 mv{0.f, 0.f}; const Surface& s = surf[i];
             if (s.t > 0.f) {
-                const float cx = ((float)x + 0.5f) / (float)st.width, cy = ((float)y + 0.5f) / (float)st.height;
+                const float cx = ((float)x + 0.5f) / (float)st.width, cy = ((float)(y + st.band_row0) + 0.5f) / (float)full_height();
                 const float px = fmaf(M[0], s.pos.x, fmaf(M[1], s.pos.y, fmaf(M[2], s.pos.z, M[3])));
                 const float py = fmaf(M[4], s.pos.x, fmaf(M[5], s.pos.y, fmaf(M[6], s.pos.z, M[7])));
                 const float pw = fmaf(M[12], s.pos.x, fmaf(M[13], s.pos.y, fmaf(M[14], s.pos.z, M[15])));
@@ -417,7 +421,7 @@ struct Renderer {
 
     // ------------------------------------------------------------------ NEE: ShadeDirect, GPUShadeDirect.cu:42-153
     bool shade_direct_pixel(const Surface& s, uint32_t pixel_index, uint32_t seed_in, int chan, const VolumeHit* vh, std::vector<ShadowRay>* vol_rays, ShadowRay& out) {
-        uint32_t seed = wang_hash(seed_in + pixel_index);
+        uint32_t seed = wang_hash(seed_in + pixel_index + pix0());
         if (vh && vh->vinst >= 0 && vh->t1 > vh->t0 && st.volume_mode == LB_VOLUME_COMPAT && !lights.empty()) volume_compat_pixel(s, pixel_index, *vh, seed, *vol_rays);
         if (s.flags || lights.empty()) return false;
         uint32_t li; float lpdf; cdf_get(rand_f(seed), li, lpdf);
@@ -434,7 +438,7 @@ struct Renderer {
         c *= ((1.f / lpdf) * s.transport);
         out = {pixel_index % st.width, pixel_index / st.width, s.pos, dir, dist - 0.2f, c, chan};
         if (!vinstances.empty() && st.volume_mode == LB_VOLUME_DELTA) {          // shadow rays cross the media: ratio-tracked transmittance
-            uint32_t vseed = wang_hash((seed_in ^ 0x85ebca6bu) + pixel_index);
+            uint32_t vseed = wang_hash((seed_in ^ 0x85ebca6bu) + pixel_index + pix0());
             out.radiance *= ratio_transmittance(out.o, out.d, 0.01f, out.tmax, vseed);
         }
         return true;
@@ -472,7 +476,7 @@ struct Renderer {
 
     // ------------------------------------------------------------------ ShadeIndirect, GPUShadeIndirect.cu:7-146
     bool shade_indirect_pixel(const Surface& s, uint32_t pixel_index, uint32_t seed_in, Ray& out) const {
-        uint32_t seed = wang_hash(seed_in + wang_hash(pixel_index));
+        uint32_t seed = wang_hash(seed_in + wang_hash(pixel_index + pix0()));
         const uint32_t px = pixel_index % st.width, py = pixel_index / st.width;
         if (s.flags & SURF_ALPHA) { out = {px, py, s.pos, s.incoming, s.transport}; return true; }
         if (s.flags) return false;
@@ -521,12 +525,12 @@ struct Renderer {
         seed = wang_hash(seed);
         #pragma omp parallel for schedule(dynamic, 256)
         for (int64_t i = 0; i < (int64_t)n; ++i) {
-            uint32_t bag_seed = wang_hash(seed + (uint32_t)(i / 256));                       // hazard 1: block index instead of %smid
+            uint32_t bag_seed = wang_hash(seed + ((uint32_t)i + pix0()) / 256u);                       // hazard 1: block index instead of %smid
             const int bag = (int)roundf((float)(kNumBags - 1) * rand_f(bag_seed));
             const BagEntry* picked = &bags[(size_t)bag * kLightsPerBag];
             const Surface& px = cur[i];
             if (px.flags) { R[i] = Reservoir{}; continue; }
-            uint32_t s = wang_hash(seed + wang_hash((uint32_t)i));
+            uint32_t s = wang_hash(seed + wang_hash((uint32_t)i + pix0()));
             Reservoir fresh;
             for (uint32_t k = 0; k < kPrimarySamples; ++k) {
                 const float r = rand_f(s);
@@ -548,7 +552,7 @@ struct Renderer {
             #pragma omp parallel for schedule(dynamic, 256)
             for (int64_t i = 0; i < (int64_t)n; ++i) {
                 const int cy = (int)(i / st.width), cx = (int)(i - (int64_t)cy * st.width);
-                const int mx = (int)roundf((float)st.width * motion[i].x), my = (int)roundf((float)st.height * motion[i].y);
+                const int mx = (int)roundf((float)st.width * motion[i].x), my = (int)roundf((float)full_height() * motion[i].y);
                 int ty = cy + my, tx = cx + mx; int64_t ti = i;
                 if (ty >= 0 && ty < (int)st.height && tx >= 0 && tx < (int)st.width) ti = (int64_t)ty * st.width + tx;
                 const Surface& sp = prev[ti]; const Surface& sc = cur[i];
@@ -559,7 +563,7 @@ struct Renderer {
                 if (!(pct < 0.10f && ang > kSimilarCos)) continue;
                 if (Rprev[ti].weight > 0.f) { const V3 c = Rprev[ti].sample.contribution * (Rprev[ti].weight / shaded); V4& o = channel[LB_CHANNEL_DIRECT][i]; o.x += c.x; o.y += c.y; o.z += c.z; }
                 pair[0].count = std::min(pair[0].count, pair[1].count * 20);
-                combine_biased(R[i], 2, pair, sc, wang_hash(seed + (uint32_t)i));
+                combine_biased(R[i], 2, pair, sc, wang_hash(seed + (uint32_t)i + pix0()));
             }
         }
         if (st.restir_spatial) {
@@ -571,7 +575,7 @@ struct Renderer {
                 #pragma omp parallel for schedule(dynamic, 256)
                 for (int64_t i = 0; i < (int64_t)n; ++i) {
                     const Surface& sc = cur[i]; if (sc.flags) continue;
-                    uint32_t s = wang_hash(seed + (uint32_t)i);
+                    uint32_t s = wang_hash(seed + (uint32_t)i + pix0());
                     const int y = (int)(i / st.width), x = (int)(i - (int64_t)y * st.width);
                     const Surface* pd[kSpatialSamples]; const Reservoir* pr[kSpatialSamples]; int count = 0;
                     for (uint32_t k = 0; k < kSpatialSamples; ++k) {
@@ -606,7 +610,7 @@ struct Renderer {
             for (int64_t i = 0; i < (int64_t)n; ++i) {
                 if (cur[i].flags) continue;
                 Reservoir pair[2] = {R[i], Nb[i]};
-                combine_biased(R[i], 2, pair, cur[i], wang_hash(cseed + (uint32_t)i));
+                combine_biased(R[i], 2, pair, cur[i], wang_hash(cseed + (uint32_t)i + pix0()));
             }
         }
     }
@@ -672,7 +676,7 @@ struct Renderer {
             if (vh.vinst < 0) continue;
             const Ray& ray = rays[i];
             const uint32_t pixel = ray.py * st.width + ray.px;
-            uint32_t seed = wang_hash((seed_in ^ 0x9e3779b9u) + pixel);
+            uint32_t seed = wang_hash((seed_in ^ 0x9e3779b9u) + pixel + pix0());
             float ts;
             if (!delta_track(vh, ray, seed, ts)) continue;
             hits[i].t = -2.f;
@@ -828,6 +832,9 @@ extern "C" {
 
 LB_API int lo_create(const LbSettings* s, LbRenderer* out) {
     if (!s || !out || !s->width || !s->height || !s->depth) return fail(LB_ERR_INVALID_ARGUMENT, "bad settings");
+    if (s->band_full_height && (s->band_row0 + s->height > s->band_full_height || ((uint64_t)s->band_row0 * s->width) % 256u))
+        return fail(LB_ERR_INVALID_ARGUMENT, "row band: band_row0 + height must fit band_full_height and band_row0 * width must be a multiple of 256");
+    if (!s->band_full_height && s->band_row0) return fail(LB_ERR_INVALID_ARGUMENT, "band_row0 without band_full_height");
     auto* r = new lo::Renderer(); r->st = *s;
     Texture white; white.px = {255, 255, 255, 255}; Texture nrm; nrm.px = {128, 128, 255, 255};   // LM/Renderer/LumenRenderer.cpp:50-58
     r->textures.push_back(white); r->textures.push_back(nrm);
@@ -989,6 +996,7 @@ LB_API int lo_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
     if (!json || cap < o.size() + 1) return (json || cap) ? fail(LB_ERR_INVALID_ARGUMENT, "buffer too small") : (needed ? (int)LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "null"));
     memcpy(json, o.c_str(), o.size() + 1); return LB_OK;
 }
+LB_API int lo_hdr_buffer(LbRenderer r, void** p, size_t* bytes) { CHECK_R; if (!p || !bytes) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *p = R_->combined.data(); *bytes = R_->combined.size() * 16; return LB_OK; }
 LB_API int lo_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) { CHECK_R; *p = R_->accum.data(); *bytes = R_->accum.size() * 16; *frames = R_->blend_count; return LB_OK; }
 LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); const float inv = 1.0f / (float)total;
     for (size_t i = 0; i < R_->accum.size(); ++i) R_->combined[i] = {R_->accum[i].x * inv, R_->accum[i].y * inv, R_->accum[i].z * inv, R_->accum[i].w * inv}; R_->write_ldr(); return LB_OK; }
