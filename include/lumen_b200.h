@@ -135,7 +135,7 @@ typedef struct LbEmissiveness {
 } LbEmissiveness;
 
 /* Procedural / dense float density grid standing in for nanovdb::FloatGrid
- * (PT/Framework/PTVolume.cpp:47-108 loads .vdb/.vndb; file decode is out of scope).
+ * (PT/Framework/PTVolume.cpp:47-108 loads .vdb/.vndb; NanoVDB files: lb_volume_create_file / lb_nanovdb_* below).
  * density[(z*ny + y)*nx + x], world bbox = bbox_min..bbox_max in the volume's object space. */
 typedef struct LbVolumeDesc {
     const float* density;       /* may be NULL: homogeneous medium of value 1 */
@@ -270,6 +270,49 @@ LB_API int lb_gltf_instance(LbGltf g, uint32_t instance, uint32_t* mesh, float* 
  * LumenPTModelConverter::LoadFile issues them (:105-268). root_transform16 (row-major, may be NULL) is applied on the left of
  * every instance transform (SceneManager::LoadGLTF's a_TransformMat, LM/ModelLoading/SceneManager.cpp:41). */
 LB_API int lb_gltf_upload(LbRenderer r, LbGltf g, const float* root_transform16, LbHandle* first_instance, uint32_t* instance_count);
+
+/* ---- asset ingest in front of the path: NanoVDB files (.vndb / .nvdb) ----
+ * Restates nanovdb::io::readGrid + the grid accessors of the NanoVDB the reference vendors (ABI 29.3.0,
+ * LumenPT/vendor/openvdb/nanovdb/nanovdb/util/IO.h:107-160,301-352,573-592; NanoVDB.h:1890-1905,2184-2190,2394-2456,2733-2766,3022-3040),
+ * which PTVolume::Load calls for ".vndb" (PT/Framework/PTVolume.cpp:93-98). Host-only: opening and inspecting a file needs no renderer
+ * and no GPU. Float grids only (the reference reads nanovdb::FloatGrid); codecs NONE and ZIP (BLOSC: LB_ERR_UNSUPPORTED). */
+typedef struct LbNanoVdbOpaque* LbNanoVdb;
+enum { LB_NANOVDB_TYPE_FLOAT = 1 };                                   /* nanovdb::GridType::Float, NanoVDB.h:275-288 */
+enum { LB_NANOVDB_CLASS_UNKNOWN = 0, LB_NANOVDB_CLASS_LEVEL_SET = 1, LB_NANOVDB_CLASS_FOG_VOLUME = 2 };   /* nanovdb::GridClass, NanoVDB.h:305-313 */
+typedef struct LbNanoVdbInfo {
+    uint32_t grid_type, grid_class;     /* GridData::mGridType / mGridClass */
+    uint32_t version[3];                /* major (ABI), minor, patch */
+    uint32_t codec;                     /* of the segment the grid came from: 0 none, 1 ZIP */
+    uint32_t grid_count;                /* grids in the whole file */
+    uint32_t node_count[4];             /* leaf, lower, upper, root (TreeData::mCount) */
+    int32_t index_min[3], index_max[3]; /* Tree::bbox(), inclusive; max < min = no active voxel */
+    double world_min[3], world_max[3];  /* Grid::worldBBox() */
+    double voxel_size[3];
+    double map_matrix[9];               /* row-major 3x3 of the index -> world map (Map::mMatD) */
+    double map_translation[3];          /* Map::mVecD */
+    uint64_t active_voxels, grid_bytes;
+    float background, value_min, value_max;
+    char name[256];
+} LbNanoVdbInfo;
+LB_API int lb_nanovdb_open(const char* path, uint32_t grid_index, LbNanoVdb* out);                               /* io::readGrid(fileName, n) */
+LB_API int lb_nanovdb_open_memory(const void* bytes, size_t size, uint32_t grid_index, LbNanoVdb* out);         /* io::readGrid(istream, n) */
+LB_API int lb_nanovdb_close(LbNanoVdb g);
+LB_API const char* lb_nanovdb_last_error(void);
+LB_API int lb_nanovdb_info(LbNanoVdb g, LbNanoVdbInfo* out);
+/* ReadAccessor::getValue / isActive for n index coordinates (ijk3 = n x {i, j, k}); `active` may be NULL. */
+LB_API int lb_nanovdb_values(LbNanoVdb g, const int32_t* ijk3, uint32_t n, float* values, uint8_t* active);
+/* All values of the box index_min..index_max, out[((k - kmin) * ny + (j - jmin)) * nx + (i - imin)] — the layout of LbVolumeDesc::density.
+ * as_density = 0: the stored values; 1: the density the renderer uses (fog volume: max(value, 0); level set: OpenVDB's sdfToFogVolume
+ * ramp, inside min(1, -value / background), outside 0). */
+LB_API int lb_nanovdb_dense(LbNanoVdb g, int as_density, float* out, size_t capacity_floats);
+/* LumenRenderer::CreateVolume for a parsed grid: object-space box = the world-space box of the stored voxels (= Grid::worldBBox(), what
+ * Shaders/volumetric_wavefront.cu:87 intersects), density field = lb_nanovdb_dense(as_density = 1). The index -> world map must be
+ * scale + translation. */
+LB_API int lb_volume_create_nanovdb(LbRenderer r, LbNanoVdb g, LbHandle* out);
+/* LumenRenderer::CreateVolume(const std::string& path), LM/Renderer/LumenRenderer.h:168: dispatches on the extension like
+ * PTVolume::Load (PT/Framework/PTVolume.cpp:69-107): ".vndb" / ".nvdb" are read here; ".vdb" (OpenVDB's own container, decoded by the
+ * OpenVDB library in the reference) and anything else return LB_ERR_UNSUPPORTED. Error text: lb_nanovdb_last_error(). */
+LB_API int lb_volume_create_file(LbRenderer r, const char* path, LbHandle* out);
 
 /* ---- multi-GPU / framework interop ---- */
 /* Device pointer of the fp32 RGBA accumulation buffer (sum over blended frames) and its frame count, for an

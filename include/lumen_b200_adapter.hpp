@@ -414,10 +414,14 @@ public:
         return scene;
     }
 
-    // .vdb / .vndb decoding is not part of the path (the caller decodes): use CreateVolume(const LbVolumeDesc&)
+    // PTVolume::Load (PT/Framework/PTVolume.cpp:47-108): ".vndb" / ".nvdb" are read by the library (lb_volume_create_file); ".vdb"
+    // needs the OpenVDB library and is reported as unsupported — decode it in the application and use CreateVolume(const LbVolumeDesc&)
     std::shared_ptr<Lumen::ILumenVolume> CreateVolume(const std::string& a_FilePath) override
     {
-        throw std::runtime_error("lumen_b200: CreateVolume(" + a_FilePath + "): pass the decoded grid to CreateVolume(const LbVolumeDesc&)");
+        LbHandle h = LB_NO_HANDLE;
+        if (lb_volume_create_file(m_Renderer, a_FilePath.c_str(), &h) != LB_OK)
+            throw std::runtime_error("lumen_b200: CreateVolume(" + a_FilePath + "): " + lb_nanovdb_last_error());
+        return std::make_shared<Volume>(h);
     }
     std::shared_ptr<Lumen::ILumenVolume> CreateVolume(const LbVolumeDesc& a_Grid)
     {

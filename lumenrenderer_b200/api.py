@@ -194,6 +194,15 @@ class LbGltfInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("images", "undecoded_images", "materials", "meshes", "primitives", "instances", "triangles", "vertices")]
 
 
+class LbNanoVdbInfo(C.Structure):
+    _fields_ = [("grid_type", C.c_uint32), ("grid_class", C.c_uint32), ("version", C.c_uint32 * 3), ("codec", C.c_uint32), ("grid_count", C.c_uint32),
+                ("node_count", C.c_uint32 * 4), ("index_min", C.c_int32 * 3), ("index_max", C.c_int32 * 3),
+                ("world_min", C.c_double * 3), ("world_max", C.c_double * 3), ("voxel_size", C.c_double * 3),
+                ("map_matrix", C.c_double * 9), ("map_translation", C.c_double * 3),
+                ("active_voxels", C.c_uint64), ("grid_bytes", C.c_uint64),
+                ("background", C.c_float), ("value_min", C.c_float), ("value_max", C.c_float), ("name", C.c_char * 256)]
+
+
 IMAGE_DECODE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p)
 _HOST_SIGS = {
     "gltf_open": [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
@@ -205,8 +214,16 @@ _HOST_SIGS = {
     "gltf_primitive": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(LbPrimitiveDesc)],
     "gltf_instance": [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p],
     "gltf_upload": [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)],
+    "nanovdb_open": [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)],
+    "nanovdb_open_memory": [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p)],
+    "nanovdb_close": [C.c_void_p],
+    "nanovdb_info": [C.c_void_p, C.POINTER(LbNanoVdbInfo)],
+    "nanovdb_values": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
+    "nanovdb_dense": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
+    "volume_create_nanovdb": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
+    "volume_create_file": [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)],
 }
-HOST_ONLY_SYMBOLS = tuple(_HOST_SIGS) + ("gltf_last_error",)
+HOST_ONLY_SYMBOLS = tuple(_HOST_SIGS) + ("gltf_last_error", "nanovdb_last_error")
 C_ABI_SYMBOLS = tuple(_SIGS) + ("last_error", "version")
 
 HIT_DTYPE = np.dtype([("instance", np.uint32), ("primitive", np.uint32), ("u", np.float32), ("v", np.float32), ("t", np.float32)])
@@ -232,6 +249,8 @@ class Bindings:
                 setattr(self, name, fn)
             self.gltf_last_error = lib.lb_gltf_last_error
             self.gltf_last_error.restype = C.c_char_p
+            self.nanovdb_last_error = lib.lb_nanovdb_last_error
+            self.nanovdb_last_error.restype = C.c_char_p
 
     def check(self, code: int):
         if code != LB_OK:

@@ -110,6 +110,20 @@ int main(int argc, char** argv) try {
         if (overrideMaterial >= 0) inst->SetOverrideMaterial(materials.at(size_t(overrideMaterial)));
         instances.push_back(inst);
     }
+    // optional trailing section: volumes loaded from files through LumenRenderer::CreateVolume(path) + ILumenScene::AddVolume()
+    std::vector<Lumen::VolumeInstance*> volumeInstances;
+    if (rd.in.peek() != std::char_traits<char>::eof()) {
+        for (uint32_t n = rd.get<uint32_t>(), i = 0; i < n; ++i) {
+            const std::vector<uint8_t> path = rd.bytes(rd.get<uint32_t>());
+            const glm::mat4 rowMajor = rd.get<glm::mat4>();
+            const float density = rd.get<float>();
+            Lumen::VolumeInstance* inst = scene.AddVolume();
+            inst->SetVolume(renderer->CreateVolume(std::string(path.begin(), path.end())));
+            inst->m_Transform = glm::transpose(rowMajor);
+            inst->m_Density = density;
+            volumeInstances.push_back(inst);
+        }
+    }
     scene.m_Camera->SetRotation(glm::quat(qw, qx, qy, qz));
     scene.m_Camera->SetPosition(camPosition);                           // SetPosition raises the dirty flag, SetRotation does not (Camera.cpp:32-45)
     scene.m_Camera->SetAspectRatio(float(settings.renderResolution.x) / float(settings.renderResolution.y));
@@ -123,6 +137,7 @@ int main(int argc, char** argv) try {
     std::vector<float> worlds;
     for (auto* inst : instances) { float m[16]; B200::RowMajor(inst->m_Transform.GetWorldTransformationMatrix(), m); worlds.insert(worlds.end(), m, m + 16); }
     { glm::mat4 prev, cur; scene.m_Camera->GetMatrixData(prev, cur); float m[16]; B200::RowMajor(cur, m); worlds.insert(worlds.end(), m, m + 16); }
+    for (auto* inst : volumeInstances) { float m[16]; B200::RowMajor(inst->m_Transform.GetWorldTransformationMatrix(), m); worlds.insert(worlds.end(), m, m + 16); }
     write_file(out + ".ldr", ldr.data(), ldr.size());
     write_file(out + ".hdr", hdr.data(), hdr.size() * sizeof(float));
     write_file(out + ".worlds", worlds.data(), worlds.size() * sizeof(float));

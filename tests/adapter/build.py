@@ -43,7 +43,8 @@ def build(force: bool = False) -> dict:
     sys.path.insert(0, ROOT)
     from lumenrenderer_b200.api import C_ABI_SYMBOLS
     exes = {"oracle": os.path.join(OUT, "adapter_driver_oracle"), "b200": os.path.join(OUT, "adapter_driver_b200")}
-    srcs = [os.path.join(HERE, "adapter_driver.cpp"), os.path.join(ROOT, "include", "lumen_b200_adapter.hpp"), os.path.join(ROOT, "include", "lumen_b200.h"), __file__]
+    srcs = [os.path.join(HERE, "adapter_driver.cpp"), os.path.join(ROOT, "include", "lumen_b200_adapter.hpp"), os.path.join(ROOT, "include", "lumen_b200.h"),
+            os.path.join(ROOT, "lumenrenderer_b200", "csrc", "lb_nanovdb.cpp"), __file__]
     if not force and all(os.path.exists(e) and os.path.getmtime(e) > max(os.path.getmtime(s) for s in srcs) for e in exes.values()):
         return exes
     os.makedirs(OUT, exist_ok=True)
@@ -74,8 +75,14 @@ def build(force: bool = False) -> dict:
                                          ("b200", f"{ROOT}/lumenrenderer_b200", "lumen_b200", [])):
             obj = os.path.join(tmp, f"driver_{kind}.o")
             _run(["g++", *flags, *extra, "-c", os.path.join(HERE, "adapter_driver.cpp"), "-o", obj])
+            more = []
+            if kind == "oracle":
+                # the host-only NanoVDB ingest is product code with no oracle twin: the same source, its renderer calls (lb_volume_create,
+                # lb_last_error) renamed to the oracle's like the adapter's own
+                more = [os.path.join(tmp, "lb_nanovdb_oracle.o")]
+                _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", *extra, "-c", os.path.join(ROOT, "lumenrenderer_b200", "csrc", "lb_nanovdb.cpp"), "-o", more[0]])
             rel = os.path.relpath(libdir, OUT)
-            _run(["g++", obj, *objs, "-o", exes[kind], f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,$ORIGIN/{rel}", "-lpthread"])
+            _run(["g++", obj, *more, *objs, "-o", exes[kind], f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,$ORIGIN/{rel}", "-lpthread"])
     return exes
 
 

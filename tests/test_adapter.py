@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "adapter"))
 import build as adapter_build  # noqa: E402
 
-from lumenrenderer_b200 import api, scenes  # noqa: E402
+from lumenrenderer_b200 import api, scenes, nanovdb  # noqa: E402
+import nanovdb_tools  # noqa: E402
 
 MATERIAL_FLOATS = ("transmission_factor", "clear_coat_factor", "clear_coat_roughness_factor", "index_of_refraction", "specular_factor", "specular_tint_factor",
                    "subsurface_factor", "luminance", "anisotropic", "sheen_factor", "sheen_tint_factor", "metallic_factor", "roughness_factor")
@@ -59,6 +60,13 @@ def dump_scene(path, scene, width, height, depth, restir, frames, interleaved):
             f.write(struct.pack("<I", inst["mesh"])); f.write(m.tobytes())
             f.write(struct.pack("<i3ffi", inst.get("emission_mode", api.EMISSION_ENABLED), *inst.get("override_radiance", (0, 0, 0)), inst.get("emission_scale", 1.0),
                                 inst.get("override_material", -1)))
+        files = [v for v in scene.volumes if v.get("file")]
+        if files:
+            f.write(struct.pack("<I", len(files)))
+            for v in files:
+                path = os.fsencode(v["file"])
+                m = np.eye(4, dtype=np.float32) if v.get("transform") is None else np.asarray(v["transform"], np.float32).reshape(4, 4)
+                f.write(struct.pack("<I", len(path))); f.write(path); f.write(m.tobytes()); f.write(struct.pack("<f", v.get("instance_density", 0.001)))
 
 
 def render_through_c_abi(bindings, scene, worlds, width, height, depth, restir, frames):
@@ -75,6 +83,14 @@ def render_through_c_abi(bindings, scene, worlds, width, height, depth, restir, 
                     if p.get(key) is None:
                         p[key] = np.zeros((n, w), np.float32)
         r.load_scene(s2)
+        for k, v in enumerate(v for v in scene.volumes if v.get("file")):
+            world = worlds[len(scene.instances) + 1 + k]
+            if bindings.prefix == "lb_":
+                h = nanovdb.create_volume_from_file(r, v["file"])
+            else:                                   # the oracle has no file reader: the numpy restatement's density box stands in
+                g = nanovdb_tools.read_grid(open(v["file"], "rb").read())
+                h = r.create_volume(g.density(), *g.volume_box())
+            r.add_volume_instance(h, world, v.get("instance_density", 0.001))
         r.set_camera_matrix(worlds[len(scene.instances)])
         r.render_frames(frames)
         return r.read_hdr(), r.read_ldr()
@@ -87,7 +103,7 @@ def run_case(exe, bindings, tmp_path, scene, width, height, depth, restir, frame
     assert res.returncode == 0, res.stderr[-2000:]
     assert f"frames {frames} resolution {width}x{height} instances {len(scene.instances)} frame-id {frames}" in res.stdout, res.stdout
     worlds = np.fromfile(out + ".worlds", np.float32).reshape(-1, 16)
-    assert len(worlds) == len(scene.instances) + 1
+    assert len(worlds) == len(scene.instances) + 1 + sum(1 for v in scene.volumes if v.get("file"))
     hdr = np.fromfile(out + ".hdr", np.float32).reshape(height, width, 4)
     ldr = np.fromfile(out + ".ldr", np.uint8).reshape(height, width, 4)
     ref_hdr, ref_ldr = render_through_c_abi(bindings, scene, worlds, width, height, depth, restir, frames)
@@ -107,8 +123,17 @@ def moved_cornell():
     return s
 
 
+def room_with_nanovdb_volume():
+    """The fog room with its medium loaded from a NanoVDB file through LumenRenderer::CreateVolume(path) (level-set sphere fixture written
+    by the reference's own NanoVDB, tests/golden/make_golden_nanovdb.py), scaled and moved in front of the two boxes."""
+    s = scenes.fog_room(grid=8)
+    s.volumes = [{"file": os.path.join(ROOT, "tests", "golden", "nanovdb", "ls10_zip.vndb"), "instance_density": 0.8,
+                  "transform": scenes.translate(-8.4, 4.2, -1.0, scale=0.4)}]
+    return s
+
+
 @pytest.mark.skipif(not adapter_build.available(), reason="needs the reference tree (/root/reference) to compile against")
-@pytest.mark.parametrize("case", ["cornell_nee_separate_streams", "moved_restir_interleaved", "gallery_textures"])
+@pytest.mark.parametrize("case", ["cornell_nee_separate_streams", "moved_restir_interleaved", "gallery_textures", "volume_from_nanovdb_file"])
 def test_adapter_over_reference_interface_cpu(oracle, tmp_path, case):
     exe = adapter_build.build()["oracle"]
     if case == "cornell_nee_separate_streams":
@@ -120,6 +145,8 @@ def test_adapter_over_reference_interface_cpu(oracle, tmp_path, case):
         worlds = run_case(exe, oracle, tmp_path, moved_cornell(), 40, 32, 3, True, 2, True)
         want = np.asarray(scenes.translate(0.05, 0.0, 0.1, scale=0.9, angle_y_deg=12.0), np.float32).reshape(4, 4)
         assert np.allclose(worlds[4].reshape(4, 4), want, atol=1e-5)       # decompose + recompose reproduces the matrix to rounding
+    elif case == "volume_from_nanovdb_file":
+        run_case(exe, oracle, tmp_path, room_with_nanovdb_volume(), 64, 40, 3, False, 2, False)
     else:
         run_case(exe, oracle, tmp_path, scenes.material_gallery(), 40, 24, 3, True, 1, True)
 
@@ -130,3 +157,4 @@ def test_adapter_over_reference_interface_gpu(gpu, tmp_path):
     if not os.path.exists(exe):
         pytest.skip("tests/adapter/_build/adapter_driver_b200 was not prebuilt (needs /root/reference at build time)")
     run_case(exe, gpu, tmp_path, moved_cornell(), 96, 64, 3, True, 2, True)
+    run_case(exe, gpu, tmp_path, room_with_nanovdb_volume(), 96, 64, 3, False, 2, False)
