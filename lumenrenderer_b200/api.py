@@ -179,6 +179,7 @@ _SIGS = {
     "frame_stats_json": [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
     "accum_buffer": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)],
     "resolve_accum": [C.c_void_p, C.c_uint32],
+    "set_overlap": [C.c_void_p, C.c_int],
     "set_stream": [C.c_void_p, C.c_void_p],
     "debug_trace_closest": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p],
     "debug_trace_any": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p],
@@ -554,6 +555,10 @@ class Renderer:
 
     def resolve_accum(self, total_frames: int):
         self.b.check(self.b.resolve_accum(self._h, total_frames))
+
+    def set_overlap(self, enabled: bool):
+        """ReSTIR chain and bounce chain of a frame on two streams (default) or serialised (exclusive stage times)."""
+        self.b.check(self.b.set_overlap(self._h, 1 if enabled else 0))
 
     def set_stream(self, cuda_stream: int):
         self.b.check(self.b.set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -86,8 +86,15 @@ struct Renderer {
     uint64_t counters[12]{};
 
     // ---- FrameStats (LumenRenderer.h:29-34): CUDA events instead of host wall clock around forced syncs
-    struct Lap { const char* name; cudaEvent_t ev; };
+    // A lap's time is measured from `prev`, the preceding lap of the same stream (overlap mode has two chains; the ReSTIR chain starts at
+    // the fork lap)
+    struct Lap { const char* name; cudaEvent_t ev; size_t prev; };
     std::vector<Lap> laps; std::vector<cudaEvent_t> event_pool; size_t events_used = 0;
+    size_t last_lap[2] = {0, 0};
+    // ---- overlap mode (lb_set_overlap): the ReSTIR passes depend only on the primary surface records and write only the DIRECT channel;
+    // the bounce waves (extend / shade / shadow at depth > 0) write only the other channels. They run as two chains that fork after the
+    // primary shade and join before the merge, so that the latency-bound tail waves execute under the ReSTIR kernels.
+    bool overlap = overlap_default(); cudaStream_t restir_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string stats_names;
 
     // ---- render thread (StartRendering, WaveFrontRenderer.cpp:1109-1117)
@@ -96,6 +103,7 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
+    static bool overlap_default() { const char* e = getenv("LB_OVERLAP"); return !e || atoi(e) != 0; }
     static TraceTuning trace_tuning() {
         TraceTuning t;
         if (const char* e = getenv("LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
@@ -113,6 +121,9 @@ struct Renderer {
         if (ev_rendered) cudaEventDestroy(ev_rendered);
         if (ev_copied) cudaEventDestroy(ev_copied);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (restir_stream) { cudaStreamSynchronize(restir_stream); cudaStreamDestroy(restir_stream); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
     void stop_thread() {
         if (render_thread.joinable()) { stop_flag = true; render_thread.join(); }
@@ -329,17 +340,18 @@ struct Renderer {
         return fv;
     }
 
-    void lap(const char* name) {
+    void lap(const char* name, int chain = 0) {
         if (events_used == event_pool.size()) { cudaEvent_t e; LB_CUDA(cudaEventCreate(&e)); event_pool.push_back(e); }
         cudaEvent_t e = event_pool[events_used++];
-        LB_CUDA(cudaEventRecord(e, stream));
-        laps.push_back(Lap{name, e});
+        LB_CUDA(cudaEventRecord(e, chain ? restir_stream : stream));
+        laps.push_back(Lap{name, e, last_lap[chain]});
+        last_lap[chain] = laps.size() - 1;
     }
 
     // ---- WaveFrontRenderer::TraceFrame
     void render_frame() {
         if (scene_dirty || resources_dirty) commit_scene();
-        laps.clear(); events_used = 0;
+        laps.clear(); events_used = 0; last_lap[0] = last_lap[1] = 0;
         lap("begin");
         const LaunchCfg c = cfg();
         FrameView fv = frame_view();
@@ -357,6 +369,7 @@ struct Renderer {
         ShadeArgs a{}; a.max_depth = st.depth;
         a.volumes = d_volumes.p; a.num_volumes = (uint32_t)vinstances.size(); a.volume_mode = (int)st.volume_mode;
         prev_view_proj(a.prev_view_proj);
+        bool forked = false;
         for (uint32_t depth = 0; depth < st.depth; ++depth) {
             const int queue = (int)(depth & 1u);
             launch_extend(c, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
@@ -378,17 +391,30 @@ struct Renderer {
             lap("shade");
             if (depth == 0 && st.restir) {
                 RestirArgs ra{seed, (int)st.restir_temporal, (int)st.restir_spatial};
-                ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage); }; ra.lap_user = this;
                 RestirBuffers rb{d_bags.p};
-                const uint32_t t0 = ticket;
-                launch_restir(c, fv, sc, bv, rb, ra, ticket);
+                forked = overlap && st.depth > 1 && sc.num_lights != 0u && a.num_volumes == 0u;      // media: volume shadow rays also write DIRECT at depth 0
+                LaunchCfg cr = c;
+                if (forked) {
+                    if (!restir_stream) {
+                        int lo = 0, hi = 0; LB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                        static const bool high = []() { const char* e = getenv("LB_OVERLAP_PRIORITY"); return !e || atoi(e) != 0; }();
+                        LB_CUDA(cudaStreamCreateWithPriority(&restir_stream, cudaStreamNonBlocking, high ? hi : lo));   // the ReSTIR chain is the critical path
+                        LB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+                    }
+                    LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
+                    cr.stream = restir_stream; last_lap[1] = last_lap[0];
+                    ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
+                } else ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 0); };
+                ra.lap_user = this;
+                launch_restir(cr, fv, sc, bv, rb, ra, ticket);
+                if (forked) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
                 if (sc.num_lights) launches += 3u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
-                (void)t0;
             }
             if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
+        if (forked) { LB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); lap("restir_join"); }    // the time the bounce chain waited for the ReSTIR chain
         if (copy_pending) LB_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));      // an asynchronous read-back still owns the combined buffer
         launch_merge(c, fv, (int)st.blend_output, blend_count); ++launches;
         lap("merge");
@@ -630,7 +656,7 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
         LB_CUDA(cudaStreamSynchronize(R_->stream));
         R_->stats_names.clear(); uint32_t n = 0;
         for (size_t i = 1; i < R_->laps.size() && n < cap; ++i) {
-            float ms = 0.f; LB_CUDA(cudaEventElapsedTime(&ms, R_->laps[i - 1].ev, R_->laps[i].ev));
+            float ms = 0.f; LB_CUDA(cudaEventElapsedTime(&ms, R_->laps[R_->laps[i].prev].ev, R_->laps[i].ev));
             if (n) R_->stats_names += ';';
             R_->stats_names += R_->laps[i].name; if (micros) micros[n] = ms * 1000.f; ++n;
         }
@@ -670,7 +696,7 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
         // stages that run several times per frame (extend, shade, shadow per wave) are summed, as FrameStats::m_Times does with its map
         std::vector<std::pair<std::string, double>> times;
         for (size_t i = 1; i < R_->laps.size(); ++i) {
-            float ms = 0.f; LB_CUDA(cudaEventElapsedTime(&ms, R_->laps[i - 1].ev, R_->laps[i].ev));
+            float ms = 0.f; LB_CUDA(cudaEventElapsedTime(&ms, R_->laps[R_->laps[i].prev].ev, R_->laps[i].ev));
             auto it = std::find_if(times.begin(), times.end(), [&](const std::pair<std::string, double>& t) { return t.first == R_->laps[i].name; });
             if (it == times.end()) times.emplace_back(R_->laps[i].name, (double)ms * 1000.0); else it->second += (double)ms * 1000.0;
         }
@@ -694,6 +720,9 @@ LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* fram
 }
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
     return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
+}
+LB_API int lb_set_overlap(LbRenderer r, int enabled) {
+    return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled != 0; return (int)LB_OK; });
 }
 LB_API int lb_set_stream(LbRenderer r, void* s) {
     return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->stream = s ? (cudaStream_t)s : R_->own_stream; return (int)LB_OK; });

@@ -21,6 +21,9 @@ namespace lb {
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef LB_GATHER_BLOCKS
+#define LB_GATHER_BLOCKS 2        // resident blocks per SM the gather kernels (temporal / spatial / combine) are compiled for
+#endif
 constexpr uint32_t kNumBags = 50, kLightsPerBag = 1000, kPrimarySamples = 32, kSpatialSamples = 5, kSpatialRadius = 30, kSpatialIterations = 2;   // ReSTIRData.h:34-56
 constexpr float kSimilarCos = 0.72222222223f;
 
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhVi
     if ((threadIdx.x & 31u) == 0u && traced) atomicAdd(stat, (unsigned long long)traced);
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
+__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
     const TileWalk tw(fv);
@@ -280,7 +283,7 @@ LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i)
     return p;
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
     const TileWalk tw(fv);
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_spatial(FrameView fv, uint32_t* t
     }
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_combine(FrameView fv, const float4* __restrict__ nbuf, uint32_t cseed) {
+__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_combine(FrameView fv, const float4* __restrict__ nbuf, uint32_t cseed) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const size_t np = fv.npix;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
@@ -366,20 +369,20 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     lap("restir_visibility");
     if (a.temporal) {
         seed = wang_hash(seed);
-        k_temporal<<<cfg.sms * 2, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
+        k_temporal<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
         lap("restir_temporal");
     }
     if (a.spatial) {
         seed = wang_hash(seed);
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-            k_spatial<<<cfg.sms * 2, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
+            k_spatial<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
         lap("restir_spatial");
         k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
         lap("restir_visibility");
-        k_combine<<<cfg.sms * 2, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
+        k_combine<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
         lap("restir_combine");
     }
 }

@@ -21,6 +21,9 @@ namespace lb {
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef LB_SHADE_BLOCKS
+#define LB_SHADE_BLOCKS 2         // resident blocks per SM the fused shade kernel is compiled for
+#endif
 
 // ------------------------------------------------------------------ K1 ray generation
 __device__ __forceinline__ float halton(uint32_t index, uint32_t base) {
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(kBlock) k_extend(BvhView bvh, const float4* __
 
 // ------------------------------------------------------------------ fused shade: K6 (+K8, K9 at depth 0) + K10 + K11
 template <bool PRIMARY>
-__global__ void __launch_bounds__(kBlock) k_shade(FrameView fv, SceneView sc, int queue, ShadeArgs a) {
+__global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv, SceneView sc, int queue, ShadeArgs a) {
     const uint32_t n = fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A];
     const RayQueue in = fv.rays[queue], out = fv.rays[queue ^ 1];
     uint32_t* out_count = &fv.counters[queue ? CNT_RAYS_A : CNT_RAYS_B];

@@ -1001,6 +1001,7 @@ LB_API int lo_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* fram
 LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); const float inv = 1.0f / (float)total;
     for (size_t i = 0; i < R_->accum.size(); ++i) R_->combined[i] = {R_->accum[i].x * inv, R_->accum[i].y * inv, R_->accum[i].z * inv, R_->accum[i].w * inv}; R_->write_ldr(); return LB_OK; }
 LB_API int lo_set_stream(LbRenderer, void*) { return LB_OK; }
+LB_API int lo_set_overlap(LbRenderer r, int) { CHECK_R; return LB_OK; }      // the CPU restatement is one sequence of passes
 
 LB_API int lo_debug_trace_closest(LbRenderer r, const float* rays6, uint32_t n, float tmin, float tmax, void* hits20) {
     CHECK_R; if (R_->scene_dirty) R_->commit_scene();
