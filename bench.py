@@ -262,8 +262,8 @@ def run_gpu(args):
     finite = bool(np.isfinite(host.numpy()).all())
 
     # ---- per-stage device time (CUDA events on the renderer's stream, per frame) for the roofline lines
-    # Stage times are taken with the two chains of a frame serialised (lb_set_overlap(0)): every stage time is then an exclusive device
-    # time. The timed regions above ran in the default overlap mode (ReSTIR chain and bounce chain on two streams).
+    # Stage times are taken with the two chains of a frame serialised (lb_set_overlap(0), the default): every stage time is an exclusive
+    # device time. LB_OVERLAP=1 runs the timed regions above with the ReSTIR chain and the bounce chain on two streams (an experiment).
     r.set_overlap(False)
     r.render_frames(1)
     stage_ms, stage_frames = {}, max(3, min(args.steps, 10))
@@ -314,8 +314,8 @@ def run_gpu(args):
                 "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
-                "overlap": {"enabled": os.environ.get("LB_OVERLAP", "1") != "0", "ms_per_frame_serialised": serial_ms,
-                            "note": "ReSTIR passes and bounce waves (depth > 0) of a frame run as two chains forked after the primary shade and joined before the merge; stage_ms / roofline_kernels are exclusive times measured with the chains serialised"},
+                "overlap": {"enabled": os.environ.get("LB_OVERLAP", "0") != "0", "ms_per_frame_serialised": serial_ms,
+                            "note": "optional mode (LB_OVERLAP=1): ReSTIR passes and bounce waves (depth > 0) of a frame as two chains forked after the primary shade and joined before the merge; off by default (measured slower); stage_ms / roofline_kernels are always exclusive times measured with the chains serialised"},
                 "roofline": roofline, "roofline_extend": roofline_extend, "roofline_kernels": table, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
         print(json.dumps(line), flush=True)
     r.close()

@@ -322,7 +322,7 @@ LB_API int lb_volume_create_file(LbRenderer r, const char* path, LbHandle* out);
 LB_API int lb_hdr_buffer(LbRenderer r, void** device_ptr, size_t* bytes);
 LB_API int lb_accum_buffer(LbRenderer r, void** device_ptr, size_t* bytes, uint32_t* frames);
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
-/* Overlap mode (default on; environment LB_OVERLAP=0 turns it off at creation): the ReSTIR passes of a frame and its bounce waves
+/* Overlap mode (default OFF — measured slower on B200; environment LB_OVERLAP=1 turns it on at creation): the ReSTIR passes of a frame and its bounce waves
  * (depth > 0) are independent — they fork after the primary shade and join before the merge (the reference serialises every kernel with
  * cudaDeviceSynchronize, PT/Framework/WaveFrontRenderer.cpp:604-850). Results are identical either way; with overlap off every stage time
  * of lb_frame_stats is an exclusive device time (what bench.py uses for its per-kernel roofline table). */

@@ -93,7 +93,8 @@ struct Renderer {
     size_t last_lap[2] = {0, 0};
     // ---- overlap mode (lb_set_overlap): the ReSTIR passes depend only on the primary surface records and write only the DIRECT channel;
     // the bounce waves (extend / shade / shadow at depth > 0) write only the other channels. They run as two chains that fork after the
-    // primary shade and join before the merge, so that the latency-bound tail waves execute under the ReSTIR kernels.
+    // primary shade and join before the merge, so that the latency-bound tail waves can execute under the ReSTIR kernels. Off by default:
+    // on B200 the two chains of persistent grids interfere (8.45 -> 8.87..9.45 ms/frame, profiles/r01_p_experiments.md).
     bool overlap = overlap_default(); cudaStream_t restir_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string stats_names;
 
@@ -103,7 +104,7 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
-    static bool overlap_default() { const char* e = getenv("LB_OVERLAP"); return !e || atoi(e) != 0; }
+    static bool overlap_default() { const char* e = getenv("LB_OVERLAP"); return e && atoi(e) != 0; }      // off: measured slower
     static TraceTuning trace_tuning() {
         TraceTuning t;
         if (const char* e = getenv("LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);

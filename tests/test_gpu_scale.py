@@ -6,6 +6,10 @@
   C5  3840x2160 progressive accumulation: the accumulation buffer is a plain fp32 sum, so two sample shards with disjoint frameCount
       streams add up to the single-renderer result (NEE path: frames are independent), and resolve(sum / n) equals the blended image.
   C2  at 2560x1440 with ReSTIR: finite output, ray accounting, temporal history switches on after the first frame.
+  C3  2560x1440, delta tracking, homogeneous box + 256^3 heterogeneous grid + a NanoVDB file: media of density 0 leave the image
+      bit-identical to the scene without media; the number of primary rays that scatter inside a medium equals the analytic
+      sum over pixels of 1 - exp(-integral of sigma along the ray) within binomial noise (homogeneous: closed form; 256^3 grid:
+      numerical integration of the same nearest-voxel field).
 """
 import os
 
@@ -114,3 +118,101 @@ def test_c2_atrium_1440p_restir_properties():
     res = g.read_reservoirs()
     assert (res[..., 2] > 32).mean() > 0.3, "temporal / spatial reuse did not raise the sample counts"
     g.close()
+
+
+def _fog_room_without_media():
+    s = scenes.fog_room(grid=8)
+    s.volumes = []
+    return s
+
+
+def _ray_box(o, d, lo, hi, tmin, tmax):
+    """Slab intervals of rays o + t d against an axis-aligned box, clipped to [tmin, tmax]; float64, [n] arrays."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / d
+        ta, tb = (lo - o) * inv, (hi - o) * inv
+    t0 = np.maximum(np.minimum(ta, tb).max(axis=1), tmin)
+    t1 = np.minimum(np.maximum(ta, tb).min(axis=1), tmax)
+    return t0, t1
+
+
+def test_c3_fog_room_1440p_delta_tracking(tmp_path):
+    from lumenrenderer_b200 import nanovdb as nv
+    W, H = 2560, 1440
+    kw = dict(width=W, height=H, depth=3, restir=False, volume_mode=lr.VOLUME_DELTA)
+    eye = np.array([0.0, 10.0, 20.0])
+    base = _renderer(_fog_room_without_media(), **kw)
+    base.render_frames(1)
+    img0 = base.read_hdr().copy()
+    t_hit = base.read_primary_hits()["t"].reshape(-1).astype(np.float64)
+    pos = base.read_surface()[..., 0:3].reshape(-1, 3).astype(np.float64)
+    base.close()
+    hit = t_hit > 0
+    assert hit.mean() > 0.4                      # fovY 90 at 16:9 also sees past the open room
+    d = pos - eye
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    o = np.broadcast_to(eye, d.shape)
+
+    # heterogeneous field at the BASELINE size (256^3): a noise-modulated ball, as scenes.fog_room builds at test size
+    n = 256
+    z, y, x = np.meshgrid(*(np.arange(n, dtype=np.float32) / (n - 1) - 0.5,) * 3, indexing="ij")
+    r = np.sqrt(x * x + y * y + z * z)
+    field = (np.clip(1.0 - r / 0.5, 0, 1) * (0.6 + 0.4 * np.sin(18 * x) * np.sin(15 * y + 1.0) * np.sin(13 * z + 2.0))).astype(np.float32)
+    field = np.clip(field, 0, 1)
+    del x, y, z, r
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nanovdb", "fog12_zip.vndb")
+
+    def with_media(sigma_box, sigma_grid, sigma_file, only=None):
+        g = _renderer(_fog_room_without_media(), **kw)
+        if only in (None, "box"):
+            g.add_volume_instance(g.create_volume(None, (-6.0, 2.0, -6.0), (6.0, 12.0, 4.0)), None, sigma_box)
+        if only in (None, "grid"):
+            g.add_volume_instance(g.create_volume(field, (-7.0, 3.0, 0.0), (5.0, 15.0, 12.0)), None, sigma_grid)
+        if only is None:
+            m = np.array([[0.3, 0, 0, -2.0], [0, 0.3, 0, 12.0], [0, 0, 0.3, 1240.0], [0, 0, 0, 1]], np.float32)   # the file's ball lands near (7, 6, 10)
+            g.add_volume_instance(nv.create_volume_from_file(g, fixture), m, sigma_file)
+        g.render_frames(1)
+        return g
+
+    # (1) media of density 0: bit-identical to the scene without media (tracking draws come from their own random streams)
+    g = with_media(0.0, 0.0, 0.0)
+    assert np.array_equal(g.read_hdr(), img0)
+    g.close()
+
+    # (2) homogeneous box: P(scatter) = 1 - exp(-sigma * length inside the box in front of the surface)
+    sigma = 0.12
+    g = with_media(sigma, 0.0, 0.0, only="box")
+    img = g.read_hdr()
+    assert np.isfinite(img).all() and not np.array_equal(img, img0)
+    scattered = hit & ~(g.read_primary_hits()["t"].reshape(-1) > 0)
+    g.close()
+    t0, t1 = _ray_box(o, d, np.array([-6.0, 2.0, -6.0]), np.array([6.0, 12.0, 4.0]), 0.01, np.where(hit, t_hit, 5000.0))
+    length = np.where(hit, np.maximum(t1 - t0, 0.0), 0.0)
+    p = 1.0 - np.exp(-sigma * length)
+    expect, sd = p.sum(), np.sqrt((p * (1 - p)).sum())
+    assert expect > 3e4
+    assert abs(scattered.sum() - expect) < 5 * sd + 1e-3 * expect, (int(scattered.sum()), expect, sd)
+
+    # (3) 256^3 heterogeneous grid on a random subset of pixels: numerical integral of the same nearest-voxel field
+    sigma = 0.9
+    g = with_media(0.0, sigma, 0.0, only="grid")
+    scattered = hit & ~(g.read_primary_hits()["t"].reshape(-1) > 0)
+    assert np.isfinite(g.read_hdr()).all()
+    g.close()
+    lo, hi = np.array([-7.0, 3.0, 0.0]), np.array([5.0, 15.0, 12.0])
+    t0, t1 = _ray_box(o, d, lo, hi, 0.01, np.where(hit, t_hit, 5000.0))
+    inside = np.flatnonzero(hit & (t1 > t0))
+    sub = np.random.default_rng(11).choice(inside, 150000, replace=False)
+    steps = 768
+    u = (np.arange(steps) + 0.5) / steps
+    tau = np.zeros(len(sub))
+    for k in range(0, len(sub), 10000):
+        idx = sub[k:k + 10000]
+        t = t0[idx, None] + (t1[idx] - t0[idx])[:, None] * u[None, :]
+        pts = o[idx, None, :] + d[idx, None, :] * t[..., None]
+        ijk = np.clip(((pts - lo) / (hi - lo) * n).astype(np.int64), 0, n - 1)
+        tau[k:k + 10000] = field[ijk[..., 2], ijk[..., 1], ijk[..., 0]].mean(axis=1) * (t1[idx] - t0[idx]) * sigma
+    p = 1.0 - np.exp(-tau)
+    expect, sd = p.sum(), np.sqrt((p * (1 - p)).sum())
+    assert expect > 1e4
+    assert abs(scattered[sub].sum() - expect) < 5 * sd + 5e-3 * expect, (int(scattered[sub].sum()), expect, sd)
