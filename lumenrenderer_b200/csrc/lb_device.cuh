@@ -54,6 +54,13 @@ LB_HD float mixf(float a, float b, float t) { return a + t * (b - a); }
 LB_HD float sq(float a) { return a * a; }
 LB_HD float comp(const float3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
+// IEEE division, square root and normalisation spelled out. Exact-class code (ray generation, traversal, hit records, surface extraction,
+// motion vectors: bit-compared with the oracle, DESIGN.md "Arithmetic contract") uses these, so that it does not depend on the
+// -prec-div / -prec-sqrt setting of the translation unit it is inlined into (the fused shade kernel lives in a fast-math unit).
+LB_D float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+LB_D float xsqrt(float a) { return __fsqrt_rn(a); }
+LB_D float3 xnormalize(const float3& v) { const float inv = xdiv(1.0f, xsqrt(dot(v, v))); return v * inv; }
+
 // fp16 round trip: barycentrics (IntersectionData.h:90) and motion vectors (MotionVectors.cu:44) are stored as half.
 LB_D float half_round(float f) { return __half2float(__float2half_rn(f)); }
 

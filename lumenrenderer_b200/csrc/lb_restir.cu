@@ -12,6 +12,7 @@
 // B200 design: reservoirs and surfaces are SoA 16-byte planes; the visibility pass generates, traces and shades in ONE
 // kernel (no 32-B ray round trip through HBM, no host read-back of a ray counter).
 #include "lb_kernels.h"
+#define LB_TRACE_TOLERANCE_CLASS          // visibility rays: occlusion of a reservoir sample, never a bit-compared hit record
 #include "lb_trace.cuh"
 #include "lb_shade.cuh"
 #include <cfloat>

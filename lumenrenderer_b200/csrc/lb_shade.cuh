@@ -27,8 +27,11 @@ LB_D float4 tex2d(const SceneView& sc, int handle, float u, float v) {
     const float x0f = floorf(x), y0f = floorf(y);
     const float ax = x - x0f, ay = y - y0f;
     const int w = (int)t.w, h = (int)t.h;
-    const int x0 = (((int)x0f % w) + w) % w, y0 = (((int)y0f % h) + h) % h;
-    const int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+    // wrap addressing without integer division: fu, fv are in [0, 1], so x0f is in [-1, w - 1] (and y0f in [-1, h - 1]) — the general
+    // ((i % w) + w) % w of the oracle reduces to one compare each
+    const int xi = (int)x0f, yi = (int)y0f;
+    const int x0 = xi < 0 ? xi + w : (xi >= w ? xi - w : xi), y0 = yi < 0 ? yi + h : (yi >= h ? yi - h : yi);
+    const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
     const float4 a = texel_at(sc, t, x0, y0), b = texel_at(sc, t, x1, y0), c = texel_at(sc, t, x0, y1), d = texel_at(sc, t, x1, y1);
     return mix4(mix4(a, b, ax), mix4(c, d, ax), ay);
 }
@@ -79,21 +82,21 @@ LB_D Surface extract_surface(const SceneView& sc, const float3& ro, const float3
     float4 em = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.em_mode == 0 /* ENABLED */) { em = dm.mat.emissive * e.em_scale; em = em * tex2d(sc, dm.tex_emissive, uv.x, uv.y); }
     else if (e.em_mode == 2 /* OVERRIDE */) em = make_float4(e.em_r, e.em_g, e.em_b, e.em_scale) * e.em_scale;
-    const float3 ln = normalize((f3(na) * W + f3(nb) * U) + f3(nc) * V);
-    const float3 lt = normalize((f3(ta) * W + f3(tb) * U) + f3(tc) * V);
-    const float3 nw = normalize(xform_vector(e.m, ln)), tw = normalize(xform_vector(e.m, lt));
+    const float3 ln = xnormalize((f3(na) * W + f3(nb) * U) + f3(nc) * V);
+    const float3 lt = xnormalize((f3(ta) * W + f3(tb) * U) + f3(tc) * V);
+    const float3 nw = xnormalize(xform_vector(e.m, ln)), tw = xnormalize(xform_vector(e.m, lt));
     const float3 bw = cross(nw, tw) * flip;
     float3 nm = f3(nmap.x, nmap.y, nmap.z) * 2.f - f3(1.f);
-    nm = normalize(nm);
-    nm = normalize(f3(nm.x * tw.x + nm.y * bw.x + nm.z * nw.x, nm.x * tw.y + nm.y * bw.y + nm.z * nw.y, nm.x * tw.z + nm.y * bw.z + nm.z * nw.z));
+    nm = xnormalize(nm);
+    nm = xnormalize(f3(nm.x * tw.x + nm.y * bw.x + nm.z * nw.x, nm.x * tw.y + nm.y * bw.y + nm.z * nw.y, nm.x * tw.z + nm.y * bw.z + nm.z * nw.z));
     s.t = hit_t; s.normal = nm;
     if (em.x > 0.f || em.y > 0.f || em.z > 0.f) {
-        const float mx = fmaxf(em.x, fmaxf(em.y, em.z)); const float inv = 1.0f / mx;
+        const float mx = fmaxf(em.x, fmaxf(em.y, em.z)); const float inv = xdiv(1.0f, mx);
         s.mat.color = em * inv; s.flags |= SURF_EMISSIVE; return s;
     }
     s.pos = ro + rd * hit_t; s.incoming = rd; s.transport = throughput;
     if (tcol.w < 0.51f) { s.flags |= SURF_ALPHA; return s; }
-    const float eta = 1.f / dm.mat.transmittance.w;
+    const float eta = xdiv(1.f, dm.mat.transmittance.w);
     s.tangent = tw; s.mat = dm.mat;
     const Shading mv(dm.mat);
     const float4 mr = tex2d(sc, dm.tex_mr, uv.x, uv.y);

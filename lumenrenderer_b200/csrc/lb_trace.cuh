@@ -20,6 +20,15 @@
 
 namespace lb {
 
+// Division used by the traversal. Exact class by default (hit records are bit-compared with the oracle). A translation unit whose rays
+// only decide visibility of ReSTIR samples (lb_restir.cu: DIRECT radiance, tolerance class) defines LB_TRACE_TOLERANCE_CLASS before
+// including this header and gets its own unit's division (approximate under --use_fast_math), as it always had.
+#ifdef LB_TRACE_TOLERANCE_CLASS
+LB_D float tdiv(float a, float b) { return a / b; }
+#else
+LB_D float tdiv(float a, float b) { return xdiv(a, b); }
+#endif
+
 struct RayShear { int kx, ky, kz; float sx, sy, sz; };
 
 LB_D RayShear make_shear(const float3& d) {
@@ -30,7 +39,7 @@ LB_D RayShear make_shear(const float3& d) {
     r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
     if (comp(d, r.kz) < 0.0f) { const int t = r.kx; r.kx = r.ky; r.ky = t; }
     const float dz = comp(d, r.kz);
-    r.sx = comp(d, r.kx) / dz; r.sy = comp(d, r.ky) / dz; r.sz = 1.0f / dz;
+    r.sx = tdiv(comp(d, r.kx), dz); r.sy = tdiv(comp(d, r.ky), dz); r.sz = tdiv(1.0f, dz);
     return r;
 }
 
@@ -56,7 +65,7 @@ LB_D bool tri_test(const float3& org, const RayShear& s, const float3& p0, const
     if (det == 0.0f) return false;
     const float Az = s.sz * Akz, Bz = s.sz * Bkz, Cz = s.sz * Ckz;
     const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
-    t = T / det; u = V / det; v = W / det;
+    t = tdiv(T, det); u = tdiv(V, det); v = tdiv(W, det);
     return true;
 }
 
@@ -64,7 +73,7 @@ struct HitInfo { uint32_t inst, prim; float u, v, t; };
 
 constexpr int kTraceStack = 64;
 
-LB_D float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+LB_D float safe_rcp(float d) { return tdiv(1.0f, fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
 
 // 2^23 + (byte J of `word`) as a float: one PRMT builds the bit pattern 0x4B0000bb, no integer-to-float conversion (I2F runs
 // on the quarter-rate XU pipe and was the top stall of the first version of this kernel). The 2^23 bias is folded into the
