@@ -56,33 +56,33 @@ LB_D Reservoir combine_pair(const Reservoir& a, const Reservoir& b, const Surfac
     return out;
 }
 
-// Pixel order of the gather kernels (temporal / spatial reuse): 32x8-pixel tiles, one per block iteration, handed out by a
-// device ticket (so the tiles in flight are always consecutive, whatever the grid / occupancy) and walked in vertical strips
-// 16 tiles (512 px) wide. The blocks in flight then cover a compact 2-D region whose +-30-pixel neighbour
-// halo is mostly shared, instead of ~60 full image rows — the gathers stay in L2. A warp is one 32-pixel row segment, so
-// the pixel's own loads and stores are still 512-byte coalesced.
+// Pixel order of the gather kernels (temporal / spatial reuse): the image is cut into 32x8-pixel tiles walked in vertical strips
+// 16 tiles (512 px) wide; the unit of work is one 32-pixel ROW of a tile, handed out to WARPS by a device ticket in tile order (row r of
+// tile t is item 8 t + r). The warps in flight therefore always hold consecutive rows of a few consecutive tiles, whatever the grid /
+// occupancy — a compact 2-D region whose +-30-pixel neighbour halo is mostly shared, instead of ~60 full image rows — so the gathers stay
+// in L2 / L1, and no warp ever waits for another one (the first version handed whole tiles to blocks: two __syncthreads per tile and the
+// block's slowest warp cost 0.9 stalled warps per issue, profiles/r01_u_kernels.md). A warp's own loads and stores are 512-byte coalesced.
 constexpr uint32_t kTileW = 32, kTileH = 8, kStripTiles = 16;
 struct TileWalk {
-    uint32_t tiles_x, tiles_y, ntiles, full;
+    uint32_t tiles_x, tiles_y, nitems, full;
     LB_D explicit TileWalk(const FrameView& fv) {
         tiles_x = (fv.width + kTileW - 1u) / kTileW; tiles_y = (fv.height + kTileH - 1u) / kTileH;
-        ntiles = tiles_x * tiles_y; full = kStripTiles * tiles_y;
+        nitems = tiles_x * tiles_y * kTileH; full = kStripTiles * tiles_y;
     }
-    // pixel of this thread in tile t; false when it falls outside the image
-    LB_D bool pixel(const FrameView& fv, uint32_t t, int& x, int& y) const {
+    // pixel of this lane in row item `it`; false when it falls outside the image
+    LB_D bool pixel(const FrameView& fv, uint32_t it, int& x, int& y) const {
+        const uint32_t t = it / kTileH, row = it - t * kTileH;
         const uint32_t strip = t / full, r = t - strip * full;
         const uint32_t sw = min(kStripTiles, tiles_x - strip * kStripTiles);
         const uint32_t ty = r / sw, tx = strip * kStripTiles + (r - ty * sw);
-        x = (int)(tx * kTileW + (threadIdx.x & 31u)); y = (int)(ty * kTileH + (threadIdx.x >> 5));
+        x = (int)(tx * kTileW + (threadIdx.x & 31u)); y = (int)(ty * kTileH + row);
         return (uint32_t)x < fv.width && (uint32_t)y < fv.height;
     }
-    // next tile of this block (block-uniform); >= ntiles when the image is exhausted
+    // next row item of this warp (warp-uniform); >= nitems when the image is exhausted
     LB_D uint32_t next(uint32_t* ticket) const {
-        __shared__ uint32_t s_tile;
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        return s_tile;
+        uint32_t it = 0u;
+        if ((threadIdx.x & 31u) == 0u) it = atomicAdd(ticket, 1u);
+        return __shfl_sync(0xFFFFFFFFu, it, 0);
     }
 };
 
@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
     const TileWalk tw(fv);
-    for (uint32_t tile = tw.next(ticket); tile < tw.ntiles; tile = tw.next(ticket)) {
+    for (uint32_t item = tw.next(ticket); item < tw.nitems; item = tw.next(ticket)) {
         int cx, cy;
-        if (!tw.pixel(fv, tile, cx, cy)) continue;
+        if (!tw.pixel(fv, item, cx, cy)) continue;
         const uint32_t i = (uint32_t)cy * fv.width + (uint32_t)cx;
         const float2 mvec = fv.motion[i];
         const int mx = (int)roundf((float)W * mvec.x), my = (int)roundf((float)fv.full_height * mvec.y);
@@ -290,9 +290,9 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView 
     const TileWalk tw(fv);
     const float4* __restrict__ geom = fv.surf_cur + np;          // plane 1: normal, signed depth
     const bool degenerate = seed == 0u;
-    for (uint32_t tile = tw.next(ticket); tile < tw.ntiles; tile = tw.next(ticket)) {
+    for (uint32_t item = tw.next(ticket); item < tw.nitems; item = tw.next(ticket)) {
         int x, y;
-        if (!tw.pixel(fv, tile, x, y)) continue;
+        if (!tw.pixel(fv, item, x, y)) continue;
         const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
         const SurfGeom gc = surf_geom_unpack(geom[i]);
         if (gc.flagged) continue;
