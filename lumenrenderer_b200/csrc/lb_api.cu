@@ -82,7 +82,7 @@ struct Renderer {
     // ---- per-resolution buffers
     DevBuf<float4> d_rays[2][3], d_shadow[3], d_surf[2], d_res[4], d_channels, d_combined, d_accum, d_vol_hits, d_vol_shadow[3];
     DevBuf<uint4> d_hits, d_primary_hits; DevBuf<float2> d_motion; DevBuf<uchar4> d_ldr;
-    DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags;
+    DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags, d_ris_order;
     uint64_t counters[12]{};
 
     // ---- FrameStats (LumenRenderer.h:29-34): CUDA events instead of host wall clock around forced syncs
@@ -157,6 +157,7 @@ struct Renderer {
 
     void resize() {
         const size_t n = npix();
+        d_ris_order.reserve((n + 255) / 256 + 128);          // + per-bag {start, count} and work tickets (lb_restir.cu k_ris_order)
         for (auto& q : d_rays) for (auto& p : q) p.reserve(n);
         for (auto& p : d_shadow) p.reserve(n);
         for (auto& p : d_surf) { p.reserve(n * kSurfPlanes); p.zero(stream); }
@@ -392,7 +393,7 @@ struct Renderer {
             lap("shade");
             if (depth == 0 && st.restir) {
                 RestirArgs ra{seed, (int)st.restir_temporal, (int)st.restir_spatial};
-                RestirBuffers rb{d_bags.p};
+                RestirBuffers rb{d_bags.p, d_ris_order.p};
                 forked = overlap && st.depth > 1 && sc.num_lights != 0u && a.num_volumes == 0u;      // media: volume shadow rays also write DIRECT at depth 0
                 LaunchCfg cr = c;
                 if (forked) {
@@ -409,7 +410,7 @@ struct Renderer {
                 ra.lap_user = this;
                 launch_restir(cr, fv, sc, bv, rb, ra, ticket);
                 if (forked) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
-                if (sc.num_lights) launches += 3u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
+                if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
             }
             if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }

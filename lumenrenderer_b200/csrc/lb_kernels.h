@@ -76,7 +76,7 @@ void launch_debug_reservoirs(const LaunchCfg&, const float4* planes, uint32_t np
 void launch_debug_hits(const LaunchCfg&, const uint4* hits, uint32_t n, void* hits20);
 
 // ---- ReSTIR (lb_restir.cu)
-struct RestirBuffers { uint2* bags = nullptr; };      // kNumBags*kLightsPerBag entries {light index, pdf bits}
+struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; };      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
 void launch_restir(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView&, const RestirBuffers&, const RestirArgs&, uint32_t& ticket);
 
 // ---- scene preparation (lb_scene.cu)

@@ -135,9 +135,43 @@ LB_D uint32_t draw_candidate_geom(const BagSmem& b, uint32_t& s, BagCandidate& c
 
 extern __shared__ __align__(16) unsigned char ris_smem[];
 
-__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint32_t* ticket, uint32_t seed) {
+// canonical bag of a 256-pixel group (hazard 1): WangHash(seed + full-frame group index) -> one of the 50 bags
+LB_D uint32_t bag_of_group(uint32_t seed, uint32_t group_base_pixel) {
+    uint32_t bag_seed = wang_hash(seed + group_base_pixel / 256u);
+    return (uint32_t)(int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
+}
+
+// Pixel groups ordered by their bag (counting sort in one block; the order inside a bag is irrelevant — every pixel's result depends on
+// its own group's bag only). Layout of `order`: [0, ngroups) = {group, bag} sorted by bag; [ngroups + b] = {first entry, entry count} of
+// bag b; [ngroups + 64 + b].x = the bag's work ticket (zeroed here, every frame).
+__global__ void __launch_bounds__(1024) k_ris_order(uint32_t seed, uint32_t npix, uint32_t pix0, uint2* __restrict__ order) {
+    __shared__ uint32_t s_count[kNumBags], s_start[kNumBags];
+    const uint32_t ngroups = (npix + 255u) / 256u;
+    if (threadIdx.x < kNumBags) s_count[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) atomicAdd(&s_count[bag_of_group(seed, g * 256u + pix0)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        uint32_t run = 0u;
+        for (uint32_t b = 0; b < kNumBags; ++b) { s_start[b] = run; order[ngroups + b] = make_uint2(run, s_count[b]); order[ngroups + 64u + b] = make_uint2(0u, 0u); run += s_count[b]; }
+    }
+    __syncthreads();
+    for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
+        const uint32_t bag = bag_of_group(seed, g * 256u + pix0);
+        order[atomicAdd(&s_start[bag], 1u)] = make_uint2(g, bag);
+    }
+}
+
+// Work item = one 32-pixel row of a 256-pixel group, taken by WARPS from the work ticket of ONE bag: a block stages a bag (1000 entries
+// with the full light record, 72 KB of shared memory) and its 8 warps then work through that bag's rows without ever waiting for one
+// another. Blocks start on bag (blockIdx mod 50) — about six blocks per bag at 2 blocks per SM — and, when their bag is exhausted, move
+// on to the next bag that still has rows (work stealing; costs one more staging). The first version handed whole 256-pixel groups to
+// blocks in image order and re-staged the bag for every group (14 400 times per frame at 1440p): barrier stalls 0.46 and
+// long-scoreboard 0.64 warps per issue (profiles/r01_u_kernels.md).
+__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed) {
     static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
-    static_assert(kBlock == 256, "one block = one 256-pixel bag group");
+    static_assert(kBlock == 256, "8 warps = the 8 rows of a 256-pixel bag group");
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
     const size_t np = fv.npix;
     BagSmem bag;
     bag.g0 = reinterpret_cast<float4*>(ris_smem); bag.g1 = bag.g0 + kLightsPerBag; bag.g2 = bag.g1 + kLightsPerBag; bag.rad = bag.g2 + kLightsPerBag;
@@ -145,18 +179,32 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
     // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
     // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
     uint32_t (*s_state)[kBlock] = reinterpret_cast<uint32_t (*)[kBlock]>(ris_smem + kRisBagBytes);
-    __shared__ uint32_t s_base;
-    for (;;) {
-        // 256 pixels per block and turn, handed out by a device ticket: the work per pixel varies (sky / emissive pixels cost
-        // nothing), a static split would leave SMs idle at the end
-        __syncthreads();                                    // the previous group's bag is no longer read
-        if (threadIdx.x == 0u) s_base = atomicAdd(ticket, (uint32_t)kBlock);
+    __shared__ uint32_t s_next;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ngroups = (fv.npix + 255u) / 256u;
+    const uint2* meta = order + ngroups;
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(order + ngroups + 64u);        // .x of entry b (stride 2 words)
+    uint32_t cur = blockIdx.x % kNumBags;                       // block-uniform
+    for (uint32_t visited = 0u; ; ) {
+        // ---- next bag with rows left, starting at `cur` (warp 0 looks at all 50 tickets at once)
+        __syncthreads();                                        // nobody reads the staged bag any more
+        if (threadIdx.x < 32u) {
+            bool open[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t b = lane + 32u * (uint32_t)h;
+                open[h] = b < kNumBags && *reinterpret_cast<volatile uint32_t*>(&tickets[2u * b]) < meta[b].y * 8u;
+            }
+            const unsigned long long m = (unsigned long long)__ballot_sync(0xFFFFFFFFu, open[0]) | ((unsigned long long)__ballot_sync(0xFFFFFFFFu, open[1]) << 32);
+            // first open bag at or after cur, cyclically
+            const unsigned long long hi = m >> cur, lo = m & ((1ull << cur) - 1ull);
+            const uint32_t nxt = hi ? cur + (uint32_t)__ffsll((long long)hi) - 1u : (lo ? (uint32_t)__ffsll((long long)lo) - 1u : kNone);
+            if (lane == 0u) s_next = nxt;
+        }
         __syncthreads();
-        const uint32_t base = s_base;
-        if (base >= fv.npix) break;
-        uint32_t bag_seed = wang_hash(seed + (base + fv.pix0) / 256u);        // full-frame group index (pix0 is a multiple of 256)
-        const int bag_index = (int)roundf((float)(kNumBags - 1u) * rand_f(bag_seed));
-        const uint2* picked = bags + (size_t)bag_index * kLightsPerBag;
+        cur = s_next;
+        if (cur == kNone || ++visited > 2u * kNumBags) break;
+        const uint2* picked = bags + (size_t)cur * kLightsPerBag;
         for (uint32_t e = threadIdx.x; e < kLightsPerBag; e += kBlock) {
             const uint2 be = __ldg(&picked[e]);
             const float4* lp = reinterpret_cast<const float4*>(sc.lights + be.x);
@@ -164,8 +212,16 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
             bag.g0[e] = a; bag.g1[e] = b; bag.g2[e] = c; bag.rad[e] = make_float4(d.x, d.y, d.z, 0.f); bag.pa[e] = make_float2(__uint_as_float(be.y), d.w);
         }
         __syncthreads();
+        const uint2 range = meta[cur];
+        // ---- this warp's rows of the bag
+        for (;;) {
+        uint32_t it = 0u;
+        if (lane == 0u) it = atomicAdd(&tickets[2u * cur], 1u);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= range.y * 8u) break;
+        const uint32_t my_base = __ldg(&order[range.x + (it >> 3)]).x * 256u + (it & 7u) * 32u;
 
-        const uint32_t i = base + threadIdx.x;
+        const uint32_t i = my_base + lane;
         bool valid = i < fv.npix;
         Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
         px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
@@ -183,10 +239,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
                 s_state[k][threadIdx.x] = sa;
                 BagCandidate c; draw_candidate_geom(bag, sa, c);
                 ResampleGeom g;
-                const bool have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
+                const bool have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
                 // ordered unless the update is provably a pure count increment: weight 0 / bag_pdf exactly 0 (bag_pdf neither 0 nor NaN)
                 // and a non-zero acceptance draw
-                const bool ordered = have || !(c.bag_pdf != 0.f && c.bag_pdf == c.bag_pdf) || sa == 0u;
+                const bool ordered = have_g || !(c.bag_pdf != 0.f && c.bag_pdf == c.bag_pdf) || sa == 0u;
                 mask |= (ordered ? 1u : 0u) << k;
             }
             fresh.count = (int)kPrimarySamples - __popc(mask);
@@ -197,7 +253,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
         uint32_t sb = s0;
         while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
             const bool active = mask != 0u;
-            BagCandidate c; ResampleGeom g; bool have = false;
+            BagCandidate c; ResampleGeom g; bool have_g = false;
             c.ls.radiance = f3(0.f); c.ls.normal = f3(0.f); c.ls.position = f3(0.f); c.ls.contribution = f3(0.f); c.ls.area = 0.f; c.ls.pdf = 0.f; c.bag_pdf = 1.f;
             g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
             if (active) {
@@ -205,16 +261,17 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
                 sb = s_state[k][threadIdx.x];
                 const uint32_t slot = draw_candidate_geom(bag, sb, c);
                 c.ls.radiance = f3(bag.rad[slot]);
-                have = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
+                have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
             }
             __syncwarp();
-            if (have) resample_shade(ctx, g, c.ls);
-            if (active) reservoir_update(fresh, c.ls, (have ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
+            if (have_g) resample_shade(ctx, g, c.ls);
+            if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
             __syncwarp();
         }
         if (valid) {
             reservoir_update_weight(fresh);
             reservoir_store(fv.res_cur, np, i, fresh);
+        }
         }
     }
 }
@@ -363,7 +420,8 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     k_fill_bags<<<grid_for(kNumBags * kLightsPerBag, kBlock), kBlock, 0, st>>>(sc, rb.bags, a.seed); LB_LAUNCH_CHECK();
     seed = wang_hash(seed);
     LB_CUDA(cudaFuncSetAttribute(k_ris, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRisSmemBytes));      // per device; a host-side setting, no launch
-    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, &fv.counters[CNT_TICKET0 + ticket++], seed); LB_LAUNCH_CHECK();
+    k_ris_order<<<1, 1024, 0, st>>>(seed, fv.npix, fv.pix0, rb.ris_order); LB_LAUNCH_CHECK();
+    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed); LB_LAUNCH_CHECK();
     lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
     k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
