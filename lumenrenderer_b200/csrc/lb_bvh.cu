@@ -22,7 +22,10 @@ namespace lb {
 
 namespace {
 
-constexpr uint32_t kLeafMax = 3;
+#ifndef LB_LEAF_MAX
+#define LB_LEAF_MAX 3            // triangles per leaf child (the node meta byte has 3 unary bits); A/B builds: 1, 2
+#endif
+constexpr uint32_t kLeafMax = LB_LEAF_MAX;
 
 __device__ __forceinline__ int float_order(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 __device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }

@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 
 // visibility of the reservoir's sample + shading of the survivor into DIRECT, one kernel
 struct VisibilityJob {
+    static constexpr bool kDeferDone = true;
     FrameView fv; float shaded; uint32_t traced;
     float4 r0;                                                  // lane state between load and done: weightSum, weight, count, pdf
     LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) {

@@ -222,6 +222,7 @@ LB_D bool bvh8_trace(const BvhView& bvh, const float3& o, const float3& d, float
 // A warp works through queue entries [0, n) handed out by a device ticket.
 //   job.load(i, o, d, tmin, tmax) -> bool : fetch entry i; false = the entry needs no ray (job.done is still called, hit = false)
 //   job.done(i, hit, tracer)              : consume the result (ANY: hit = occluded; else hit = tracer.found)
+//   Job::kDeferDone                       : consume results when the lane is refilled (jobs whose done() waits for memory) or at once
 // All 32 lanes of the warp must call this together.
 template <bool ANY, class Job>
 LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job, const TraceTuning tune) {
@@ -230,11 +231,16 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
     uint2 stack_mem[kTraceStack];
     Tracer tr; tr.stack = stack_mem; tr.cur = make_uint2(0u, 0u); tr.sp = 0;
     uint32_t item = 0u; bool live = false, exhausted = false;
+    // A finished ray's result is consumed (job.done: for shadow / visibility rays a dependent load + read-modify-write) when its lane is
+    // refilled, together with the other finished lanes of the warp, not at the moment it finishes: the warp then waits for that memory
+    // round trip once per refill batch instead of once per ray.
+    bool fin = false, fin_hit = false;
     for (;;) {
         // ---- refill idle lanes from the queue
         const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !live);
         if (idle != 0u && !exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= tune.refill_min)) {
             if (!live) {
+                if (fin) { job.done(item, fin_hit, tr); fin = false; }
                 uint32_t base = 0u;
                 const int leader = __ffs(idle) - 1;
                 if ((int)lane == leader) base = atomicAdd(ticket, (uint32_t)__popc(idle));
@@ -259,15 +265,16 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
             const int live_n = 32 - __popc(idle);
             while (tri_mask != 0u && (node_mask == 0u || __popc(tri_mask) * tune.tri_quarter >= live_n)) {
                 if (live && tr.is_tri()) {
-                    if (tr.template tri_step<ANY>(bvh)) { job.done(item, true, tr); live = false; }
+                    if (tr.template tri_step<ANY>(bvh)) { if (Job::kDeferDone) { fin = true; fin_hit = true; } else job.done(item, true, tr); live = false; }
                 }
                 tri_mask = __ballot_sync(0xFFFFFFFFu, live && tr.is_tri());
             }
             if (live && tr.is_tri()) tr.swap_in_node();
         }
         // ---- every live lane holds a non-empty group for the next round, or retires
-        if (live && !tr.refill_group()) { job.done(item, ANY ? false : tr.found, tr); live = false; }
+        if (live && !tr.refill_group()) { if (Job::kDeferDone) { fin = true; fin_hit = ANY ? false : tr.found; } else job.done(item, ANY ? false : tr.found, tr); live = false; }
     }
+    if (fin) job.done(item, fin_hit, tr);
 }
 
 } // namespace lb

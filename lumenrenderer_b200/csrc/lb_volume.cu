@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kBlock) k_volume_extend(const float4* __restri
 
 // volumetric shadow rays of the compat march: several per pixel and launch -> atomic adds (all carry the same constant radiance)
 struct VolShadowJob {
+    static constexpr bool kDeferDone = false;
     ShadowQueue q; float4* channels; size_t npix; float tmin;
     LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { const float4 o4 = q.o[i]; o = f3(o4); d = f3(q.d[i]); t0 = tmin; t1 = o4.w; return true; }
     LB_D void done(uint32_t i, bool occluded, const Tracer&) const {

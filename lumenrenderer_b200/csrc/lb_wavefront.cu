@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(FrameView fv, CameraBasis cam
 
 // ------------------------------------------------------------------ K2 extend: persistent warps, per-lane ray refill (trace_queue)
 struct ExtendJob {
+    static constexpr bool kDeferDone = false;
     const float4* __restrict__ ro; const float4* __restrict__ rd; uint4* __restrict__ hits; float tmin, tmax;
     LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { o = f3(ro[i]); d = f3(rd[i]); t0 = tmin; t1 = tmax; return true; }
     LB_D void done(uint32_t i, bool hit, const Tracer& tr) const {
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv,
 // One shadow ray per pixel per launch (one NEE sample per wave), so the fp32 read-modify-write below is race free —
 // the reference's fp16 RMW is racy (SURVEY hazard 2).
 struct ShadowJob {
+    static constexpr bool kDeferDone = true;
     ShadowQueue q; float4* channels; size_t npix; float tmin;
     LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) const { const float4 o4 = q.o[i]; o = f3(o4); d = f3(q.d[i]); t0 = tmin; t1 = o4.w; return true; }
     LB_D void done(uint32_t i, bool occluded, const Tracer&) const {
