@@ -38,6 +38,16 @@ ALG_BYTES = {"raygen": 40.0, "extend": 40.0, "shadow": 44.0, "extract": 232.0, "
              "ris": 256.0, "vis_gen": 288.0, "vis_trace": 32.0, "res_shade": 96.0, "temporal": 612.0, "spatial": 336.0, "combine": 416.0, "merge": 84.0}
 
 
+# what bounds each stage (ncu, profiles/r01_v_frame.md): goes into the `roofline` object of the stage where most of the frame goes
+STAGE_NOTES = {
+    "restir_ris": "instruction-issue bound (74 % issue utilisation): 32 Disney BSDF evaluations per pixel on light records staged in shared memory",
+    "restir_visibility": "instruction-issue bound (78 % issue utilisation, 20 of 32 lanes active): traversal of incoherent any-hit rays on an L2-resident BVH; DRAM traffic is a fifth of the algorithmic bytes because only the planes a pixel needs are touched",
+    "restir_spatial": "L2 gather latency (3.5 stalled warps per issue on long scoreboard) + BSDF re-evaluation",
+    "extend": "instruction-issue bound (77 %): BVH8 traversal, BVH entirely L2-resident",
+    "shade": "dependent texture gathers and BSDF arithmetic at 2 blocks per SM",
+}
+
+
 def stage_table(stage_ms, fc, npix, depth, peak, traffic):
     """Per-stage achieved GB/s = algorithmic bytes of the stage (SURVEY 8d per-unit figure x units of this frame) / device time of the stage."""
     ext, sh, vis = fc["extend_rays"], fc["shadow_rays"], fc["visibility_rays"]
@@ -299,7 +309,7 @@ def run_gpu(args):
         roofline = {"kernel": top["kernel"], "stage": top["stage"], "bound": "hbm", "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
                     "peak_source": peak_source, "traffic": top["traffic"], "alg_bytes_per_frame": top["alg_bytes"], "alg_bytes_how": top["alg_bytes_how"],
                     "ms_per_frame": top["ms_per_frame"], "share_of_frame": top["share_of_frame"],
-                    "note": "compute (instruction-issue) bound: 32 Disney BSDF evaluations per pixel; reported against HBM because no stage is a dense contraction"}
+                    "note": STAGE_NOTES.get(top["stage"], "") + "; reported against HBM because no stage is a dense contraction"}
         roofline_extend = {"kernel": "k_extend (BVH8 traversal, all waves of a frame)", "bound": "hbm", "achieved": ext["achieved"], "peak": peak, "unit": "GB/s", "frac": ext["frac"],
                            "peak_source": peak_source, "traffic": ext["traffic"], "alg_bytes_per_ray": ALG_BYTES["extend"], "rays_per_launch_avg": fc["extend_rays"] / args.depth,
                            "ms_per_frame": ext["ms_per_frame"], "share_of_frame": ext["share_of_frame"], "mrays_per_s": fc["extend_rays"] / (ext["ms_per_frame"] * 1e-3) / 1e6}
