@@ -69,7 +69,9 @@ struct Renderer {
     DevBuf<DevVolume> d_volumes; std::vector<std::unique_ptr<DevBuf<float>>> d_volume_grids;
     std::vector<uint32_t> prim_index_base, prim_vertex_base, prim_flag_offset;
     std::vector<DevEntry> h_entries;
-    DeviceBvh bvh; LightBuild lights;
+    // Two hierarchies over the same triangles (hits are a pure function of ray and triangle set, so which hierarchy answers is free):
+    // `bvh` serves closest-hit rays (extend), `bvh_any` any-hit rays (shadow, ReSTIR visibility). DESIGN.md "Two hierarchies".
+    DeviceBvh bvh, bvh_any; bool dual_bvh = false; LightBuild lights;
     uint32_t total_tris = 0;
 
     // ---- frame state
@@ -272,6 +274,10 @@ struct Renderer {
         {   // LB_BVH_BUILDER=lbvh selects the fastest build (Karras radix tree); default is the SAH-quality PLOC hierarchy
             const char* e = getenv("LB_BVH_BUILDER");
             bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC);
+            // LB_BVH_ANYHIT=same: one hierarchy for every ray (halves the build); default: a second PLOC hierarchy with a 128-wide search window
+            const char* a = getenv("LB_BVH_ANYHIT");
+            dual_bvh = !(a && !strcmp(a, "same")) && total_tris > 1u;
+            if (dual_bvh) bvh_build(stream, d_flat.p, total_tris, bvh_any, BvhBuilder::PLOC, a && !strcmp(a, "ploc64") ? 64 : 128);
         }
         lights.num_lights = 0; lights.cdf_sum = 0.f;
         if (total_tris) build_lights(cfg(), scene_view(), in, d_prim_flags.p, lights);
@@ -290,8 +296,8 @@ struct Renderer {
         }
         d_volumes.upload(dv.data(), dv.size(), stream);
         LB_CUDA(cudaStreamSynchronize(stream));
-        counters[4] = lights.num_lights; counters[5] = total_tris; counters[6] = bvh.num_nodes; counters[7] = bvh.bytes();
-        counters[8] = (uint64_t)(bvh.build_ms * 1000.f); counters[9] = bvh.levels; counters[10] = bvh.ploc_rounds;
+        counters[4] = lights.num_lights; counters[5] = total_tris; counters[6] = bvh.num_nodes + (dual_bvh ? bvh_any.num_nodes : 0u); counters[7] = bvh.bytes() + (dual_bvh ? bvh_any.bytes() : 0u);
+        counters[8] = (uint64_t)((bvh.build_ms + (dual_bvh ? bvh_any.build_ms : 0.f)) * 1000.f); counters[9] = bvh.levels; counters[10] = bvh.ploc_rounds;
         scene_dirty = false;
     }
 
@@ -358,7 +364,7 @@ struct Renderer {
         const LaunchCfg c = cfg();
         FrameView fv = frame_view();
         const SceneView sc = scene_view();
-        const BvhView bv = bvh.view();
+        const BvhView bv = bvh.view(), bva = dual_bvh ? bvh_any.view() : bvh.view();
         const uint32_t stride = st.frame_count_stride ? st.frame_count_stride : 2u;
         const uint32_t frame_count = st.first_frame_count + 1u + stride * frame_index;      // the reference's counter advances twice per frame
         uint32_t launches = 0;
@@ -408,12 +414,12 @@ struct Renderer {
                     ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
                 } else ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 0); };
                 ra.lap_user = this;
-                launch_restir(cr, fv, sc, bv, rb, ra, ticket);
+                launch_restir(cr, fv, sc, bva, rb, ra, ticket);
                 if (forked) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
                 if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
             }
-            if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("shadow"); }
-            if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bv, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
+            if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("shadow"); }
+            if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
         if (forked) { LB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); lap("restir_join"); }    // the time the bounce chain waited for the ReSTIR chain
@@ -747,7 +753,7 @@ LB_API int lb_debug_trace_any(LbRenderer r, const float* rays6, const float* tma
         if (!n) return (int)LB_OK;
         DevBuf<float> d_rays, d_tmax; DevBuf<uint8_t> d_occ;
         d_rays.upload(rays6, (size_t)n * 6, R_->stream); d_tmax.upload(tmaxs, n, R_->stream); d_occ.reserve(n);
-        launch_debug_trace(R_->cfg(), R_->bvh.view(), d_rays.p, d_tmax.p, n, tmin, 0.f, nullptr, d_occ.p);
+        launch_debug_trace(R_->cfg(), R_->dual_bvh ? R_->bvh_any.view() : R_->bvh.view(), d_rays.p, d_tmax.p, n, tmin, 0.f, nullptr, d_occ.p);
         return read_back(R_, d_occ.p, n, occ, n);
     });
 }

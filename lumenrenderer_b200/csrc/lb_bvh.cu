@@ -140,7 +140,9 @@ __global__ void k_refit(const uint32_t* __restrict__ sorted, const float4* __res
 }
 
 // ---- PLOC. Clusters live in three parallel arrays in Morton order: node id, box lo, box hi.
-constexpr int kPlocRadius = 16, kPlocBlock = 256;
+// Neighbour search window of PLOC in Morton order, chosen per hierarchy (bvh_build's ploc_radius): 16 for the closest-hit hierarchy,
+// 128 for the any-hit one (measured on C2, DESIGN.md "Two hierarchies").
+constexpr int kPlocBlock = 256;
 
 __global__ void k_ploc_init(const uint32_t* __restrict__ sorted, const float4* __restrict__ tlo, const float4* __restrict__ thi, uint32_t n,
                             uint32_t* __restrict__ cl, float4* __restrict__ clo, float4* __restrict__ chi, float4* __restrict__ nlo, float4* __restrict__ nhi, uint32_t* __restrict__ count) {
@@ -152,6 +154,7 @@ __global__ void k_ploc_init(const uint32_t* __restrict__ sorted, const float4* _
 }
 
 // nearest neighbour of every cluster within +-kPlocRadius positions: smallest surface area of the merged box, ties to the smaller index
+template <int kPlocRadius>
 __global__ void __launch_bounds__(kPlocBlock) k_ploc_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, uint32_t m, uint32_t* __restrict__ nearest) {
     __shared__ float4 slo[kPlocBlock + 2 * kPlocRadius], shi[kPlocBlock + 2 * kPlocRadius];
     const int first = (int)(blockIdx.x * kPlocBlock) - kPlocRadius;
@@ -314,7 +317,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
 
 } // namespace
 
-void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder) {
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder, int ploc_radius) {
     out.num_nodes = 0; out.num_tris = 0; out.levels = 0; out.build_ms = 0.f; out.ploc_rounds = 0;
     if (n == 0) return;
     cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
@@ -358,7 +361,10 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
         uint32_t m = n; int cur = 0;
         while (m > 1u) {
-            k_ploc_nearest<<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p); LB_LAUNCH_CHECK();
+            if (ploc_radius >= 128) k_ploc_nearest<128><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
+            else if (ploc_radius >= 64) k_ploc_nearest<64><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
+            else k_ploc_nearest<16><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
+            LB_LAUNCH_CHECK();
             k_ploc_merge<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, nearest.p, m, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, keep.p); LB_LAUNCH_CHECK();
             LB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, scan_bytes, keep.p, offset.p, (int)m, s));
             k_ploc_compact<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, keep.p, offset.p, m, cl[cur ^ 1].p, clo[cur ^ 1].p, chi[cur ^ 1].p, m_dev.p); LB_LAUNCH_CHECK();

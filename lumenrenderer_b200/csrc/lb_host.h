@@ -56,7 +56,8 @@ struct DeviceBvh {
 // -> greedy surface-area collapse into compressed 8-wide nodes. Replaces optixAccelBuild (LumenPT/src/Framework/OptixWrapper.cpp:46-131).
 // tris_in: world-space triangles in any order; the builder writes its own leaf-ordered copy into out.tris.
 enum class BvhBuilder { PLOC, LBVH };
-void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC);
+// ploc_radius: neighbour search window of PLOC in Morton order (16, 64 or 128)
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC, int ploc_radius = 16);
 
 inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 
