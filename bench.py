@@ -274,7 +274,7 @@ def run_gpu(args):
     # ---- per-stage device time (CUDA events on the renderer's stream, per frame) for the roofline lines
     # Stage times are taken with the two chains of a frame serialised (lb_set_overlap(0), the default): every stage time is an exclusive
     # device time. LB_OVERLAP=1 runs the timed regions above with the ReSTIR chain and the bounce chain on two streams (an experiment).
-    r.set_overlap(False)
+    r.set_overlap(0)
     r.render_frames(1)
     stage_ms, stage_frames = {}, max(3, min(args.steps, 10))
     for _ in range(stage_frames):
@@ -324,8 +324,8 @@ def run_gpu(args):
                 "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
-                "overlap": {"enabled": os.environ.get("LB_OVERLAP", "0") != "0", "ms_per_frame_serialised": serial_ms,
-                            "note": "optional mode (LB_OVERLAP=1): ReSTIR passes and bounce waves (depth > 0) of a frame as two chains forked after the primary shade and joined before the merge; off by default (measured slower); stage_ms / roofline_kernels are always exclusive times measured with the chains serialised"},
+                "overlap": {"mode": int(os.environ.get("LB_OVERLAP", "1")), "ms_per_frame_serialised": serial_ms,
+                            "note": "mask: bit 0 (default) = shadow rays of bounce wave d on a side stream under the extend launch of wave d+1; bit 1 (off, measured slower) = ReSTIR chain beside the bounce waves; stage_ms / roofline_kernels are always exclusive times measured with mode 0"},
                 "roofline": roofline, "roofline_extend": roofline_extend, "roofline_kernels": table, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
         print(json.dumps(line), flush=True)
     r.close()

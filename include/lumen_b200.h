@@ -322,11 +322,13 @@ LB_API int lb_volume_create_file(LbRenderer r, const char* path, LbHandle* out);
 LB_API int lb_hdr_buffer(LbRenderer r, void** device_ptr, size_t* bytes);
 LB_API int lb_accum_buffer(LbRenderer r, void** device_ptr, size_t* bytes, uint32_t* frames);
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
-/* Overlap mode (default OFF — measured slower on B200; environment LB_OVERLAP=1 turns it on at creation): the ReSTIR passes of a frame and its bounce waves
- * (depth > 0) are independent — they fork after the primary shade and join before the merge (the reference serialises every kernel with
- * cudaDeviceSynchronize, PT/Framework/WaveFrontRenderer.cpp:604-850). Results are identical either way; with overlap off every stage time
- * of lb_frame_stats is an exclusive device time (what bench.py uses for its per-kernel roofline table). */
-LB_API int lb_set_overlap(LbRenderer r, int enabled);
+/* Overlap mode, a mask (environment LB_OVERLAP sets it at creation). The reference serialises every kernel with cudaDeviceSynchronize
+ * (PT/Framework/WaveFrontRenderer.cpp:604-850); here independent launches of a frame may share the device:
+ *   bit 0 (default ON)  the shadow rays of bounce wave d run on a side stream under the extend launch of wave d + 1;
+ *   bit 1 (default OFF — measured slower on B200) the ReSTIR passes run on the side stream beside the bounce waves.
+ * Results are identical in every mode; with mode 0 every stage time of lb_frame_stats is an exclusive device time (what bench.py uses for
+ * its per-kernel roofline table). */
+LB_API int lb_set_overlap(LbRenderer r, int mode);
 /* Run all work on an externally owned CUDA stream (e.g. torch's current stream); 0/NULL = the renderer's own. */
 LB_API int lb_set_stream(LbRenderer r, void* cuda_stream);
 

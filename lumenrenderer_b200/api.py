@@ -556,9 +556,10 @@ class Renderer:
     def resolve_accum(self, total_frames: int):
         self.b.check(self.b.resolve_accum(self._h, total_frames))
 
-    def set_overlap(self, enabled: bool):
-        """ReSTIR chain and bounce chain of a frame on two streams (default) or serialised (exclusive stage times)."""
-        self.b.check(self.b.set_overlap(self._h, 1 if enabled else 0))
+    def set_overlap(self, mode: int):
+        """Overlap mask: bit 0 = bounce-wave shadow rays under the next extend launch (default), bit 1 = ReSTIR chain beside the bounce
+        waves; 0 = every launch serialised (exclusive stage times)."""
+        self.b.check(self.b.set_overlap(self._h, int(mode)))
 
     def set_stream(self, cuda_stream: int):
         self.b.check(self.b.set_stream(self._h, C.c_void_p(cuda_stream)))

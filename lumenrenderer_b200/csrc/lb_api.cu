@@ -97,7 +97,9 @@ struct Renderer {
     // the bounce waves (extend / shade / shadow at depth > 0) write only the other channels. They run as two chains that fork after the
     // primary shade and join before the merge, so that the latency-bound tail waves can execute under the ReSTIR kernels. Off by default:
     // on B200 the two chains of persistent grids interfere (8.45 -> 8.87..9.45 ms/frame, profiles/r01_p_experiments.md).
-    bool overlap = overlap_default(); cudaStream_t restir_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // `overlap` is a mask: bit 0 (default on) = the shadow rays of bounce wave d run on the side stream under the extend of wave d + 1 — two
+    // small latency-bound launches that share nothing but read-only data; bit 1 (default off) = the ReSTIR chain on the side stream.
+    int overlap = overlap_default(); cudaStream_t restir_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_shadow = nullptr;
     std::string stats_names;
 
     // ---- render thread (StartRendering, WaveFrontRenderer.cpp:1109-1117)
@@ -106,14 +108,14 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
-    static bool overlap_default() { const char* e = getenv("LB_OVERLAP"); return e && atoi(e) != 0; }      // off: measured slower
-    static TraceTuning trace_tuning() {
+    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 3) : 1; }      // ReSTIR-chain overlap (bit 1) off: measured slower
+    static TraceTuning trace_tuning(bool any) {
         TraceTuning t;
-        if (const char* e = getenv("LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
-        if (const char* e = getenv("LB_TRACE_TRI_QUARTER")) t.tri_quarter = atoi(e);
+        if (const char* e = getenv(any ? "LB_TRACE_ANY_REFILL_MIN" : "LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
+        if (const char* e = getenv(any ? "LB_TRACE_ANY_TRI_QUARTER" : "LB_TRACE_TRI_QUARTER")) t.tri_quarter = atoi(e);
         return t;
     }
-    LaunchCfg cfg() const { static const TraceTuning tune = trace_tuning(); LaunchCfg c; c.sms = sms; c.stream = stream; c.trace = tune; return c; }
+    LaunchCfg cfg() const { static const TraceTuning tune = trace_tuning(false), tune_any = trace_tuning(true); LaunchCfg c; c.sms = sms; c.stream = stream; c.trace = tune; c.trace_any = tune_any; return c; }
 
     ~Renderer() {
         stop_thread();
@@ -127,6 +129,7 @@ struct Renderer {
         if (restir_stream) { cudaStreamSynchronize(restir_stream); cudaStreamDestroy(restir_stream); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_shadow) cudaEventDestroy(ev_shadow);
     }
     void stop_thread() {
         if (render_thread.joinable()) { stop_flag = true; render_thread.join(); }
@@ -348,6 +351,14 @@ struct Renderer {
         return fv;
     }
 
+    void need_side_stream() {
+        if (restir_stream) return;
+        int lo = 0, hi = 0; LB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        static const bool high = []() { const char* e = getenv("LB_OVERLAP_PRIORITY"); return !e || atoi(e) != 0; }();
+        LB_CUDA(cudaStreamCreateWithPriority(&restir_stream, cudaStreamNonBlocking, high ? hi : lo));
+        LB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        LB_CUDA(cudaEventCreateWithFlags(&ev_shadow, cudaEventDisableTiming));
+    }
     void lap(const char* name, int chain = 0) {
         if (events_used == event_pool.size()) { cudaEvent_t e; LB_CUDA(cudaEventCreate(&e)); event_pool.push_back(e); }
         cudaEvent_t e = event_pool[events_used++];
@@ -377,11 +388,13 @@ struct Renderer {
         ShadeArgs a{}; a.max_depth = st.depth;
         a.volumes = d_volumes.p; a.num_volumes = (uint32_t)vinstances.size(); a.volume_mode = (int)st.volume_mode;
         prev_view_proj(a.prev_view_proj);
-        bool forked = false;
+        bool forked = false, shadow_in_flight = false;
         for (uint32_t depth = 0; depth < st.depth; ++depth) {
             const int queue = (int)(depth & 1u);
             launch_extend(c, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
             lap("extend");
+            // the previous wave's shadow rays (side stream) read the shadow queue this wave's shade kernel is about to refill
+            if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
             // the next wave's queue and this wave's shadow queues start empty
             LB_CUDA(cudaMemsetAsync(d_counters.p + (queue ? CNT_RAYS_A : CNT_RAYS_B), 0, sizeof(uint32_t), stream));
             LB_CUDA(cudaMemsetAsync(d_counters.p + CNT_SHADOW, 0, sizeof(uint32_t), stream));
@@ -400,15 +413,10 @@ struct Renderer {
             if (depth == 0 && st.restir) {
                 RestirArgs ra{seed, (int)st.restir_temporal, (int)st.restir_spatial};
                 RestirBuffers rb{d_bags.p, d_ris_order.p};
-                forked = overlap && st.depth > 1 && sc.num_lights != 0u && a.num_volumes == 0u;      // media: volume shadow rays also write DIRECT at depth 0
+                forked = (overlap & 2) && st.depth > 1 && sc.num_lights != 0u && a.num_volumes == 0u;      // media: volume shadow rays also write DIRECT at depth 0
                 LaunchCfg cr = c;
                 if (forked) {
-                    if (!restir_stream) {
-                        int lo = 0, hi = 0; LB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                        static const bool high = []() { const char* e = getenv("LB_OVERLAP_PRIORITY"); return !e || atoi(e) != 0; }();
-                        LB_CUDA(cudaStreamCreateWithPriority(&restir_stream, cudaStreamNonBlocking, high ? hi : lo));   // the ReSTIR chain is the critical path
-                        LB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-                    }
+                    need_side_stream();
                     LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
                     cr.stream = restir_stream; last_lap[1] = last_lap[0];
                     ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
@@ -418,10 +426,22 @@ struct Renderer {
                 if (forked) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
                 if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
             }
-            if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) { launch_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("shadow"); }
+            if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) {
+                // bounce waves: this launch and the next wave's extend are both small and latency-bound (each lasts as long as its slowest
+                // ray) and touch disjoint buffers — the shadow rays go to the side stream and are joined before the next shade
+                const bool side = (overlap & 1) && !forked && depth >= 1u && depth + 1u < st.depth && a.num_volumes == 0u;
+                if (side) {
+                    need_side_stream();
+                    LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
+                    LaunchCfg cs = c; cs.stream = restir_stream; last_lap[1] = last_lap[0];
+                    launch_shadow(cs, fv, bva, ticket++, 0.01f); ++launches; lap("shadow", 1);
+                    LB_CUDA(cudaEventRecord(ev_shadow, restir_stream)); shadow_in_flight = true;
+                } else { launch_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("shadow"); }
+            }
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
+        if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
         if (forked) { LB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); lap("restir_join"); }    // the time the bounce chain waited for the ReSTIR chain
         if (copy_pending) LB_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));      // an asynchronous read-back still owns the combined buffer
         launch_merge(c, fv, (int)st.blend_output, blend_count); ++launches;
@@ -730,7 +750,7 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
     return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
 }
 LB_API int lb_set_overlap(LbRenderer r, int enabled) {
-    return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled != 0; return (int)LB_OK; });
+    return guarded(R_, [&]() { if (enabled < 0 || enabled > 3) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
 }
 LB_API int lb_set_stream(LbRenderer r, void* s) {
     return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->stream = s ? (cudaStream_t)s : R_->own_stream; return (int)LB_OK; });

@@ -17,7 +17,7 @@ enum : uint32_t { STAT_EXTEND = 0, STAT_SHADOW = 1, STAT_VIS = 2, kNumStats = 4 
 
 struct CameraBasis { float3 eye, U, V, W; };
 
-struct LaunchCfg { int sms = 148; cudaStream_t stream = nullptr; TraceTuning trace; };
+struct LaunchCfg { int sms = 148; cudaStream_t stream = nullptr; TraceTuning trace, trace_any; };      // warp-scheduling knobs of closest-hit / any-hit launches
 
 struct FrameView {
     uint32_t width = 0, height = 0, npix = 0;

@@ -425,7 +425,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed); LB_LAUNCH_CHECK();
     lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
-    k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
+    k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
     lap("restir_visibility");
     if (a.temporal) {
         seed = wang_hash(seed);
@@ -440,7 +440,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
         lap("restir_spatial");
-        k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace); LB_LAUNCH_CHECK();
+        k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
         lap("restir_visibility");
         k_combine<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
         lap("restir_combine");

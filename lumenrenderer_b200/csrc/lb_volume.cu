@@ -99,7 +99,7 @@ void launch_volume_extend(const LaunchCfg& cfg, const FrameView& fv, int queue, 
         volumes, num_volumes, tmin, tmax, fv.vol_hits); LB_LAUNCH_CHECK();
 }
 void launch_volume_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
-    k_vol_shadow<<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(bvh, fv.vol_shadow, &fv.counters[CNT_VOL_SHADOW], &fv.counters[CNT_TICKET0 + ticket], fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace); LB_LAUNCH_CHECK();
+    k_vol_shadow<<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(bvh, fv.vol_shadow, &fv.counters[CNT_VOL_SHADOW], &fv.counters[CNT_TICKET0 + ticket], fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace_any); LB_LAUNCH_CHECK();
 }
 void launch_volume_delta(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, int queue, bool primary, const ShadeArgs& a) {
     if (primary) k_volume_delta<true><<<cfg.sms * 4, kBlock, 0, cfg.stream>>>(fv, sc, queue, a);

@@ -262,7 +262,7 @@ void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc
 }
 void launch_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
     k_shadow<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.shadow, &fv.counters[CNT_SHADOW], &fv.counters[CNT_TICKET0 + ticket],
-        fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace); LB_LAUNCH_CHECK();
+        fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace_any); LB_LAUNCH_CHECK();
 }
 void launch_merge(const LaunchCfg& cfg, const FrameView& fv, int blend, uint32_t blend_count) {
     k_merge<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, blend, blend_count); LB_LAUNCH_CHECK();
