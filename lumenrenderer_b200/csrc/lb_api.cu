@@ -146,6 +146,10 @@ struct Renderer {
         if (prop.major != 10) throw CudaError("liblumen_b200 is built for sm_100a (B200) only; no usable device and no fallback path");
         sms = prop.multiProcessorCount;
         LB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        {   // build scratch comes from the default stream-ordered pool (StreamBuf, lb_host.h): keep up to 4 GiB cached between scene commits
+            cudaMemPool_t pool = nullptr; LB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = 4ull << 30; LB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         stream = own_stream;
         LB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         LB_CUDA(cudaEventCreateWithFlags(&ev_rendered, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&ev_copied, cudaEventDisableTiming));

@@ -324,11 +324,11 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     LB_CUDA(cudaEventRecord(e0, s));
 
     const uint32_t n_binary = 2u * n - 1u;
-    DevBuf<float4> tlo, thi, nlo, nhi; DevBuf<int> cbounds; DevBuf<uint64_t> keys, keys_sorted; DevBuf<uint32_t> vals, sorted, count, counters;
-    DevBuf<uint2> children; DevBuf<WorkItem> items_a, items_b; DevBuf<unsigned char> cub_tmp;
-    tlo.reserve(n); thi.reserve(n); nlo.reserve(n_binary); nhi.reserve(n_binary); count.reserve(n_binary); cbounds.reserve(6);
-    keys.reserve(n); keys_sorted.reserve(n); vals.reserve(n); sorted.reserve(n); counters.reserve(4);
-    children.reserve(n); items_a.reserve(n); items_b.reserve(n);
+    StreamBuf<float4> tlo, thi, nlo, nhi; StreamBuf<int> cbounds; StreamBuf<uint64_t> keys, keys_sorted; StreamBuf<uint32_t> vals, sorted, count, counters;
+    StreamBuf<uint2> children; StreamBuf<WorkItem> items_a, items_b; StreamBuf<unsigned char> cub_tmp;
+    tlo.reserve(n, s); thi.reserve(n, s); nlo.reserve(n_binary, s); nhi.reserve(n_binary, s); count.reserve(n_binary, s); cbounds.reserve(6, s);
+    keys.reserve(n, s); keys_sorted.reserve(n, s); vals.reserve(n, s); sorted.reserve(n, s); counters.reserve(4, s);
+    children.reserve(n, s); items_a.reserve(n, s); items_b.reserve(n, s);
     out.nodes.reserve(n); out.tris.reserve(n);
 
     const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
@@ -338,25 +338,25 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     k_morton<<<grid_for(n, B), B, 0, s>>>(tlo.p, thi.p, n, cbounds.p, keys.p, vals.p); LB_LAUNCH_CHECK();
     size_t tmp_bytes = 0;
     LB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
-    cub_tmp.reserve(tmp_bytes);
+    cub_tmp.reserve(tmp_bytes, s);
     LB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
 
     uint32_t root = 0u;                                     // binary node ids: internal [0, n-2], leaf j = (n-1) + j
     if (builder == BvhBuilder::LBVH || n == 1) {
-        DevBuf<uint32_t> parent, flags; DevBuf<uint2> range;
-        parent.reserve(n_binary); flags.reserve(n); range.reserve(n);
-        flags.zero(s);
+        StreamBuf<uint32_t> parent, flags; StreamBuf<uint2> range;
+        parent.reserve(n_binary, s); flags.reserve(n, s); range.reserve(n, s);
+        flags.zero();
         if (n > 1) { k_hierarchy<<<grid_for(n - 1, B), B, 0, s>>>(keys_sorted.p, (int)n, children.p, parent.p, range.p); LB_LAUNCH_CHECK(); }
         k_refit<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, (int)n, children.p, parent.p, nlo.p, nhi.p, count.p, flags.p); LB_LAUNCH_CHECK();
         LB_CUDA(cudaStreamSynchronize(s));                  // the temporaries above are released here
     } else {
         // PLOC: the cluster arrays ping-pong through a flag / exclusive-scan / scatter compaction every round
-        DevBuf<uint32_t> cl[2], nearest, keep, offset, m_dev; DevBuf<float4> clo[2], chi[2];
-        for (int k = 0; k < 2; ++k) { cl[k].reserve(n); clo[k].reserve(n); chi[k].reserve(n); }
-        nearest.reserve(n); keep.reserve(n); offset.reserve(n); m_dev.reserve(2);
+        StreamBuf<uint32_t> cl[2], nearest, keep, offset, m_dev; StreamBuf<float4> clo[2], chi[2];
+        for (int k = 0; k < 2; ++k) { cl[k].reserve(n, s); clo[k].reserve(n, s); chi[k].reserve(n, s); }
+        nearest.reserve(n, s); keep.reserve(n, s); offset.reserve(n, s); m_dev.reserve(2, s);
         size_t scan_bytes = 0;
         LB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep.p, offset.p, (int)n, s));
-        cub_tmp.reserve(scan_bytes);
+        cub_tmp.reserve(scan_bytes, s);
         LB_CUDA(cudaMemsetAsync(m_dev.p, 0, 2 * sizeof(uint32_t), s));          // [0]: cluster count after the round, [1]: next internal node id
         k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
         uint32_t m = n; int cur = 0;

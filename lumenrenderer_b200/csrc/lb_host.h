@@ -44,6 +44,24 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Scratch buffer of a build step: stream-ordered allocation from the device's default memory pool (cudaMallocAsync / cudaFreeAsync on the
+// build's stream). The renderer raises the pool's release threshold at creation, so a scene that is re-committed every frame (dynamic
+// scenes) re-uses the pool's cached blocks instead of paying ~25 cudaMalloc / cudaFree (each a device-wide synchronisation) per build.
+template <class T>
+struct StreamBuf {
+    T* p = nullptr; size_t n = 0; cudaStream_t s = nullptr;
+    StreamBuf() = default;
+    StreamBuf(const StreamBuf&) = delete; StreamBuf& operator=(const StreamBuf&) = delete;
+    ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+    void reserve(size_t count, cudaStream_t stream) {
+        if (count <= n) return;
+        if (p) { cudaFreeAsync(p, s); p = nullptr; }
+        s = stream; n = count;
+        if (count) LB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+    }
+    void zero() { if (n) LB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
 struct DeviceBvh {
     DevBuf<Bvh8Node> nodes; DevBuf<DevTri> tris;
     uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0;
