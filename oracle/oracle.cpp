@@ -56,6 +56,20 @@ struct Reservoir {                                                            //
     }
     void reset() { weight_sum = 0; count = 0; weight = 0; }
 };
+// CDF::Get / BinarySearch (ReSTIRData.h:232-302) over the accumulated sums cdf[0..n): index of the entry whose interval holds value * sum
+static void cdf_lookup(const float* cdf, int n, float cdf_sum, float value, uint32_t& index, float& pdf) {
+    const float required = cdf_sum * value;
+    int first = 0, last = n - 1, center = 0;
+    for (;;) {
+        center = (last + first) / 2;
+        const float higher = cdf[center], lower = center ? cdf[center - 1] : 0.f;
+        if (required < lower && center - 1 >= first) { last = center - 1; continue; }
+        if (required > higher && center + 1 <= last) { first = center + 1; continue; }
+        break;
+    }
+    const float higher = cdf[center], lower = center ? cdf[center - 1] : 0.f;
+    index = (uint32_t)center; pdf = (higher - lower) / cdf_sum;
+}
 struct BagEntry { uint32_t light; float pdf; };                              // LightBagEntry, ReSTIRData.h:308-312 (light by index)
 struct VolumeHit { float t0 = -1, t1 = -1; float density = 0; int vinst = -1; };   // VolumetricData.h
 
@@ -226,19 +240,7 @@ struct Renderer {
         counters[4] = n;
     }
     // CDF::Get / BinarySearch, PT/Shaders/CppCommon/ReSTIRData.h:232-302
-    void cdf_get(float value, uint32_t& index, float& pdf) const {
-        const float required = cdf_sum * value;
-        int first = 0, last = (int)cdf.size() - 1, center = 0;
-        for (;;) {
-            center = (last + first) / 2;
-            const float higher = cdf[center], lower = center ? cdf[center - 1] : 0.f;
-            if (required < lower && center - 1 >= first) { last = center - 1; continue; }
-            if (required > higher && center + 1 <= last) { first = center + 1; continue; }
-            break;
-        }
-        const float higher = cdf[center], lower = center ? cdf[center - 1] : 0.f;
-        index = (uint32_t)center; pdf = (higher - lower) / cdf_sum;
-    }
+    void cdf_get(float value, uint32_t& index, float& pdf) const { cdf_lookup(cdf.data(), (int)cdf.size(), cdf_sum, value, index, pdf); }
 
     // ------------------------------------------------------------------ camera (LM/Renderer/Camera.cpp:79-93,122-140)
     void camera_matrix(double m[16]) const {   // row-major world matrix (columns right, up, forward, position)
@@ -1000,6 +1002,19 @@ LB_API int lo_hdr_buffer(LbRenderer r, void** p, size_t* bytes) { CHECK_R; if (!
 LB_API int lo_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* frames) { CHECK_R; *p = R_->accum.data(); *bytes = R_->accum.size() * 16; *frames = R_->blend_count; return LB_OK; }
 LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); const float inv = 1.0f / (float)total;
     for (size_t i = 0; i < R_->accum.size(); ++i) R_->combined[i] = {R_->accum[i].x * inv, R_->accum[i].y * inv, R_->accum[i].z * inv, R_->accum[i].w * inv}; R_->write_ldr(); return LB_OK; }
+// ---- known-answer taps of the ReSTIR data structures (oracle only; checked against the reference's own ReSTIRData.h compiled for the host,
+// oracle/ref_shim/ref_restir.cpp -> tests/golden/restir_reference.npz). Same signatures as ref_kat_reservoir / ref_kat_cdf.
+LB_API void lo_kat_reservoir(const float* weights, const unsigned* seeds, const float* pdfs, unsigned n, float* out5, unsigned char* selected) {
+    Reservoir r; r.sample.radiance.x = -1.f;
+    for (unsigned k = 0; k < n; ++k) { LightSample s; s.pdf = pdfs[k]; s.radiance.x = (float)k; selected[k] = r.update(s, weights[k], seeds[k]) ? 1 : 0; }
+    r.update_weight();
+    out5[0] = r.weight_sum; out5[1] = (float)r.count; out5[2] = r.weight; out5[3] = r.sample.radiance.x; out5[4] = r.sample.pdf;
+}
+LB_API void lo_kat_cdf(const float* weights, unsigned n, const float* values, unsigned m, float* cdf_out, unsigned* index, float* pdf) {
+    float sum = 0.f;
+    for (unsigned k = 0; k < n; ++k) { sum += weights[k]; cdf_out[k] = sum; }          // CDF::Insert, ReSTIRData.h:194-203
+    for (unsigned k = 0; k < m; ++k) { uint32_t i; float p; cdf_lookup(cdf_out, (int)n, sum, values[k], i, p); index[k] = i; pdf[k] = p; }
+}
 LB_API int lo_set_stream(LbRenderer, void*) { return LB_OK; }
 LB_API int lo_set_overlap(LbRenderer r, int) { CHECK_R; return LB_OK; }      // the CPU restatement is one sequence of passes
 

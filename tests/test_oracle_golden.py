@@ -96,3 +96,36 @@ def test_cornell_c1_regression(oracle):
     assert np.array_equal(hits["instance"], g["instance"]) and np.array_equal(hits["primitive"], g["primitive"]) and np.array_equal(hits["t"], g["t"])
     assert rel_l1(r.read_hdr()[..., :3], g["hdr"]) < 1e-6
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# ReSTIR data structures: the reference's own ReSTIRData.h compiled for the host (oracle/ref_shim/ref_restir.cpp) recorded known answers of
+# Reservoir::Update / UpdateWeight and CDF::Insert / Get / BinarySearch (tests/golden/make_golden_restir.py); the oracle's restatement
+# (lo_kat_reservoir / lo_kat_cdf over the very functions its renderer uses) must reproduce them bit for bit.
+def _restir_gold():
+    return np.load(os.path.join(GOLDEN, "restir_reference.npz"))
+
+
+def test_reservoir_update_matches_reference_header(oracle):
+    import ctypes as C
+    z = _restir_gold()
+    for k in range(int(z["res_count"])):
+        w, seeds, pdfs = z[f"res{k}/weights"], z[f"res{k}/seeds"], z[f"res{k}/pdfs"]
+        out, sel = np.zeros(5, np.float32), np.zeros(len(w), np.uint8)
+        oracle.lib.lo_kat_reservoir(w.ctypes.data_as(C.c_void_p), seeds.ctypes.data_as(C.c_void_p), pdfs.ctypes.data_as(C.c_void_p), C.c_uint(len(w)),
+                                    out.ctypes.data_as(C.c_void_p), sel.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(sel, z[f"res{k}/selected"]), f"case {k}: acceptance decisions differ"
+        assert np.array_equal(out.view(np.uint32), z[f"res{k}/out"].view(np.uint32)), f"case {k}: {out} vs {z[f'res{k}/out']}"
+
+
+def test_cdf_lookup_matches_reference_header(oracle):
+    import ctypes as C
+    z = _restir_gold()
+    for k in range(int(z["cdf_count"])):
+        w, v = z[f"cdf{k}/weights"], z[f"cdf{k}/values"]
+        cdf, idx, pdf = np.zeros(len(w), np.float32), np.zeros(len(v), np.uint32), np.zeros(len(v), np.float32)
+        oracle.lib.lo_kat_cdf(w.ctypes.data_as(C.c_void_p), C.c_uint(len(w)), v.ctypes.data_as(C.c_void_p), C.c_uint(len(v)),
+                              cdf.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), pdf.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(cdf.view(np.uint32), z[f"cdf{k}/cdf"].view(np.uint32)), f"case {k}: accumulated sums differ"
+        assert np.array_equal(idx, z[f"cdf{k}/index"]), f"case {k}: {np.flatnonzero(idx != z[f'cdf{k}/index'])[:5]}"
+        assert np.array_equal(pdf.view(np.uint32), z[f"cdf{k}/pdf"].view(np.uint32)), f"case {k}: pdf differs"
