@@ -324,8 +324,8 @@ def run_gpu(args):
                 "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
-                "overlap": {"mode": int(os.environ.get("LB_OVERLAP", "1")), "ms_per_frame_serialised": serial_ms,
-                            "note": "mask: bit 0 (default) = shadow rays of bounce wave d on a side stream under the extend launch of wave d+1; bit 1 (off, measured slower) = ReSTIR chain beside the bounce waves; stage_ms / roofline_kernels are always exclusive times measured with mode 0"},
+                "overlap": {"mode": int(os.environ.get("LB_OVERLAP", "5")), "ms_per_frame_serialised": serial_ms,
+                            "note": "mask: bit 0 = shadow rays of bounce wave d on a side stream under the extend launch of wave d+1; bit 2 = ReSTIR chain launched after the first bounce wave, later waves beside it (default 5); bit 1 (off, measured slower) = ReSTIR chain beside all bounce waves; stage_ms / roofline_kernels are always exclusive times measured with mode 0"},
                 "roofline": roofline, "roofline_extend": roofline_extend, "roofline_kernels": table, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
         print(json.dumps(line), flush=True)
     r.close()

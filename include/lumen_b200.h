@@ -325,7 +325,9 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
 /* Overlap mode, a mask (environment LB_OVERLAP sets it at creation). The reference serialises every kernel with cudaDeviceSynchronize
  * (PT/Framework/WaveFrontRenderer.cpp:604-850); here independent launches of a frame may share the device:
  *   bit 0 (default ON)  the shadow rays of bounce wave d run on a side stream under the extend launch of wave d + 1;
- *   bit 1 (default OFF — measured slower on B200) the ReSTIR passes run on the side stream beside the bounce waves.
+ *   bit 1 (default OFF — measured slower on B200) the ReSTIR passes run on the side stream beside ALL bounce waves;
+ *   bit 2 (default ON)  the ReSTIR passes are launched after the first bounce wave; the later, latency-bound waves (1e5 .. 1e4 rays) run
+ *                       on the side stream beside them (takes precedence over bit 0 where it applies: ReSTIR on, depth >= 3, no media).
  * Results are identical in every mode; with mode 0 every stage time of lb_frame_stats is an exclusive device time (what bench.py uses for
  * its per-kernel roofline table). */
 LB_API int lb_set_overlap(LbRenderer r, int mode);

@@ -557,8 +557,8 @@ class Renderer:
         self.b.check(self.b.resolve_accum(self._h, total_frames))
 
     def set_overlap(self, mode: int):
-        """Overlap mask: bit 0 = bounce-wave shadow rays under the next extend launch (default), bit 1 = ReSTIR chain beside the bounce
-        waves; 0 = every launch serialised (exclusive stage times)."""
+        """Overlap mask: bit 0 = bounce-wave shadow rays under the next extend launch, bit 1 = ReSTIR chain beside all bounce waves,
+        bit 2 = late bounce waves beside the ReSTIR chain (default 5); 0 = every launch serialised (exclusive stage times)."""
         self.b.check(self.b.set_overlap(self._h, int(mode)))
 
     def set_stream(self, cuda_stream: int):

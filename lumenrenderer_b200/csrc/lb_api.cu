@@ -98,7 +98,8 @@ struct Renderer {
     // primary shade and join before the merge, so that the latency-bound tail waves can execute under the ReSTIR kernels. Off by default:
     // on B200 the two chains of persistent grids interfere (8.45 -> 8.87..9.45 ms/frame, profiles/r01_p_experiments.md).
     // `overlap` is a mask: bit 0 (default on) = the shadow rays of bounce wave d run on the side stream under the extend of wave d + 1 — two
-    // small latency-bound launches that share nothing but read-only data; bit 1 (default off) = the ReSTIR chain on the side stream.
+    // small latency-bound launches that share nothing but read-only data; bit 1 (default off) = the ReSTIR chain on the side stream beside ALL
+    // bounce waves; bit 2 (default on) = the ReSTIR chain is launched after the first bounce wave and the later waves run beside it.
     int overlap = overlap_default(); cudaStream_t restir_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_shadow = nullptr;
     std::string stats_names;
 
@@ -108,7 +109,7 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
-    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 3) : 1; }      // ReSTIR-chain overlap (bit 1) off: measured slower
+    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 7) : 5; }      // whole-chain overlap (bit 1) off: measured slower
     static TraceTuning trace_tuning(bool any) {
         TraceTuning t;
         if (const char* e = getenv(any ? "LB_TRACE_ANY_REFILL_MIN" : "LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
@@ -393,15 +394,37 @@ struct Renderer {
         a.volumes = d_volumes.p; a.num_volumes = (uint32_t)vinstances.size(); a.volume_mode = (int)st.volume_mode;
         prev_view_proj(a.prev_view_proj);
         bool forked = false, shadow_in_flight = false;
+        // overlap bit 2: the ReSTIR chain is launched after the FIRST bounce wave (the only bounce wave that fills the machine); the later,
+        // latency-bound waves (1e5 .. 1e4 rays) then run on the side stream beside it
+        const bool tail_mode = (overlap & 4) && !(overlap & 2) && st.restir && st.depth >= 3u && sc.num_lights != 0u && a.num_volumes == 0u;
+        bool tail_forked = false;
+        const uint32_t seed0 = seed;
+        auto run_restir = [&](bool on_side) {
+            RestirArgs ra{seed0, (int)st.restir_temporal, (int)st.restir_spatial};
+            RestirBuffers rb{d_bags.p, d_ris_order.p};
+            LaunchCfg cr = c;
+            if (on_side) {
+                need_side_stream();
+                LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
+                cr.stream = restir_stream; last_lap[1] = last_lap[0];
+                ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
+            } else ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 0); };
+            ra.lap_user = this;
+            launch_restir(cr, fv, sc, bva, rb, ra, ticket);
+            if (on_side) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
+            if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
+        };
         for (uint32_t depth = 0; depth < st.depth; ++depth) {
             const int queue = (int)(depth & 1u);
-            launch_extend(c, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
-            lap("extend");
+            LaunchCfg cb = c; if (tail_forked) cb.stream = restir_stream;         // stream of the bounce chain
+            const int chain = tail_forked ? 1 : 0;
+            launch_extend(cb, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
+            lap("extend", chain);
             // the previous wave's shadow rays (side stream) read the shadow queue this wave's shade kernel is about to refill
             if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
             // the next wave's queue and this wave's shadow queues start empty
-            LB_CUDA(cudaMemsetAsync(d_counters.p + (queue ? CNT_RAYS_A : CNT_RAYS_B), 0, sizeof(uint32_t), stream));
-            LB_CUDA(cudaMemsetAsync(d_counters.p + CNT_SHADOW, 0, sizeof(uint32_t), stream));
+            LB_CUDA(cudaMemsetAsync(d_counters.p + (queue ? CNT_RAYS_A : CNT_RAYS_B), 0, sizeof(uint32_t), cb.stream));
+            LB_CUDA(cudaMemsetAsync(d_counters.p + CNT_SHADOW, 0, sizeof(uint32_t), cb.stream));
             a.depth = depth; a.seed = seed;
             a.do_nee = (depth > 0 || !st.restir) ? 1 : 0;
             a.nee_channel = depth == 0 ? LB_CHANNEL_DIRECT : LB_CHANNEL_INDIRECT;
@@ -412,39 +435,36 @@ struct Renderer {
                 if (st.volume_mode == LB_VOLUME_DELTA) { launch_volume_delta(c, fv, sc, queue, depth == 0, a); ++launches; }
                 lap("volume");
             }
-            launch_shade(c, fv, sc, queue, a); ++launches;
-            lap("shade");
-            if (depth == 0 && st.restir) {
-                RestirArgs ra{seed, (int)st.restir_temporal, (int)st.restir_spatial};
-                RestirBuffers rb{d_bags.p, d_ris_order.p};
+            launch_shade(cb, fv, sc, queue, a); ++launches;
+            lap("shade", chain);
+            if (depth == 0 && st.restir && !tail_mode) {
                 forked = (overlap & 2) && st.depth > 1 && sc.num_lights != 0u && a.num_volumes == 0u;      // media: volume shadow rays also write DIRECT at depth 0
-                LaunchCfg cr = c;
-                if (forked) {
-                    need_side_stream();
-                    LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
-                    cr.stream = restir_stream; last_lap[1] = last_lap[0];
-                    ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
-                } else ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 0); };
-                ra.lap_user = this;
-                launch_restir(cr, fv, sc, bva, rb, ra, ticket);
-                if (forked) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
-                if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
+                run_restir(forked);
             }
+            if (depth == 1u && tail_mode) {
+                // fork: the rest of the bounce chain continues on the side stream, the ReSTIR chain takes the main stream
+                need_side_stream();
+                LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
+                last_lap[1] = last_lap[0]; tail_forked = true; cb.stream = restir_stream;
+                run_restir(false);
+            }
+            const int chain_s = tail_forked ? 1 : 0;
             if (a.do_nee || (a.num_volumes && st.volume_mode == LB_VOLUME_DELTA)) {
                 // bounce waves: this launch and the next wave's extend are both small and latency-bound (each lasts as long as its slowest
                 // ray) and touch disjoint buffers — the shadow rays go to the side stream and are joined before the next shade
-                const bool side = (overlap & 1) && !forked && depth >= 1u && depth + 1u < st.depth && a.num_volumes == 0u;
+                const bool side = (overlap & 1) && !forked && !tail_forked && depth >= 1u && depth + 1u < st.depth && a.num_volumes == 0u;
                 if (side) {
                     need_side_stream();
                     LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
                     LaunchCfg cs = c; cs.stream = restir_stream; last_lap[1] = last_lap[0];
                     launch_shadow(cs, fv, bva, ticket++, 0.01f); ++launches; lap("shadow", 1);
                     LB_CUDA(cudaEventRecord(ev_shadow, restir_stream)); shadow_in_flight = true;
-                } else { launch_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("shadow"); }
+                } else { launch_shadow(cb, fv, bva, ticket++, 0.01f); ++launches; lap("shadow", chain_s); }
             }
             if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
+        if (tail_forked) { LB_CUDA(cudaEventRecord(ev_join, restir_stream)); forked = true; }
         if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
         if (forked) { LB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); lap("restir_join"); }    // the time the bounce chain waited for the ReSTIR chain
         if (copy_pending) LB_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));      // an asynchronous read-back still owns the combined buffer
@@ -754,7 +774,7 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
     return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
 }
 LB_API int lb_set_overlap(LbRenderer r, int enabled) {
-    return guarded(R_, [&]() { if (enabled < 0 || enabled > 3) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
+    return guarded(R_, [&]() { if (enabled < 0 || enabled > 7) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
 }
 LB_API int lb_set_stream(LbRenderer r, void* s) {
     return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->stream = s ? (cudaStream_t)s : R_->own_stream; return (int)LB_OK; });
