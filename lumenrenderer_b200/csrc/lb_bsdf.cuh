@@ -36,11 +36,17 @@ struct Shading {
     }
 };
 
+// Two kinds of arithmetic live in this header (DESIGN.md "Arithmetic contract"). EVALUATION (value and pdf of a given pair of directions)
+// is well conditioned — a relative error of 1e-6 in, 1e-6 out — and is written with plain operators: it takes the unit's division /
+// square root / transcendentals (fast in lb_wavefront.cu and lb_restir.cu). SAMPLING A DIRECTION is not: the direction a bounce ray leaves
+// in decides what it hits, and one more ulp of error at a near-mirror surface (alpha down to 1e-4) is a different radiance at the next
+// vertex. Everything on the way from the random numbers to the sampled direction (lobe weights and thresholds, alphas, frames, the lobe
+// samplers, Fresnel split, refraction) therefore spells IEEE division / square root (xdiv, xsqrt), the accurate pow (xpow) and the portable sin / cos of lb_device.cuh (det_sincos).
 // ---------------------------------------------------------------- microfacet distributions
 LB_D void mf_alpha(float roughness, float anisotropy, float& ax, float& ay) {
     const float r2 = roughness * roughness;
-    const float aspect = sqrtf(1.0f + anisotropy * (anisotropy < 0 ? 0.9f : -0.9f));
-    ax = fmaxf(0.001f, r2 / aspect);
+    const float aspect = xsqrt(1.0f + anisotropy * (anisotropy < 0 ? 0.9f : -0.9f));
+    ax = fmaxf(0.001f, xdiv(r2, aspect));
     ay = fmaxf(0.001f, r2 * aspect);
 }
 LB_D float ggx_D(const float3& m, float ax, float ay) {
@@ -73,17 +79,17 @@ LB_D float ggx_pdf(const float3& v, const float3& m, float ax, float ay) {
 // visible-normal sampling, device branch of ggxmdf.cuh:78-107
 LB_D float3 ggx_sample(const float3& v, float r0, float r1, float ax, float ay) {
     const float sgn = v.z < 0.0f ? -1.0f : 1.0f;
-    const float3 st = normalize(f3(sgn * v.x * ax, sgn * v.y * ay, sgn * v.z));
-    const float3 t1 = v.z < 0.9999f ? normalize(cross(st, f3(0, 0, 1))) : f3(1, 0, 0);
+    const float3 st = xnormalize(f3(sgn * v.x * ax, sgn * v.y * ay, sgn * v.z));
+    const float3 t1 = v.z < 0.9999f ? xnormalize(cross(st, f3(0, 0, 1))) : f3(1, 0, 0);
     const float3 t2 = cross(t1, st);
-    const float a = 1.0f / (1.0f + st.z);
-    const float r = sqrtf(r0);
-    const float phi = r1 < a ? (r1 / a * kPi) : (kPi + (r1 - a) / (1.0f - a) * kPi);
-    float p1 = cosf(phi), p2 = sinf(phi);
+    const float a = xdiv(1.0f, 1.0f + st.z);
+    const float r = xsqrt(r0);
+    const float phi = r1 < a ? (xdiv(r1, a) * kPi) : (kPi + xdiv(r1 - a, 1.0f - a) * kPi);
+    float p1, p2; det_sincos(phi, p2, p1);
     p1 *= r;
     p2 *= r * (r1 < a ? 1.0f : st.z);
-    const float3 h = p1 * t1 + p2 * t2 + sqrtf(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2)) * st;
-    return normalize(f3(h.x * ax, h.y * ay, fmaxf(0.0f, h.z)));
+    const float3 h = p1 * t1 + p2 * t2 + xsqrt(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2)) * st;
+    return xnormalize(f3(h.x * ax, h.y * ay, fmaxf(0.0f, h.z)));
 }
 LB_D float gtr1_clamp(float a) { return clampf(a, 0.001f, 0.999f); }
 LB_D float gtr1_D(const float3& m, float ax) {
@@ -110,11 +116,11 @@ LB_D float gtr1_G(const float3& wi, const float3& wo, float ax) { return 1.0f / 
 LB_D float gtr1_pdf(const float3& m, float ax) { return gtr1_D(m, ax) * fabsf(m.z); }
 LB_D float3 gtr1_sample(float r0, float r1, float ax) {
     const float a2 = sq(gtr1_clamp(ax));
-    const float c2 = (1.0f - powf(a2, 1.0f - r0)) / (1.0f - a2);
-    const float s = sqrtf(fmaxf(0.0f, 1.0f - c2));
+    const float c2 = xdiv(1.0f - xpow(a2, 1.0f - r0), 1.0f - a2);
+    const float s = xsqrt(fmaxf(0.0f, 1.0f - c2));
     const float phi = kTwoPi * r1;
-    const float cp = cosf(phi), sp = sinf(phi);
-    return f3(cp * s, sp * s, sqrtf(c2));
+    float cp, sp; det_sincos(phi, sp, cp);
+    return f3(cp * s, sp * s, xsqrt(c2));
 }
 
 // ---------------------------------------------------------------- lobes
@@ -189,11 +195,11 @@ LB_D float sheen_lobe(const Shading& s, const float3& wi, const float3& m, float
 LB_D float fresnel_dielectric(float cos_i, float eta, float& cos_t) {
     const float s2 = (1 - sq(cos_i)) * sq(eta);
     if (s2 > 1) { cos_t = 0; return 1; }
-    cos_t = fminf(sqrtf(fmaxf(1 - s2, 0.0f)), 1.0f);
+    cos_t = fminf(xsqrt(fmaxf(1 - s2, 0.0f)), 1.0f);            // cos_t is a component of the refracted direction, F splits reflect / refract
     const float ci = fabsf(cos_i);
     if (ci == 0 && cos_t == 0) return 1;
     const float k0 = eta * cos_t, k1 = eta * ci;
-    return 0.5f * (sq((ci - k0) / (ci + k0)) + sq((cos_t - k1) / (cos_t + k1)));
+    return 0.5f * (sq(xdiv(ci - k0, ci + k0)) + sq(xdiv(cos_t - k1, cos_t + k1)));
 }
 LB_D float3 refracted(const float3& wo, const float3& m, float cos_wom, float cos_t, float rcp_eta) {
     const float3 wi = cos_wom > 0 ? (rcp_eta * cos_wom - cos_t) * m - rcp_eta * wo
@@ -234,14 +240,14 @@ LB_D float jacobian_refraction(const float3& wo, const float3& wi, const float3&
 LB_D float3 to_local(const float3& v, const float3& n, const float3& t, const float3& b) { return f3(dot(v, t), dot(v, b), dot(v, n)); }
 LB_D float3 to_world(const float3& v, const float3& n, const float3& t, const float3& b) { return v.x * t + v.y * b + v.z * n; }
 LB_D float3 cosine_hemisphere(float r0, float r1, const float3& n, const float3& t, const float3& b) {
-    const float term1 = kTwoPi * r0, term2 = sqrtf(1 - r1);
-    const float s = sinf(term1), c = cosf(term1);
-    return (c * term2 * t) + (s * term2) * b + sqrtf(r1) * n;
+    const float term1 = kTwoPi * r0, term2 = xsqrt(1 - r1);
+    float s, c; det_sincos(term1, s, c);
+    return (c * term2 * t) + (s * term2) * b + xsqrt(r1) * n;
 }
 LB_D void lobe_weights(const Shading& s, float w[4]) {
     w[0] = mixf(s.luminance, 0.f, s.metallic); w[1] = mixf(s.sheen, 0.f, s.metallic);
     w[2] = mixf(s.specular, 1.f, s.metallic);  w[3] = s.clearcoat * 0.25f;
-    const float inv = 1.0f / (w[0] + w[1] + w[2] + w[3]);
+    const float inv = xdiv(1.0f, w[0] + w[1] + w[2] + w[3]);     // the weights are the lobe-selection thresholds of bsdf_sample
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[i] *= inv;
 }
@@ -407,17 +413,17 @@ LB_D float3 bsdf_sample(const Material& mat, float3 iN, const float3& N, const f
     const Shading s(mat);
     const float flip = (dot(wow, N) < 0) ? -1.f : 1.f;
     iN *= flip;
-    const float3 B = normalize(cross(iN, iT)), T = normalize(cross(iN, B));
+    const float3 B = xnormalize(cross(iN, iT)), T = xnormalize(cross(iN, B));
     if (r0 < s.transmission) {
         specular = true;
-        const float r3 = r0 / s.transmission;
+        const float r3 = xdiv(r0, s.transmission);
         const float3 wol = to_local(wow, iN, T, B);
-        const float eta = flip < 0 ? (1 / s.ior) : s.ior;
+        const float eta = flip < 0 ? xdiv(1.f, s.ior) : s.ior;
         if (eta == 1) return f3(0.f);
         const float3 beer = f3(expf(-s.transmittance.x * distance * 2.0f), expf(-s.transmittance.y * distance * 2.0f), expf(-s.transmittance.z * distance * 2.0f));
         float ax, ay; mf_alpha(s.roughness, s.anisotropic, ax, ay);
         const float3 m = ggx_sample(wol, r1, r3, ax, ay);
-        const float rcp_eta = 1 / eta, cos_wom = clampf(dot(wol, m), -1.0f, 1.0f);
+        const float rcp_eta = xdiv(1.f, eta), cos_wom = clampf(dot(wol, m), -1.0f, 1.0f);
         float ct, jac;
         const float F = fresnel_dielectric(cos_wom, eta, ct);
         float3 wil, ret = f3(0.f);
@@ -436,13 +442,13 @@ LB_D float3 bsdf_sample(const Material& mat, float3 iN, const float3& N, const f
         if (pdf > 1.0e-6f) wiw = to_world(wil, iN, T, B);
         return ret * beer;
     }
-    const float r3 = (r0 - s.transmission) / (1 - s.transmission);
+    const float r3 = xdiv(r0 - s.transmission, 1 - s.transmission);
     float w[4]; lobe_weights(s, w);
     const float cdf_x = w[0], cdf_y = w[0] + w[1], cdf_z = w[0] + w[1] + w[2];
     float probability, component_pdf = 0;
     float3 contrib = f3(0.f), value = f3(0.f);
     if (r3 < cdf_y) {
-        const float rr = r3 / cdf_y;
+        const float rr = xdiv(r3, cdf_y);
         wiw = cosine_hemisphere(rr, r1, iN, T, B);
         const float3 m = normalize(wiw + wow);
         if (r3 < cdf_x) { component_pdf = diffuse_lobe(s, iN, wow, wiw, m, value); probability = w[0] * component_pdf; w[0] = 0; }
@@ -451,12 +457,12 @@ LB_D float3 bsdf_sample(const Material& mat, float3 iN, const float3& N, const f
         const float3 wol = to_local(wow, iN, T, B);
         float3 wil = f3(0.f);
         if (r3 < cdf_z) {
-            const float rr = (r3 - cdf_y) / (cdf_z - cdf_y);
+            const float rr = xdiv(r3 - cdf_y, cdf_z - cdf_y);
             float ax, ay; mf_alpha(s.roughness, s.anisotropic, ax, ay);
             lobe_sample<true>(s, rr, r1, ax, ay, wol, wil, component_pdf, value);
             probability = w[2] * component_pdf; w[2] = 0;
         } else {
-            const float rr = (r3 - cdf_z) / (1 - cdf_z);
+            const float rr = xdiv(r3 - cdf_z, 1 - cdf_z);
             const float a = coat_alpha(s);
             lobe_sample<false>(s, rr, r1, a, a, wol, wil, component_pdf, value);
             probability = w[3] * component_pdf; w[3] = 0;

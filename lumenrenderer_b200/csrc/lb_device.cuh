@@ -60,6 +60,26 @@ LB_HD float comp(const float3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y :
 LB_D float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 LB_D float xsqrt(float a) { return __fsqrt_rn(a); }
 LB_D float3 xnormalize(const float3& v) { const float inv = xdiv(1.0f, xsqrt(dot(v, v))); return v * inv; }
+// sin and cos of an angle in [0, 2 pi] by Cody-Waite reduction to [-pi/4, pi/4] and the Cephes single-precision minimax polynomials
+// (about 1 ulp), written with explicit fmaf only: the SAME sequence of IEEE operations in the CUDA library (lb_device.cuh) and in the
+// oracle (lo_math.h), so the direction a bounce ray leaves in is bit-identical on both sides. A libm call is not: glibc's and libdevice's
+// sinf differ in the last ulp, and a bounce direction is amplified at the next near-mirror vertex (canonical choice 16).
+LB_D void det_sincos(float x, float& s, float& c) {
+    const float j = floorf(fmaf(x, 0.636619772367581343f, 0.5f));                   // nearest multiple of pi/2: 0 .. 4
+    float r = fmaf(-j, 1.5703125f, x);
+    r = fmaf(-j, 4.837512969970703125e-4f, r);
+    r = fmaf(-j, 7.54978995489188216e-8f, r);
+    const float r2 = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2, fmaf(-0.5f, r2, 1.0f));
+    const int q = (int)j & 3;
+    s = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
+    c = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
+}
+// The accurate libdevice pow, whatever the unit's --use_fast_math says (which silently turns powf into exp2(y log2 x) approximations):
+// the clear-coat lobe's sampled direction.
+extern "C" __device__ float __nv_powf(float, float);
+LB_D float xpow(float a, float b) { return __nv_powf(a, b); }
 
 // fp16 round trip: barycentrics (IntersectionData.h:90) and motion vectors (MotionVectors.cu:44) are stored as half.
 LB_D float half_round(float f) { return __half2float(__float2half_rn(f)); }

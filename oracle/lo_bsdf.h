@@ -86,7 +86,7 @@ static inline V3 ggx_sample(const V3& v, float r0, float r1, float ax, float ay)
     const float a = 1.0f / (1.0f + st.z);
     const float r = sqrtf(r0);
     const float phi = r1 < a ? (r1 / a * kPi) : (kPi + (r1 - a) / (1.0f - a) * kPi);
-    float p1 = cosf(phi), p2 = sinf(phi);
+    float p1, p2; det_sincos(phi, p2, p1);
     p1 *= r;
     p2 *= r * (r1 < a ? 1.0f : st.z);
     const V3 h = p1 * t1 + p2 * t2 + sqrtf(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2)) * st;
@@ -120,7 +120,7 @@ static inline V3 gtr1_sample(float r0, float r1, float ax) {                    
     const float c2 = (1.0f - powf(a2, 1.0f - r0)) / (1.0f - a2);
     const float s = sqrtf(fmaxf(0.0f, 1.0f - c2));
     const float phi = kTwoPi * r1;
-    const float cp = cosf(phi), sp = sinf(phi);
+    float cp, sp; det_sincos(phi, sp, cp);
     return v3(cp * s, sp * s, sqrtf(c2));
 }
 
@@ -243,7 +243,7 @@ static inline V3 to_local(const V3& v, const V3& n, const V3& t, const V3& b) { 
 static inline V3 to_world(const V3& v, const V3& n, const V3& t, const V3& b) { return v.x * t + v.y * b + v.z * n; }
 static inline V3 cos_weighted(float r0, float r1, const V3& n, const V3& t, const V3& b) {             // bsdf_math.cuh:133-139
     const float term1 = kTwoPi * r0, term2 = sqrtf(1 - r1);
-    const float s = sinf(term1), c = cosf(term1);
+    float s, c; det_sincos(term1, s, c);
     return (c * term2 * t) + (s * term2) * b + sqrtf(r1) * n;
 }
 static inline void lobe_weights(const MatView& s, float w[4]) {                                        // disney.cuh:228-229, 368-369

@@ -71,4 +71,25 @@ static inline V3 xform_vector(const float* m, const V3& v) {
              fmaf(m[8], v.x, fmaf(m[9], v.y, m[10] * v.z)) };
 }
 
+// sin and cos of an angle in [0, 2 pi]: Cody-Waite reduction to [-pi/4, pi/4] + the Cephes single-precision minimax polynomials (about
+// 1 ulp), explicit fmaf only — operation for operation the sequence of lumenrenderer_b200/csrc/lb_device.cuh det_sincos, so that sampled
+// bounce directions are bit-identical on CPU and GPU (glibc's and libdevice's sinf differ in the last ulp; canonical choice 16). The
+// reference calls CUDA's sinf / cosf here (ggxmdf.cuh:90, disney.cuh cosine sampling); agreement with it is checked by the BSDF golden vectors.
+// lo_kat_use_libm_sincos(1) (tests only) switches to glibc's sinf / cosf: with it the oracle's SampleBSDF is bit-identical to the host build
+// of the reference headers, which pins everything around the two calls.
+static bool g_libm_sincos = false;
+static inline void det_sincos(float x, float& s, float& c) {
+    if (g_libm_sincos) { s = sinf(x); c = cosf(x); return; }
+    const float j = floorf(fmaf(x, 0.636619772367581343f, 0.5f));                   // nearest multiple of pi/2: 0 .. 4
+    float r = fmaf(-j, 1.5703125f, x);
+    r = fmaf(-j, 4.837512969970703125e-4f, r);
+    r = fmaf(-j, 7.54978995489188216e-8f, r);
+    const float r2 = r * r;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2, fmaf(-0.5f, r2, 1.0f));
+    const int q = (int)j & 3;
+    s = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
+    c = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
+}
+
 } // namespace lo

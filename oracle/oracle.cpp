@@ -1004,6 +1004,7 @@ LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total)
     for (size_t i = 0; i < R_->accum.size(); ++i) R_->combined[i] = {R_->accum[i].x * inv, R_->accum[i].y * inv, R_->accum[i].z * inv, R_->accum[i].w * inv}; R_->write_ldr(); return LB_OK; }
 // ---- known-answer taps of the ReSTIR data structures (oracle only; checked against the reference's own ReSTIRData.h compiled for the host,
 // oracle/ref_shim/ref_restir.cpp -> tests/golden/restir_reference.npz). Same signatures as ref_kat_reservoir / ref_kat_cdf.
+LB_API void lo_kat_use_libm_sincos(int on) { lo::g_libm_sincos = on != 0; }
 LB_API void lo_kat_reservoir(const float* weights, const unsigned* seeds, const float* pdfs, unsigned n, float* out5, unsigned char* selected) {
     Reservoir r; r.sample.radiance.x = -1.f;
     for (unsigned k = 0; k < n; ++k) { LightSample s; s.pdf = pdfs[k]; s.radiance.x = (float)k; selected[k] = r.update(s, weights[k], seeds[k]) ? 1 : 0; }

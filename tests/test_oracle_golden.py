@@ -58,11 +58,31 @@ def test_evaluate_bsdf_bit_exact_vs_reference(oracle, gold):
 def test_sample_bsdf_bit_exact_vs_reference(oracle, gold):
     """SampleBSDF (disney.cuh:173-304): bsdf value, sampled direction, pdf and specular flag are bit-identical to the
     reference headers (their DEVICE branches, ggxmdf.cuh:90-101,208-212 — what the reference renders with — compiled for
-    the host by oracle/ref_shim)."""
+    the host by oracle/ref_shim). The host build of the reference calls glibc's sinf / cosf; the oracle's sampled directions use the
+    portable det_sincos it shares with the CUDA library (canonical choice 16) — switched to glibc's for this comparison, which pins
+    everything around the two calls; the next test bounds what the switch changes."""
+    oracle.lib.lo_kat_use_libm_sincos(1)
+    try:
+        for i in range(gold["mats"].shape[0]):
+            got = _oracle_sample(oracle, gold["mats"][i], gold["sample_in"][i])
+            ref = gold["sample_out"][i]
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"material {i}: {np.abs(got - ref).max()}"
+    finally:
+        oracle.lib.lo_kat_use_libm_sincos(0)
+
+
+def test_portable_sincos_stays_within_an_ulp_of_the_reference_directions(oracle, gold):
+    """det_sincos (lo_math.h == lb_device.cuh) against the reference headers' sampled directions: specular flags identical, 99 % of the
+    direction components within 2.4e-7 (2 ulp at 1), all within 1e-5 (the visible-normal sampler itself amplifies an ulp of sin / cos near
+    grazing half-vectors: sqrt(1 - p1^2 - p2^2)) — the bound the GPU golden test uses for directions."""
+    diffs = []
     for i in range(gold["mats"].shape[0]):
         got = _oracle_sample(oracle, gold["mats"][i], gold["sample_in"][i])
         ref = gold["sample_out"][i]
-        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"material {i}: {np.abs(got - ref).max()}"
+        assert np.array_equal(got[:, 7], ref[:, 7])
+        diffs.append(np.abs(got[:, 3:6] - ref[:, 3:6]).reshape(-1))
+    d = np.concatenate(diffs)
+    assert d.max() <= 1e-5 and np.quantile(d, 0.99) <= 2.4e-7, (d.max(), np.quantile(d, 0.99))
 
 
 @pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
