@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kBlock) k_volume_delta(FrameView fv, SceneView
             const float z = 1.f - 2.f * rand_f(seed);
             const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
             const float phi = kTwoPi * rand_f(seed);
-            const float3 dirn = f3(r * cosf(phi), r * sinf(phi), z);
+            float sp, cp; det_sincos(phi, sp, cp);                     // portable sin / cos: the scattered direction is bit-identical in the oracle
+            const float3 dirn = f3(r * cp, r * sp, z);
             const uint32_t slot = queue_append_slot(out_count);
             out.o[slot] = f4(p, 0.f);
             out.d[slot] = f4(dirn, __uint_as_float(pixel));

@@ -701,7 +701,8 @@ struct Renderer {
                 const float z = 1.f - 2.f * rand_f(seed);
                 const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
                 const float phi = kTwoPi * rand_f(seed);
-                next.push_back({ray.px, ray.py, p, v3(r * cosf(phi), r * sinf(phi), z), T * 0.8f});
+                float sp, cp; det_sincos(phi, sp, cp);
+                next.push_back({ray.px, ray.py, p, v3(r * cp, r * sp, z), T * 0.8f});
             }
         }
     }

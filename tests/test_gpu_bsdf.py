@@ -35,20 +35,30 @@ def test_evaluate_bsdf_vs_reference_golden(gold):
         assert exact / total > 0.9          # most outputs do not touch a transcendental and are bit-identical
 
 
-def test_sample_bsdf_vs_reference_golden(gold):
+def test_sample_bsdf_vs_reference_golden(gold, oracle):
     with lr.Renderer(width=8, height=8) as g:
+        identical = 0
         for i in range(gold["mats"].shape[0]):
             v = gold["sample_in"][i]
             got = g.sample_bsdf(gold["mats"][i], v[:, 0:3], v[:, 3:6], v[:, 6:9], v[:, 9:12])
             ref = gold["sample_out"][i]
             assert np.array_equal(got[:, 7], ref[:, 7])
-            # the sampled direction itself is well conditioned: 1e-5 absolute for every material
+            # (1) against the oracle: the sampled direction comes from the same exact-class arithmetic and the same portable sin / cos on both
+            # sides — bit-identical except through the clear-coat lobe's powf (libm), and then within an ulp or two; value and pdf follow
+            orc = np.empty((v.shape[0], 8), np.float32)
+            m = np.ascontiguousarray(gold["mats"][i], np.float32); vv = np.ascontiguousarray(v, np.float32)
+            assert oracle.debug_sample_bsdf(None, m.ctypes.data, vv.ctypes.data, vv.shape[0], orc.ctypes.data) == 0
+            assert np.abs(got[:, 3:6] - orc[:, 3:6]).max() <= 2.4e-7, f"material {i}: direction vs oracle"
+            identical += int(np.array_equal(got[:, 3:6].view(np.uint32), orc[:, 3:6].view(np.uint32)))
+            assert (np.abs(got[:, :7] - orc[:, :7]) / np.maximum(np.abs(orc[:, :7]), 1.0)).max() <= 1e-6, f"material {i}: value / pdf vs oracle"
+            # (2) against the reference headers' golden vectors (glibc sinf / cosf behind the direction): 1e-5 absolute on the direction
             assert np.abs(got[:, 3:6] - ref[:, 3:6]).max() <= 1e-5, f"material {i}: direction"
             if gold["mats"][i][15] < 0.1:
-                continue        # near-mirror lobes (alpha <= 0.01): D ~ 1/alpha^4 turns one ulp of sinf/cosf into percent-level changes of value/pdf
+                continue        # near-mirror lobes (alpha <= 0.01): D ~ 1/alpha^4 turns one ulp of the azimuth's sin / cos into percent-level changes of value/pdf
             ok = _close(got[:, :7], ref[:, :7]).all(axis=1)
-            # sinf/cosf of the sampled azimuth differ by an ulp from glibc; a sharp GGX lobe amplifies that in the bsdf value and pdf of a
-            # few samples: every sample within 5e-4 relative, at least 90 % within the 1e-5 bar (rough glass, alpha = 0.0225, is the worst case)
+            # a sharp GGX lobe amplifies the last-ulp difference of the azimuth's sin / cos in the bsdf value and pdf of a few samples: every
+            # sample within 2e-3 relative, at least 90 % within the 1e-5 bar (rough glass, alpha = 0.0225, is the worst case)
             scaled = np.abs(got[:, :7] - ref[:, :7]) / np.maximum(np.abs(ref[:, :7]), 1.0)
-            assert scaled.max() <= 5e-4, f"material {i}: max scaled error {scaled.max()}"
+            assert scaled.max() <= 2e-3, f"material {i}: max scaled error {scaled.max()}"
             assert ok.mean() >= 0.90, f"material {i}: {(~ok).sum()} of {ok.size} samples off"
+        assert identical >= 18, f"only {identical} of {gold['mats'].shape[0]} materials sample bit-identical directions on GPU and oracle"
