@@ -76,10 +76,10 @@ LB_D void det_sincos(float x, float& s, float& c) {
     s = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
     c = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
 }
-// The accurate libdevice pow, whatever the unit's --use_fast_math says (which silently turns powf into exp2(y log2 x) approximations):
-// the clear-coat lobe's sampled direction.
-extern "C" __device__ float __nv_powf(float, float);
-LB_D float xpow(float a, float b) { return __nv_powf(a, b); }
+// pow behind the clear-coat lobe's sampled direction: evaluated in double and rounded to float. Double-precision pow is accurate to well
+// under one double ulp in both libdevice and glibc, so the float results agree on CPU and GPU except when the exact value lies within
+// ~1e-16 (relative) of a float rounding boundary — and --use_fast_math does not touch double precision.
+LB_D float xpow(float a, float b) { return (float)pow((double)a, (double)b); }
 
 // fp16 round trip: barycentrics (IntersectionData.h:90) and motion vectors (MotionVectors.cu:44) are stored as half.
 LB_D float half_round(float f) { return __half2float(__float2half_rn(f)); }

@@ -117,7 +117,7 @@ static inline float gtr1_g(const V3& wi, const V3& wo, float ax) { return 1.0f /
 static inline float gtr1_pdf(const V3& m, float ax) { return gtr1_d(m, ax) * fabsf(m.z); }
 static inline V3 gtr1_sample(float r0, float r1, float ax) {                                          // ggxmdf.cuh:198-213
     const float a2 = sq(gtr1_alpha(ax));
-    const float c2 = (1.0f - powf(a2, 1.0f - r0)) / (1.0f - a2);
+    const float c2 = (1.0f - det_pow(a2, 1.0f - r0)) / (1.0f - a2);
     const float s = sqrtf(fmaxf(0.0f, 1.0f - c2));
     const float phi = kTwoPi * r1;
     float cp, sp; det_sincos(phi, sp, cp);

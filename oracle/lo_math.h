@@ -92,4 +92,8 @@ static inline void det_sincos(float x, float& s, float& c) {
     c = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
 }
 
+// pow behind the clear-coat lobe's sampled direction, like lb_device.cuh xpow: double precision, rounded to float (glibc's and libdevice's
+// double pow agree after that rounding); glibc's powf under the lo_kat_use_libm_sincos switch (what the reference headers' host build calls)
+static inline float det_pow(float a, float b) { return g_libm_sincos ? powf(a, b) : (float)pow((double)a, (double)b); }
+
 } // namespace lo
