@@ -202,6 +202,20 @@ __global__ void k_ploc_compact(const uint32_t* __restrict__ cl, const float4* __
     if (i == m - 1u) *m_out = offset[i] + keep[i];
 }
 
+// Copies 1 and 2 of the leaf-ordered triangles with their coordinates rotated: component j of copy r is coordinate (j + r) mod 3 (the ids in
+// the w lanes stay). The intersection test shears the triangle along the ray's dominant axis kz and needs its coordinates in the order
+// (kz + 1, kz + 2, kz); a ray reads the copy r = (kz + 1) mod 3, where that order is (x, y, z) — no per-triangle component selection
+// (it was 10 % of the traversal's instructions, profiles/r01_u_kernels.md). 96 B more per triangle; HBM has room.
+__global__ void k_rotate_tris(DevTri* __restrict__ tris, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevTri t = tris[i];
+    DevTri a, b;
+    a.v0 = make_float4(t.v0.y, t.v0.z, t.v0.x, t.v0.w); a.v1 = make_float4(t.v1.y, t.v1.z, t.v1.x, t.v1.w); a.v2 = make_float4(t.v2.y, t.v2.z, t.v2.x, t.v2.w);
+    b.v0 = make_float4(t.v0.z, t.v0.x, t.v0.y, t.v0.w); b.v1 = make_float4(t.v1.z, t.v1.x, t.v1.y, t.v1.w); b.v2 = make_float4(t.v2.z, t.v2.x, t.v2.y, t.v2.w);
+    tris[(size_t)n + i] = a; tris[2 * (size_t)n + i] = b;
+}
+
 struct WorkItem { uint32_t bnode, wnode; };
 
 __device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
@@ -329,7 +343,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     tlo.reserve(n, s); thi.reserve(n, s); nlo.reserve(n_binary, s); nhi.reserve(n_binary, s); count.reserve(n_binary, s); cbounds.reserve(6, s);
     keys.reserve(n, s); keys_sorted.reserve(n, s); vals.reserve(n, s); sorted.reserve(n, s); counters.reserve(4, s);
     children.reserve(n, s); items_a.reserve(n, s); items_b.reserve(n, s);
-    out.nodes.reserve(n); out.tris.reserve(n);
+    out.nodes.reserve(n); out.tris.reserve(3 * (size_t)n);          // three axis-rotated copies of the leaf-ordered triangles (k_rotate_tris)
 
     const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
@@ -394,6 +408,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         n_items = h_c[2]; std::swap(cur, nxt); ++out.levels;
     }
     out.num_nodes = h_c[0]; out.num_tris = h_c[1];
+    if (out.num_tris == n) { k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(out.tris.p, n); LB_LAUNCH_CHECK(); }
     LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
     LB_CUDA(cudaEventElapsedTime(&out.build_ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -67,7 +67,7 @@ struct DeviceBvh {
     uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0;
     float build_ms = 0.f;
     BvhView view() const { return BvhView{nodes.p, tris.p, num_tris}; }
-    size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + (size_t)num_tris * sizeof(DevTri); }
+    size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + 3 * (size_t)num_tris * sizeof(DevTri); }      // three rotated triangle copies
 };
 
 // GPU build: 63-bit Morton order -> binary hierarchy by PLOC (SAH-quality, default) or LBVH (Karras 2012, fastest build)

@@ -300,7 +300,7 @@ struct VisibilityJob {
         }
     }
 };
-__global__ void __launch_bounds__(kBlock) k_visibility_shade(FrameView fv, BvhView bvh, uint32_t* ticket, float inv_shaded_count_denominator, unsigned long long* stat, TraceTuning tune) {
+__global__ void __launch_bounds__(kBlock, 4) k_visibility_shade(FrameView fv, BvhView bvh, uint32_t* ticket, float inv_shaded_count_denominator, unsigned long long* stat, TraceTuning tune) {
     VisibilityJob job{fv, inv_shaded_count_denominator, 0u, make_float4(0.f, 0.f, 0.f, 0.f)};
     trace_queue<true>(bvh, fv.npix, ticket, job, tune);
     const uint32_t traced = __reduce_add_sync(0xFFFFFFFFu, job.traced);

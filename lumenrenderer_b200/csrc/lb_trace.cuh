@@ -29,27 +29,33 @@ LB_D float tdiv(float a, float b) { return a / b; }
 LB_D float tdiv(float a, float b) { return xdiv(a, b); }
 #endif
 
-struct RayShear { int kx, ky, kz; float sx, sy, sz; };
+// Shear of the watertight test (Woop, Benthin, Wald 2013) along the ray's dominant axis kz. `rot` = (kz + 1) mod 3 selects the triangle
+// copy whose stored coordinate order is (kx, ky, kz) = (kz + 1, kz + 2, kz) (lb_bvh.cu k_rotate_tris), so nothing is selected per triangle.
+// The reference formulation swaps kx and ky when the direction's kz component is negative (to keep the winding); the swap exchanges
+// (Ax, Ay), (Bx, By), (Cx, Cy), which negates U, V, W, det and T EXACTLY (a - b == -(b - a) in IEEE arithmetic, the double fallback
+// included) and leaves the sign tests, t = T / det, u = V / det and v = W / det bit-identical — so it is simply not done here, and the
+// oracle, which does it, still agrees bit for bit (tests/test_gpu_trace.py).
+struct RayShear { int rot; float sx, sy, sz; };
 
+LB_D float3 rotate_axes(const float3& v, int rot) {              // (v[rot], v[rot + 1], v[rot + 2]) with indices mod 3
+    return rot == 0 ? v : (rot == 1 ? f3(v.y, v.z, v.x) : f3(v.z, v.x, v.y));
+}
 LB_D RayShear make_shear(const float3& d) {
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const int kz = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
     RayShear r;
-    r.kz = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
-    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
-    if (comp(d, r.kz) < 0.0f) { const int t = r.kx; r.kx = r.ky; r.ky = t; }
-    const float dz = comp(d, r.kz);
-    r.sx = tdiv(comp(d, r.kx), dz); r.sy = tdiv(comp(d, r.ky), dz); r.sz = tdiv(1.0f, dz);
+    r.rot = kz == 2 ? 0 : kz + 1;
+    const float3 dr = rotate_axes(d, r.rot);                     // (d[kx], d[ky], d[kz])
+    r.sx = tdiv(dr.x, dr.z); r.sy = tdiv(dr.y, dr.z); r.sz = tdiv(1.0f, dr.z);
     return r;
 }
 
-// true + (t, u, v) when the ray's line hits the triangle; the range test is the caller's.
+// true + (t, u, v) when the ray's line hits the triangle; the range test is the caller's. `org` and the vertices are in the rotated frame.
 LB_D bool tri_test(const float3& org, const RayShear& s, const float3& p0, const float3& p1, const float3& p2, float& t, float& u, float& v) {
     const float3 A = p0 - org, B = p1 - org, C = p2 - org;
-    const float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
-    const float Ax = fmaf(-s.sx, Akz, comp(A, s.kx)), Ay = fmaf(-s.sy, Akz, comp(A, s.ky));
-    const float Bx = fmaf(-s.sx, Bkz, comp(B, s.kx)), By = fmaf(-s.sy, Bkz, comp(B, s.ky));
-    const float Cx = fmaf(-s.sx, Ckz, comp(C, s.kx)), Cy = fmaf(-s.sy, Ckz, comp(C, s.ky));
+    const float Ax = fmaf(-s.sx, A.z, A.x), Ay = fmaf(-s.sy, A.z, A.y);
+    const float Bx = fmaf(-s.sx, B.z, B.x), By = fmaf(-s.sy, B.z, B.y);
+    const float Cx = fmaf(-s.sx, C.z, C.x), Cy = fmaf(-s.sy, C.z, C.y);
     // Edge functions with UNFUSED products (explicit _rn intrinsics are never contracted): for an edge shared by two triangles
     // the two evaluations are exact negations of each other — the watertightness property. An FMA would round only one product.
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
@@ -63,7 +69,7 @@ LB_D bool tri_test(const float3& org, const RayShear& s, const float3& p0, const
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     const float det = (U + V) + W;
     if (det == 0.0f) return false;
-    const float Az = s.sz * Akz, Bz = s.sz * Bkz, Cz = s.sz * Ckz;
+    const float Az = s.sz * A.z, Bz = s.sz * B.z, Cz = s.sz * C.z;
     const float T = fmaf(U, Az, fmaf(V, Bz, W * Cz));
     t = tdiv(T, det); u = tdiv(V, det); v = tdiv(W, det);
     return true;
@@ -88,8 +94,9 @@ template <int J> LB_D float byte_biased(uint32_t word, uint32_t k4b) {
 // bits 31..24 | imask 7..0}, otherwise a triangle group {first triangle, 24 pending bits} (Ylitie et al. 2017).
 // The octant trick orders children front to back (slot ^ octant, highest bit first).
 struct Tracer {
-    float3 o, idir; RayShear sh;
-    float tmin, tmax, best;
+    float3 o, idir, orot; RayShear sh;      // orot: origin in the rotated frame of the triangle copy this ray reads
+    uint32_t tri_off;                       // first triangle of that copy
+    float tmin, best;                        // best = upper end of the search interval: tmax until a closer hit is found (never changes for any-hit rays)
     uint32_t octinv;
     uint2 cur;
     int sp;
@@ -98,8 +105,8 @@ struct Tracer {
                                 // scalar state above is promoted to registers)
 
     LB_D void begin(const BvhView& bvh, const float3& o_, const float3& d, float tmin_, float tmax_) {
-        o = o_; tmin = tmin_; tmax = tmax_; best = tmax_;
-        sh = make_shear(d);
+        o = o_; tmin = tmin_; best = tmax_;
+        sh = make_shear(d); orot = rotate_axes(o_, sh.rot); tri_off = (uint32_t)sh.rot * bvh.num_tris;
         idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
         // octant and near/far swizzle come from the sign of the INVERSE direction, so that a component of -0.0 (inverse -1e20)
         // is treated consistently by both
@@ -190,14 +197,14 @@ struct Tracer {
     LB_D bool tri_step(const BvhView& bvh) {
         const uint32_t k = (uint32_t)__ffs(cur.y) - 1u;
         cur.y &= cur.y - 1u;
-        const float4* tp = reinterpret_cast<const float4*>(bvh.tris + (cur.x + k));
+        const float4* tp = reinterpret_cast<const float4*>(bvh.tris + (tri_off + cur.x + k));
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
         float t, u, v;
-        if (!tri_test(o, sh, f3(v0), f3(v1), f3(v2), t, u, v)) return false;
+        if (!tri_test(orot, sh, f3(v0), f3(v1), f3(v2), t, u, v)) return false;
         if (!(t > tmin)) return false;
-        if (ANY) return t < tmax;
+        if (ANY) return t < best;
         const uint32_t ti = __float_as_uint(v0.w), tpi = __float_as_uint(v1.w);
-        const bool better = found ? (t < best || (t == best && (ti < bi || (ti == bi && tpi < bp)))) : (t < tmax);
+        const bool better = found ? (t < best || (t == best && (ti < bi || (ti == bi && tpi < bp)))) : (t < best);
         if (better) { found = true; best = t; bi = ti; bp = tpi; bu = u; bv = v; }
         return false;
     }

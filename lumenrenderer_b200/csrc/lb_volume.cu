@@ -34,7 +34,7 @@ struct VolShadowJob {
         atomicAdd(dst, L.x); atomicAdd(dst + 1, L.y); atomicAdd(dst + 2, L.z);
     }
 };
-__global__ void __launch_bounds__(kBlock) k_vol_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket, float4* channels, size_t npix, float tmin, unsigned long long* stat, TraceTuning tune) {
+__global__ void __launch_bounds__(kBlock, 4) k_vol_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket, float4* channels, size_t npix, float tmin, unsigned long long* stat, TraceTuning tune) {
     const uint32_t n = *count;
     VolShadowJob job{q, channels, npix, tmin};
     trace_queue<true>(bvh, n, ticket, job, tune);

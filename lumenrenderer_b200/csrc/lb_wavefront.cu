@@ -65,7 +65,7 @@ struct ExtendJob {
         hits[i] = rec;
     }
 };
-__global__ void __launch_bounds__(kBlock) k_extend(BvhView bvh, const float4* __restrict__ ro, const float4* __restrict__ rd, const uint32_t* __restrict__ count,
+__global__ void __launch_bounds__(kBlock, 4) k_extend(BvhView bvh, const float4* __restrict__ ro, const float4* __restrict__ rd, const uint32_t* __restrict__ count,
                                                     uint32_t* ticket, uint4* __restrict__ hits, float tmin, float tmax, unsigned long long* stat, TraceTuning tune) {
     const uint32_t n = *count;
     ExtendJob job{ro, rd, hits, tmin, tmax};
@@ -179,7 +179,7 @@ struct ShadowJob {
         float4 c = *dst; c.x += L.x; c.y += L.y; c.z += L.z; *dst = c;
     }
 };
-__global__ void __launch_bounds__(kBlock) k_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket,
+__global__ void __launch_bounds__(kBlock, 4) k_shadow(BvhView bvh, ShadowQueue q, const uint32_t* __restrict__ count, uint32_t* ticket,
                                                     float4* channels, size_t npix, float tmin, unsigned long long* stat, TraceTuning tune) {
     const uint32_t n = *count;
     ShadowJob job{q, channels, npix, tmin};
