@@ -149,16 +149,21 @@ struct Loader {
         if (acc.has("sparse")) bad("sparse accessors are not supported");
         comp_type = acc["componentType"].integer(0); comp_size = component_size(comp_type); comp_count = component_count(acc["type"].string());
         if (!comp_size || !comp_count) bad("accessor with unknown component type");
-        const size_t count = (size_t)acc["count"].integer(0), elem = (size_t)comp_size * comp_count;
-        std::vector<uint8_t> out(count * elem, 0);
-        if (!acc.has("bufferView")) return out;
+        const int64_t count_field = acc["count"].integer(0);
+        if (count_field < 0 || count_field > ((int64_t)1 << 31)) bad("accessor count out of range");
+        const size_t count = (size_t)count_field, elem = (size_t)comp_size * comp_count;
+        if (!acc.has("bufferView")) return std::vector<uint8_t>(count * elem, 0);
         const Value& view = doc["bufferViews"][(size_t)acc["bufferView"].integer(-1)];
         if (view.is_null()) bad("bufferView index out of range");
         const size_t buf = (size_t)view["buffer"].integer(0);
         if (buf >= buffers.size()) bad("buffer index out of range");
-        const size_t stride = std::max<size_t>(elem, (size_t)view["byteStride"].integer(0));
-        const size_t base = (size_t)view["byteOffset"].integer(0) + (size_t)acc["byteOffset"].integer(0);
-        if (count && base + (count - 1) * stride + elem > buffers[buf].size()) bad("accessor reads past the end of its buffer");
+        const int64_t stride_field = view["byteStride"].integer(0), off_view = view["byteOffset"].integer(0), off_acc = acc["byteOffset"].integer(0);
+        if (stride_field < 0 || stride_field > 65536 || off_view < 0 || off_acc < 0) bad("negative or implausible bufferView / accessor offsets");
+        const size_t stride = std::max<size_t>(elem, (size_t)stride_field);
+        const size_t base = (size_t)off_view + (size_t)off_acc, size = buffers[buf].size();
+        // overflow-safe form of: base + (count - 1) * stride + elem <= size
+        if (count && (base > size || elem > size - base || count - 1 > (size - base - elem) / stride)) bad("accessor reads past the end of its buffer");
+        std::vector<uint8_t> out(count * elem, 0);
         for (size_t i = 0; i < count; ++i) memcpy(out.data() + i * elem, buffers[buf].data() + base + i * stride, elem);
         return out;
     }
@@ -167,7 +172,7 @@ struct Loader {
         const std::vector<uint8_t> raw = accessor_bytes(index, cs, cc, ct);
         if (ct != 5126 || cc != want_count) bad(std::string(name) + " must be a float accessor of the expected width");
         std::vector<float> out(raw.size() / 4);
-        memcpy(out.data(), raw.data(), out.size() * 4);
+        if (!out.empty()) memcpy(out.data(), raw.data(), out.size() * 4);
         return out;
     }
 

@@ -236,7 +236,9 @@ void open_bytes(const uint8_t* p, size_t size, uint32_t index, LbNanoVdbOpaque& 
                     if (metas[k].file_size < 8) bad("truncated ZIP block");
                     const uint64_t zsize = rd<uint64_t>(p + pos);
                     if (zsize > metas[k].file_size - 8) bad("ZIP block larger than the grid's share of the file");
-                    if (!lb::png::inflate(p + pos + 8, (size_t)zsize, g.buf)) bad("ZIP codec: inflate failed");
+                    if (metas[k].grid_size > zsize * 1032u + 65536u) bad("ZIP codec: the grid size field exceeds what the block can inflate to");      // deflate expands at most ~1032 : 1
+                    g.buf.reserve((size_t)metas[k].grid_size);
+                    if (!lb::png::inflate(p + pos + 8, (size_t)zsize, g.buf, (size_t)metas[k].grid_size)) bad("ZIP codec: inflate failed");
                     if (g.buf.size() != metas[k].grid_size) bad("ZIP codec: decompressed size differs from the grid size");
                 } else bad(codec == 2 ? "BLOSC-compressed NanoVDB files are not supported (re-save with codec NONE or ZIP)" : "unknown compression codec");
             }

@@ -147,7 +147,9 @@ struct Huffman {
         return -1;
     }
 };
-inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+// `max_out`: the decompressed size the caller expects (PNG: rows x (stride + 1); NanoVDB: the grid size). A stream that produces more, or
+// that keeps decoding after its input is exhausted (the bit reader pads with zeros), is rejected instead of growing the output without bound.
+inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t max_out) {
     if (n < 6) return false;
     BitReader br(src + 2, n - 2);                           // zlib header: CMF, FLG
     static const uint16_t lbase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
@@ -160,6 +162,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
             br.align();
             const uint32_t len = br.get(16), nlen = br.get(16);
             if ((len ^ 0xFFFFu) != nlen) return false;
+            if (out.size() + len > max_out || br.pos > br.n + 8) return false;
             for (uint32_t i = 0; i < len; ++i) out.push_back((uint8_t)br.get(8));
         } else if (type == 1 || type == 2) {
             Huffman lit, dist; uint8_t lengths[320];
@@ -192,7 +195,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
             }
             for (;;) {
                 const int sym = lit.decode(br);
-                if (sym < 0) return false;
+                if (sym < 0 || out.size() >= max_out + 1 || br.pos > br.n + 8) return false;
                 if (sym < 256) out.push_back((uint8_t)sym);
                 else if (sym == 256) break;
                 else {
@@ -201,7 +204,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
                     const int ds = dist.decode(br);
                     if (ds < 0 || ds > 29) return false;
                     const uint32_t d = dbase[ds] + br.get(dextra[ds]);
-                    if (d > out.size()) return false;
+                    if (d > out.size() || out.size() + len > max_out) return false;
                     const size_t from = out.size() - d;
                     for (uint32_t k = 0; k < len; ++k) out.push_back(out[from + k]);
                 }
@@ -229,11 +232,12 @@ inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rg
         pos += 12 + (size_t)len;
     }
     if (!w || !h || lace || (depth != 8 && depth != 16)) return false;
+    if (w > 65536u || h > 65536u || (uint64_t)w * h > ((uint64_t)1 << 28)) return false;      // a corrupt header must not turn into a giant allocation
     const int channels = colour == 0 ? 1 : colour == 2 ? 3 : colour == 3 ? 1 : colour == 4 ? 2 : colour == 6 ? 4 : 0;
     if (!channels || (colour == 3 && depth != 8)) return false;
     const size_t bpp = (size_t)channels * (depth / 8), stride = bpp * w;
     std::vector<uint8_t> raw; raw.reserve((stride + 1) * h);
-    if (!inflate(idat.data(), idat.size(), raw) || raw.size() < (stride + 1) * h) return false;
+    if (!inflate(idat.data(), idat.size(), raw, (stride + 1) * (size_t)h) || raw.size() < (stride + 1) * h) return false;
     std::vector<uint8_t> img(stride * h);
     for (uint32_t y = 0; y < h; ++y) {
         const uint8_t* in = raw.data() + (size_t)y * (stride + 1); const int f = in[0]; ++in;
