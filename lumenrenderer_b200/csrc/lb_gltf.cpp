@@ -50,7 +50,7 @@ inline Vec3 cross3(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - 
 // column-major 4x4 (glm::mat4 layout): m[col * 4 + row]
 struct Mat4 { float m[16]; };
 Mat4 mat_identity() { Mat4 r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.f; return r; }
-bool mat_is_identity(const Mat4& a) { const Mat4 i = mat_identity(); return memcmp(a.m, i.m, sizeof a.m) == 0; }
+bool mat_is_identity(const Mat4& a) { const Mat4 i = mat_identity(); for (int k = 0; k < 16; ++k) if (!(a.m[k] == i.m[k])) return false; return true; }   // glm's ==: by value (-0 == 0)
 // glm operator*(mat4, mat4): Result[j] = ((A[0]*B[j][0] + A[1]*B[j][1]) + A[2]*B[j][2]) + A[3]*B[j][3]
 Mat4 mat_mul(const Mat4& a, const Mat4& b) {
     Mat4 r;
@@ -58,15 +58,21 @@ Mat4 mat_mul(const Mat4& a, const Mat4& b) {
         r.m[j * 4 + i] = ((a.m[0 * 4 + i] * b.m[j * 4 + 0] + a.m[1 * 4 + i] * b.m[j * 4 + 1]) + a.m[2 * 4 + i] * b.m[j * 4 + 2]) + a.m[3 * 4 + i] * b.m[j * 4 + 3];
     return r;
 }
-// Transform::UpdateLocalMatrix (Transform.cpp:264-280): translate(I, t) * mat4_cast(q) scaled per column
+// Transform::UpdateLocalMatrix (Transform.cpp:264-280) in glm's own operation order, so that signed zeros come out as the reference's do:
+// glm::translate(I, t) -> operator*(mat4, mat4_cast(q)) -> glm::scale (every column, w included, times its factor)
 Mat4 mat_trs(const float t[3], const float q[4] /* x y z w */, const float s[3]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
     const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
-    Mat4 r{};
-    r.m[0] = (1.f - 2.f * (qyy + qzz)) * s[0]; r.m[1] = (2.f * (qxy + qwz)) * s[0]; r.m[2] = (2.f * (qxz - qwy)) * s[0];
-    r.m[4] = (2.f * (qxy - qwz)) * s[1]; r.m[5] = (1.f - 2.f * (qxx + qzz)) * s[1]; r.m[6] = (2.f * (qyz + qwx)) * s[1];
-    r.m[8] = (2.f * (qxz + qwy)) * s[2]; r.m[9] = (2.f * (qyz - qwx)) * s[2]; r.m[10] = (1.f - 2.f * (qxx + qyy)) * s[2];
-    r.m[12] = t[0]; r.m[13] = t[1]; r.m[14] = t[2]; r.m[15] = 1.f;
+    Mat4 rot{};
+    rot.m[0] = 1.f - 2.f * (qyy + qzz); rot.m[1] = 2.f * (qxy + qwz); rot.m[2] = 2.f * (qxz - qwy);
+    rot.m[4] = 2.f * (qxy - qwz); rot.m[5] = 1.f - 2.f * (qxx + qzz); rot.m[6] = 2.f * (qyz + qwx);
+    rot.m[8] = 2.f * (qxz + qwy); rot.m[9] = 2.f * (qyz - qwx); rot.m[10] = 1.f - 2.f * (qxx + qyy);
+    rot.m[15] = 1.f;
+    const Mat4 id = mat_identity();
+    Mat4 tr = id;
+    for (int i = 0; i < 4; ++i) tr.m[12 + i] = ((id.m[i] * t[0] + id.m[4 + i] * t[1]) + id.m[8 + i] * t[2]) + id.m[12 + i];
+    Mat4 r = mat_mul(tr, rot);
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 4; ++i) r.m[j * 4 + i] = r.m[j * 4 + i] * s[j];
     return r;
 }
 

@@ -212,11 +212,19 @@ def _node_local(n):
     x, y, z, w = (F(v) for v in n.get("rotation", (0, 0, 0, 1)))
     qxx, qyy, qzz, qxz, qxy, qyz, qwx, qwy, qwz = x * x, y * y, z * z, x * z, x * y, y * z, w * x, w * y, w * z
     one, two = F(1), F(2)
-    r = np.zeros((4, 4), F)
-    r[0, :3] = np.array([one - two * (qyy + qzz), two * (qxy + qwz), two * (qxz - qwy)], F) * s[0]
-    r[1, :3] = np.array([two * (qxy - qwz), one - two * (qxx + qzz), two * (qyz + qwx)], F) * s[1]
-    r[2, :3] = np.array([two * (qxz + qwy), two * (qyz - qwx), one - two * (qxx + qyy)], F) * s[2]
-    r[3] = (t[0], t[1], t[2], 1)
+    rot = np.zeros((4, 4), F)                                 # glm::mat4_cast
+    rot[0, :3] = np.array([one - two * (qyy + qzz), two * (qxy + qwz), two * (qxz - qwy)], F)
+    rot[1, :3] = np.array([two * (qxy - qwz), one - two * (qxx + qzz), two * (qyz + qwx)], F)
+    rot[2, :3] = np.array([two * (qxz + qwy), two * (qyz - qwx), one - two * (qxx + qyy)], F)
+    rot[3, 3] = one
+    # Transform::UpdateLocalMatrix (Transform.cpp:264-280) in glm's operation order (it decides the sign of zeros):
+    # glm::translate(I, t): col3 = ((I0*tx + I1*ty) + I2*tz) + I3; then operator*(mat4, mat4); then glm::scale: column j (w included) * s[j]
+    eye = np.eye(4, dtype=F)
+    tr = eye.copy()
+    tr[3] = F(F(F(eye[0] * t[0]) + F(eye[1] * t[1])) + F(eye[2] * t[2])) + eye[3]
+    r = _mat_mul(tr, rot)
+    for j in range(3):
+        r[j] = r[j] * s[j]
     return r
 
 
