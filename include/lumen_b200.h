@@ -257,6 +257,11 @@ typedef struct LbGltfInfo {
 } LbGltfInfo;
 LB_API int lb_gltf_open(const char* path, LbImageDecodeFn decoder /* may be NULL */, void* user, LbGltf* out);
 LB_API int lb_gltf_close(LbGltf g);
+/* The model converter's cache (LumenPTModelConverter::ConvertGLTF, PT/Tools/LumenPTModelConverter.cpp:27-68: GenerateHeader :533-576 +
+ * OutputToFile :588-598; on-disk records LumenPTModelConverter.h:79-186): writes the opened document as an `.ollad` file, byte for byte
+ * the file the reference writes for the same asset. lb_gltf_open reads a path ending in ".ollad" back (LoadFile :70-273) instead of
+ * parsing glTF, as SceneManager does when the cache exists. */
+LB_API int lb_gltf_save_ollad(LbGltf g, const char* path);
 LB_API const char* lb_gltf_last_error(void);
 LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out);
 /* Inspection; returned pointers stay valid until lb_gltf_close. Texture members of the material are IMAGE indices of this document

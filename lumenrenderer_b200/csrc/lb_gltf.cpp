@@ -76,10 +76,21 @@ Mat4 mat_trs(const float t[3], const float q[4] /* x y z w */, const float s[3])
     return r;
 }
 
-struct Image { std::vector<uint8_t> px; uint32_t w = 1, h = 1; bool decoded = false, srgb = false, metal_rough = false; };
-struct Primitive { std::vector<float> pos, uv, nrm, tan; std::vector<uint32_t> idx; int32_t material = -1; };
+// LumenPTModelConverter::TextureType (LumenPTModelConverter.h:66-77); the LAST role a material assigns to an image wins (:364-521)
+enum TextureType : uint64_t { T_UNSPECIFIED = 0, T_DIFFUSE = 1, T_NORMAL, T_EMISSIVE, T_METAL_ROUGHNESS, T_TRANSMISSIVE, T_CLEAR_COAT, T_CLEAR_COAT_ROUGHNESS, T_TINT };
+struct Image {
+    std::vector<uint8_t> px; uint32_t w = 1, h = 1; bool decoded = false;
+    std::vector<uint8_t> raw;                       // the encoded file as the document holds it (what the .ollad cache stores)
+    uint64_t type = T_UNSPECIFIED;
+    bool srgb() const { return type == T_DIFFUSE || type == T_EMISSIVE; }      // LoadFile :131
+    bool metal_rough() const { return type == T_METAL_ROUGHNESS; }             // LoadFile :122
+};
+struct Primitive { std::vector<float> pos, uv, nrm, tan; std::vector<uint32_t> idx; int32_t material = -1; uint32_t index_size = 4; /* bytes per index in the source */ };
 struct Mesh { std::vector<Primitive> prims; };
 struct Instance { uint32_t mesh; float m[16]; /* row-major */ };
+// HeaderNode / HeaderScene (LumenPTModelConverter.h:163-186): the node table with LOCAL matrices, kept for the .ollad cache
+struct Node { std::string name; Mat4 local; int32_t mesh = -1; std::vector<Node> children; };
+struct Scene { std::string name; std::vector<Node> roots; };
 
 bool read_file(const std::string& path, std::vector<uint8_t>& out) {
     FILE* f = fopen(path.c_str(), "rb");
@@ -114,8 +125,45 @@ std::string uri_unescape(const std::string& s) {
 
 struct LbGltfOpaque {
     std::vector<Image> images; std::vector<LbMaterialDesc> materials; std::vector<Mesh> meshes; std::vector<Instance> instances;
+    std::vector<Scene> scenes;
     LbGltfInfo info{};
 };
+
+namespace {
+// stb_image in the reference (LoadFile :121); here PNG natively, anything else through the caller's decoder, else the 1x1 default
+void decode_image(LbGltfOpaque& g, Image& im, LbImageDecodeFn decoder, void* user) {
+    const bool have = !im.raw.empty();
+    if (have && lb::png::decode_rgba8(im.raw.data(), im.raw.size(), im.px, im.w, im.h)) im.decoded = true;
+    else if (have && decoder) {
+        uint8_t* px = nullptr; uint32_t w = 0, h = 0;
+        if (decoder(im.raw.data(), im.raw.size(), &px, &w, &h, user) == 0 && px && w && h) { im.px.assign(px, px + (size_t)w * h * 4); im.w = w; im.h = h; im.decoded = true; }
+        free(px);
+    }
+    if (!im.decoded) { im.px = {255, 255, 255, 255}; im.w = im.h = 1; ++g.info.undecoded_images; }
+}
+// :127-134 metal-roughness images: green (roughness) is at least 1/255
+void floor_roughness(LbGltfOpaque& g) {
+    for (Image& im : g.images) if (im.metal_rough()) for (size_t p = 0; p < im.px.size(); p += 4) if (im.px[p + 1] < 1) im.px[p + 1] = 1;
+}
+// LoadNode (:275-317): a mesh node's instance transform is parented to the enclosing node's transform, but the children of a MESH node
+// are parented to that node's own (unparented) transform. `parent_world`: world matrix of the parent node's transform object.
+void flatten_node(LbGltfOpaque& g, const Node& n, const Mat4* parent_world) {
+    const Mat4 with_parent = parent_world ? mat_mul(*parent_world, n.local) : n.local;
+    Mat4 own_world;
+    if (n.mesh >= 0) {
+        Instance in; in.mesh = (uint32_t)n.mesh;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) in.m[r * 4 + c] = with_parent.m[c * 4 + r];
+        g.instances.push_back(in);
+        own_world = n.local;
+    } else own_world = with_parent;
+    for (const Node& c : n.children) flatten_node(g, c, &own_world);
+}
+void flatten_scenes(LbGltfOpaque& g) {
+    g.instances.clear();
+    for (const Scene& s : g.scenes) for (const Node& r : s.roots) flatten_node(g, r, nullptr);
+    g.info.instances = (uint32_t)g.instances.size();
+}
+} // namespace
 
 namespace {
 
@@ -194,13 +242,8 @@ struct Loader {
                 if (!view.is_null() && buf < buffers.size() && off + len <= buffers[buf].size()) { bytes.assign(buffers[buf].begin() + off, buffers[buf].begin() + off + len); have = true; }
             }
             Image& im = g.images[i];
-            if (have && lb::png::decode_rgba8(bytes.data(), bytes.size(), im.px, im.w, im.h)) im.decoded = true;
-            else if (have && decoder) {
-                uint8_t* px = nullptr; uint32_t w = 0, h = 0;
-                if (decoder(bytes.data(), bytes.size(), &px, &w, &h, user) == 0 && px && w && h) { im.px.assign(px, px + (size_t)w * h * 4); im.w = w; im.h = h; im.decoded = true; }
-                free(px);
-            }
-            if (!im.decoded) { im.px = {255, 255, 255, 255}; im.w = im.h = 1; ++g.info.undecoded_images; }
+            if (have) im.raw = std::move(bytes);
+            decode_image(g, im, decoder, user);
         }
         g.info.images = (uint32_t)g.images.size();
     }
@@ -229,9 +272,8 @@ struct Loader {
             d.normal_texture = texture_image(m["normalTexture"]);
             d.metallic_roughness_texture = texture_image(pbr["metallicRoughnessTexture"]);
             d.emissive_texture = texture_image(m["emissiveTexture"]);
-            if (d.diffuse_texture >= 0) g.images[d.diffuse_texture].srgb = true;
-            if (d.emissive_texture >= 0) g.images[d.emissive_texture].srgb = true;
-            if (d.metallic_roughness_texture >= 0) g.images[d.metallic_roughness_texture].metal_rough = true;
+            auto role = [&](int32_t image, TextureType t) { if (image >= 0) g.images[image].type = t; };      // assignment order of :364-521
+            role(d.diffuse_texture, T_DIFFUSE); role(d.normal_texture, T_NORMAL); role(d.metallic_roughness_texture, T_METAL_ROUGHNESS); role(d.emissive_texture, T_EMISSIVE);
             d.metallic_factor = (float)pbr["metallicFactor"].number(1.0);
             d.roughness_factor = fmaxf(0.01f, (float)pbr["roughnessFactor"].number(1.0));
             d.luminance = 1.f; d.subsurface_factor = 0.f; d.anisotropic = 0.f;
@@ -254,10 +296,10 @@ struct Loader {
             d.specular_factor = sp.is_object() ? (float)sp["specularFactor"].number(0.0) : 0.f;
             d.specular_tint_factor = sp.is_object() ? 1.f : 0.f;
             d.tint_texture = sp.is_object() ? extension_texture(sp, "specularColorTexture") : LB_NO_HANDLE;
+            role(d.transmission_texture, T_TRANSMISSIVE); role(d.clear_coat_roughness_texture, T_CLEAR_COAT_ROUGHNESS); role(d.clear_coat_texture, T_CLEAR_COAT); role(d.tint_texture, T_TINT);
             g.materials.push_back(d);
         }
-        // :127-134 metal-roughness images: green (roughness) is at least 1/255
-        for (Image& im : g.images) if (im.metal_rough) for (size_t p = 0; p < im.px.size(); p += 4) if (im.px[p + 1] < 1) im.px[p + 1] = 1;
+        floor_roughness(g);
         g.info.materials = (uint32_t)g.materials.size();
     }
 
@@ -317,7 +359,7 @@ struct Loader {
                     uint32_t cs, cc; int64_t ct;
                     const std::vector<uint8_t> raw = accessor_bytes(fp["indices"].integer(-1), cs, cc, ct);
                     if (cc != 1 || ct == 5126) bad("indices must be scalar integers");
-                    p.idx.resize(raw.size() / cs);
+                    p.idx.resize(raw.size() / cs); p.index_size = cs;
                     for (size_t k = 0; k < p.idx.size(); ++k) p.idx[k] = cs == 1 ? raw[k] : cs == 2 ? (uint32_t)(raw[2 * k] | (raw[2 * k + 1] << 8)) : (uint32_t)(raw[4 * k] | (raw[4 * k + 1] << 8) | (raw[4 * k + 2] << 16) | ((uint32_t)raw[4 * k + 3] << 24));
                 } else { p.idx.resize(nv); for (size_t k = 0; k < nv; ++k) p.idx[k] = (uint32_t)k; }
                 p.idx.resize(p.idx.size() / 3 * 3);
@@ -344,31 +386,159 @@ struct Loader {
         for (int k = 0; k < 4; ++k) q[k] = (float)n["rotation"][(size_t)k].number(k == 3 ? 1.0 : 0.0);
         return mat_trs(t, q, s);
     }
-    // `parent_world`: world matrix of the parent NODE's transform object; null for root nodes
-    void load_node(int64_t index, const Mat4* parent_world, int depth) {
+    Node load_node(int64_t index, int depth) {
         const Value& n = doc["nodes"][(size_t)index];
         if (index < 0 || n.is_null()) bad("node index out of range");
         if (depth > 512) bad("node hierarchy too deep (cycle?)");
-        const Mat4 local = node_local(n);
-        const Mat4 with_parent = parent_world ? mat_mul(*parent_world, local) : local;
+        Node out; out.name = n["name"].is_null() ? std::string() : n["name"].string(); out.local = node_local(n);
         const int64_t mesh = n["mesh"].integer(-1);
-        Mat4 own_world;                                                        // world matrix of node->m_Transform as its children see it
-        if (mesh >= 0) {
-            if (mesh >= (int64_t)g.meshes.size()) bad("mesh index out of range");
-            Instance in; in.mesh = (uint32_t)mesh;
-            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) in.m[r * 4 + c] = with_parent.m[c * 4 + r];
-            g.instances.push_back(in);
-            own_world = local;                                                 // :296-306: only the mesh instance's transform is parented
-        } else own_world = with_parent;
+        if (mesh >= (int64_t)g.meshes.size()) bad("mesh index out of range");
+        out.mesh = mesh >= 0 ? (int32_t)mesh : -1;
         const Value& ch = n["children"];
-        for (size_t k = 0; k < ch.size(); ++k) load_node(ch[k].integer(-1), &own_world, depth + 1);
+        for (size_t k = 0; k < ch.size(); ++k) out.children.push_back(load_node(ch[k].integer(-1), depth + 1));
+        return out;
     }
     void load_scenes() {
         const Value& scenes = doc["scenes"];
-        for (size_t s = 0; s < scenes.size(); ++s) { const Value& roots = scenes[s]["nodes"]; for (size_t k = 0; k < roots.size(); ++k) load_node(roots[k].integer(-1), nullptr, 0); }
-        g.info.instances = (uint32_t)g.instances.size();
+        for (size_t s = 0; s < scenes.size(); ++s) {
+            Scene sc; sc.name = scenes[s]["name"].is_null() ? std::string() : scenes[s]["name"].string();
+            const Value& roots = scenes[s]["nodes"];
+            for (size_t k = 0; k < roots.size(); ++k) sc.roots.push_back(load_node(roots[k].integer(-1), 0));
+            g.scenes.push_back(std::move(sc));
+        }
+        flatten_scenes(g);
     }
 };
+
+
+// ---- the `.ollad` cache (LumenPTModelConverter: GenerateHeader :533-576, OutputToFile :588-598, LoadFile :70-273) ----
+// file = u64 headerSize | header | blob.   header = u64 nTex, HeaderTexture[] | u64 nMat, HeaderMaterial[] | u64 nMesh, per mesh { u32 nPrim,
+// HeaderPrimitive[] } | u64 nScenes, per scene { u32 nRoots, u32 nameLength, name, nodes depth first: { u32 nameLength, u32 nChildren,
+// f32 local[16] (column-major), i32 mesh, name } }.   blob = the encoded image files, then per primitive the interleaved 64-byte Vertex
+// records (ModelStructs.h:21-28: position @0, uv @16, normal @24, tangent @48, padding zero) and the indices at their source width.
+// Offsets in the header are relative to the blob.
+struct OlladTexture { uint64_t offset, size, type; };
+struct OlladMaterial {
+    float color[4], emission[3];
+    int32_t diffuse, normal, metal_rough, emissive, transmission, clear_coat, clear_coat_roughness, tint;
+    float transmission_factor, clear_coat_factor, clear_coat_roughness_factor, ior, specular, specular_tint, subsurface, luminance, anisotropic, sheen, sheen_tint, metallic, roughness;
+    float tint_factor[3], transmittance[3];
+};
+struct OlladPrimitive { uint64_t vb_offset, vb_size, ib_offset, ib_size; uint32_t index_size, material; };
+struct OlladNode { uint32_t name_length, num_children; float local[16]; int32_t mesh; };
+struct OlladScene { uint32_t num_roots, name_length; };
+static_assert(sizeof(OlladTexture) == 24 && sizeof(OlladMaterial) == 136 && sizeof(OlladPrimitive) == 40 && sizeof(OlladNode) == 76 && sizeof(OlladScene) == 8, "ollad records are packed");
+
+void put(std::vector<uint8_t>& o, const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); o.insert(o.end(), b, b + n); }
+void put_node(std::vector<uint8_t>& o, const Node& n) {
+    OlladNode h{}; h.name_length = (uint32_t)n.name.size(); h.num_children = (uint32_t)n.children.size(); memcpy(h.local, n.local.m, 64); h.mesh = n.mesh;
+    put(o, &h, sizeof h); put(o, n.name.data(), n.name.size());
+    for (const Node& c : n.children) put_node(o, c);
+}
+OlladMaterial to_ollad(const LbMaterialDesc& d) {
+    OlladMaterial m{};
+    memcpy(m.color, d.diffuse_color, 16); memcpy(m.emission, d.emission, 12);
+    m.diffuse = d.diffuse_texture; m.normal = d.normal_texture; m.metal_rough = d.metallic_roughness_texture; m.emissive = d.emissive_texture;
+    m.transmission = d.transmission_texture; m.clear_coat = d.clear_coat_texture; m.clear_coat_roughness = d.clear_coat_roughness_texture; m.tint = d.tint_texture;
+    m.transmission_factor = d.transmission_factor; m.clear_coat_factor = d.clear_coat_factor; m.clear_coat_roughness_factor = d.clear_coat_roughness_factor;
+    m.ior = d.index_of_refraction; m.specular = d.specular_factor; m.specular_tint = d.specular_tint_factor; m.subsurface = d.subsurface_factor; m.luminance = d.luminance;
+    m.anisotropic = d.anisotropic; m.sheen = d.sheen_factor; m.sheen_tint = d.sheen_tint_factor; m.metallic = d.metallic_factor; m.roughness = d.roughness_factor;
+    memcpy(m.tint_factor, d.tint_factor, 12); memcpy(m.transmittance, d.transmittance, 12);
+    return m;
+}
+LbMaterialDesc from_ollad(const OlladMaterial& m) {
+    LbMaterialDesc d{};
+    memcpy(d.diffuse_color, m.color, 16); memcpy(d.emission, m.emission, 12);
+    d.diffuse_texture = m.diffuse; d.normal_texture = m.normal; d.metallic_roughness_texture = m.metal_rough; d.emissive_texture = m.emissive;
+    d.transmission_texture = m.transmission; d.clear_coat_texture = m.clear_coat; d.clear_coat_roughness_texture = m.clear_coat_roughness; d.tint_texture = m.tint;
+    d.transmission_factor = m.transmission_factor; d.clear_coat_factor = m.clear_coat_factor; d.clear_coat_roughness_factor = m.clear_coat_roughness_factor;
+    d.index_of_refraction = m.ior; d.specular_factor = m.specular; d.specular_tint_factor = m.specular_tint; d.subsurface_factor = m.subsurface; d.luminance = m.luminance;
+    d.anisotropic = m.anisotropic; d.sheen_factor = m.sheen; d.sheen_tint_factor = m.sheen_tint; d.metallic_factor = m.metallic; d.roughness_factor = m.roughness;
+    memcpy(d.tint_factor, m.tint_factor, 12); memcpy(d.transmittance, m.transmittance, 12);
+    return d;
+}
+
+struct OlladReader {
+    LbGltfOpaque& g; const std::vector<uint8_t>& file; size_t at = 8, header_end = 0; const uint8_t* blob = nullptr; size_t blob_size = 0;
+    [[noreturn]] void bad(const std::string& what) const { throw std::runtime_error("ollad: " + what); }
+    void get(void* out, size_t n) { if (n > header_end - at) bad("header record runs past the end of the header"); memcpy(out, file.data() + at, n); at += n; }
+    uint64_t count(size_t record) { uint64_t n; get(&n, 8); if (n > (header_end - at) / (record ? record : 1)) bad("implausible record count"); return n; }
+    const uint8_t* span(uint64_t off, uint64_t size) const { if (off > blob_size || size > blob_size - off) bad("payload range outside the file"); return blob + off; }
+    std::string name(uint32_t n) { if (n > header_end - at) bad("name runs past the end of the header"); std::string s(reinterpret_cast<const char*>(file.data() + at), n); at += n; return s; }
+    Node node(int depth) {
+        if (depth > 512) bad("node hierarchy too deep");
+        OlladNode h; get(&h, sizeof h);
+        Node n; n.name = name(h.name_length); memcpy(n.local.m, h.local, 64); n.mesh = h.mesh;
+        if (n.mesh < -1 || n.mesh >= (int64_t)g.meshes.size()) bad("mesh index out of range");
+        if (h.num_children > (header_end - at) / sizeof(OlladNode)) bad("implausible child count");
+        for (uint32_t k = 0; k < h.num_children; ++k) n.children.push_back(node(depth + 1));
+        return n;
+    }
+    void read(LbImageDecodeFn decoder, void* user) {
+        if (file.size() < 8) bad("file shorter than its size field");
+        uint64_t header_size; memcpy(&header_size, file.data(), 8);
+        if (header_size > file.size() - 8) bad("header size exceeds the file");
+        header_end = 8 + (size_t)header_size; blob = file.data() + header_end; blob_size = file.size() - header_end;
+        const uint64_t ntex = count(sizeof(OlladTexture));
+        g.images.resize((size_t)ntex);
+        for (Image& im : g.images) {
+            OlladTexture t; get(&t, sizeof t);
+            const uint8_t* p = span(t.offset, t.size);
+            im.raw.assign(p, p + t.size); im.type = t.type;
+            decode_image(g, im, decoder, user);
+        }
+        floor_roughness(g);
+        g.info.images = (uint32_t)g.images.size();
+        const uint64_t nmat = count(sizeof(OlladMaterial));
+        for (uint64_t i = 0; i < nmat; ++i) {
+            OlladMaterial m; get(&m, sizeof m);
+            LbMaterialDesc d = from_ollad(m);
+            for (LbHandle* h : {&d.diffuse_texture, &d.normal_texture, &d.metallic_roughness_texture, &d.emissive_texture, &d.transmission_texture, &d.clear_coat_texture, &d.clear_coat_roughness_texture, &d.tint_texture})
+                if (*h < -1 || *h >= (int64_t)g.images.size()) bad("texture index out of range");
+            g.materials.push_back(d);
+        }
+        g.info.materials = (uint32_t)g.materials.size();
+        const uint64_t nmesh = count(4);
+        for (uint64_t mi = 0; mi < nmesh; ++mi) {
+            uint32_t nprim; get(&nprim, 4);
+            if (nprim > (header_end - at) / sizeof(OlladPrimitive)) bad("implausible primitive count");
+            Mesh mesh;
+            for (uint32_t pi = 0; pi < nprim; ++pi) {
+                OlladPrimitive h; get(&h, sizeof h);
+                if (h.vb_size % 64 || (h.index_size != 1 && h.index_size != 2 && h.index_size != 4) || h.ib_size % h.index_size) bad("primitive with a malformed vertex or index buffer");
+                const uint8_t* vb = span(h.vb_offset, h.vb_size); const uint8_t* ib = span(h.ib_offset, h.ib_size);
+                Primitive p; const size_t nv = (size_t)(h.vb_size / 64), ni = (size_t)(h.ib_size / h.index_size) / 3 * 3;
+                if (nv > ((size_t)1 << 31) || ni > ((size_t)1 << 32)) bad("primitive too large");
+                p.pos.resize(nv * 3); p.uv.resize(nv * 2); p.nrm.resize(nv * 3); p.tan.resize(nv * 4); p.idx.resize(ni); p.index_size = h.index_size;
+                for (size_t v = 0; v < nv; ++v) {
+                    const uint8_t* r = vb + v * 64;
+                    memcpy(&p.pos[v * 3], r, 12); memcpy(&p.uv[v * 2], r + 16, 8); memcpy(&p.nrm[v * 3], r + 24, 12); memcpy(&p.tan[v * 4], r + 48, 16);
+                }
+                for (size_t k = 0; k < ni; ++k) {
+                    const uint8_t* r = ib + k * h.index_size;
+                    p.idx[k] = h.index_size == 1 ? r[0] : h.index_size == 2 ? (uint32_t)(r[0] | (r[1] << 8)) : (uint32_t)(r[0] | (r[1] << 8) | (r[2] << 16) | ((uint32_t)r[3] << 24));
+                    if (p.idx[k] >= nv) bad("index out of range");
+                }
+                p.material = (int32_t)h.material;                                  // 0xFFFFFFFF = the glTF default material
+                if (p.material < -1 || p.material >= (int32_t)g.materials.size()) bad("material index out of range");
+                g.info.triangles += (uint32_t)(ni / 3); g.info.vertices += (uint32_t)nv; ++g.info.primitives;
+                mesh.prims.push_back(std::move(p));
+            }
+            g.meshes.push_back(std::move(mesh));
+        }
+        g.info.meshes = (uint32_t)g.meshes.size();
+        const uint64_t nscenes = count(sizeof(OlladScene));
+        for (uint64_t si = 0; si < nscenes; ++si) {
+            OlladScene h; get(&h, sizeof h);
+            Scene sc; sc.name = name(h.name_length);
+            if (h.num_roots > (header_end - at) / sizeof(OlladNode)) bad("implausible root count");
+            for (uint32_t k = 0; k < h.num_roots; ++k) sc.roots.push_back(node(0));
+            g.scenes.push_back(std::move(sc));
+        }
+        flatten_scenes(g);
+    }
+};
+bool has_extension(const std::string& p, const char* ext) { const size_t n = strlen(ext); return p.size() >= n && p.compare(p.size() - n, n, ext) == 0; }
 
 } // namespace
 
@@ -383,6 +553,13 @@ LB_API int lb_gltf_open(const char* path, LbImageDecodeFn decoder, void* user, L
         std::vector<uint8_t> file;
         if (!read_file(path, file)) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("cannot read ") + path);
         const std::string p(path); const size_t slash = p.find_last_of("/\\");
+        if (has_extension(p, ".ollad")) {                                            // LumenPTModelConverter::ms_ExtensionName: the cache instead of the source
+            std::unique_ptr<LbGltfOpaque> g(new LbGltfOpaque());
+            OlladReader R{*g, file};
+            R.read(decoder, user);
+            *out = g.release();
+            return LB_OK;
+        }
         std::vector<uint8_t> bin; const char* text = reinterpret_cast<const char*>(file.data()); size_t text_len = file.size();
         if (file.size() >= 12 && memcmp(file.data(), "glTF", 4) == 0) {             // GLB container: header, JSON chunk, optional BIN chunk
             auto le = [&](size_t at) { return (uint32_t)file[at] | ((uint32_t)file[at + 1] << 8) | ((uint32_t)file[at + 2] << 16) | ((uint32_t)file[at + 3] << 24); };
@@ -405,12 +582,52 @@ LB_API int lb_gltf_open(const char* path, LbImageDecodeFn decoder, void* user, L
         return LB_OK;
     } catch (const std::exception& e) { return gfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
 }
+LB_API int lb_gltf_save_ollad(LbGltf g, const char* path) {
+    if (!g || !path) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        std::vector<uint8_t> header, blob;
+        const uint64_t ntex = g->images.size(), nmat = g->materials.size(), nmesh = g->meshes.size(), nscenes = g->scenes.size();
+        put(header, &ntex, 8);
+        for (const Image& im : g->images) { const OlladTexture t{blob.size(), im.raw.size(), im.type}; put(header, &t, sizeof t); put(blob, im.raw.data(), im.raw.size()); }
+        put(header, &nmat, 8);
+        for (const LbMaterialDesc& d : g->materials) { const OlladMaterial m = to_ollad(d); put(header, &m, sizeof m); }
+        put(header, &nmesh, 8);
+        for (const Mesh& mesh : g->meshes) {
+            const uint32_t nprim = (uint32_t)mesh.prims.size(); put(header, &nprim, 4);
+            for (const Primitive& p : mesh.prims) {
+                const size_t nv = p.pos.size() / 3;
+                OlladPrimitive h{}; h.vb_offset = blob.size(); h.vb_size = nv * 64;
+                blob.resize(blob.size() + nv * 64, 0);
+                for (size_t v = 0; v < nv; ++v) {
+                    uint8_t* r = blob.data() + h.vb_offset + v * 64;
+                    memcpy(r, &p.pos[v * 3], 12); memcpy(r + 16, &p.uv[v * 2], 8); memcpy(r + 24, &p.nrm[v * 3], 12); memcpy(r + 48, &p.tan[v * 4], 16);
+                }
+                h.ib_offset = blob.size(); h.index_size = p.index_size; h.ib_size = p.idx.size() * p.index_size;
+                for (uint32_t i : p.idx) put(blob, &i, p.index_size);          // little endian: the low bytes
+                h.material = (uint32_t)p.material;
+                put(header, &h, sizeof h);
+            }
+        }
+        put(header, &nscenes, 8);
+        for (const Scene& sc : g->scenes) {
+            const OlladScene h{(uint32_t)sc.roots.size(), (uint32_t)sc.name.size()};
+            put(header, &h, sizeof h); put(header, sc.name.data(), sc.name.size());
+            for (const Node& n : sc.roots) put_node(header, n);
+        }
+        FILE* f = fopen(path, "wb");
+        if (!f) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("cannot write ") + path);
+        const uint64_t header_size = header.size();
+        const bool ok = fwrite(&header_size, 8, 1, f) == 1 && (header.empty() || fwrite(header.data(), 1, header.size(), f) == header.size()) && (blob.empty() || fwrite(blob.data(), 1, blob.size(), f) == blob.size());
+        if (fclose(f) != 0 || !ok) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("short write to ") + path);
+        return LB_OK;
+    } catch (const std::exception& e) { return gfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
+}
 LB_API int lb_gltf_close(LbGltf g) { delete g; return LB_OK; }
 LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out) { if (!g || !out) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument"); *out = g->info; return LB_OK; }
 LB_API int lb_gltf_image(LbGltf g, uint32_t i, const uint8_t** rgba8, uint32_t* w, uint32_t* h, int* srgb, int* decoded) {
     if (!g || i >= g->images.size()) return gfail(LB_ERR_INVALID_HANDLE, "image");
     const Image& im = g->images[i];
-    if (rgba8) *rgba8 = im.px.data(); if (w) *w = im.w; if (h) *h = im.h; if (srgb) *srgb = im.srgb ? 1 : 0; if (decoded) *decoded = im.decoded ? 1 : 0;
+    if (rgba8) *rgba8 = im.px.data(); if (w) *w = im.w; if (h) *h = im.h; if (srgb) *srgb = im.srgb() ? 1 : 0; if (decoded) *decoded = im.decoded ? 1 : 0;
     return LB_OK;
 }
 LB_API int lb_gltf_material(LbGltf g, uint32_t i, LbMaterialDesc* out) {
@@ -442,7 +659,7 @@ LB_API int lb_gltf_upload(LbRenderer r, LbGltf g, const float* root16, LbHandle*
     auto check = [&](int rc) { if (rc != LB_OK) { g_error = lb_last_error(); throw rc; } };
     try {
         std::vector<LbHandle> tex(g->images.size(), LB_NO_HANDLE), mats(g->materials.size(), LB_NO_HANDLE), meshes(g->meshes.size(), LB_NO_HANDLE);
-        for (size_t i = 0; i < g->images.size(); ++i) { const Image& im = g->images[i]; if (im.decoded) check(lb_texture_create(r, im.px.data(), im.w, im.h, im.srgb ? 1 : 0, &tex[i])); }
+        for (size_t i = 0; i < g->images.size(); ++i) { const Image& im = g->images[i]; if (im.decoded) check(lb_texture_create(r, im.px.data(), im.w, im.h, im.srgb() ? 1 : 0, &tex[i])); }
         auto map_tex = [&](LbHandle& h) { h = h >= 0 ? tex[(size_t)h] : LB_NO_HANDLE; };
         for (size_t i = 0; i < g->materials.size(); ++i) {
             LbMaterialDesc d = g->materials[i];

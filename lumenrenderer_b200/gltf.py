@@ -95,6 +95,11 @@ class GltfDocument:
             raise GltfError("instance index")
         return {"mesh": mesh.value, "transform": m.reshape(4, 4)}
 
+    def save_ollad(self, path: str) -> None:
+        """lb_gltf_save_ollad: the reference converter's `.ollad` cache file of this document (GltfDocument(path.ollad) reads it back)."""
+        if self.b.gltf_save_ollad(self._h, os.fsencode(path)) != 0:
+            raise GltfError((self.b.gltf_last_error() or b"").decode())
+
     def to_scene_description(self) -> api.SceneDescription:
         s = api.SceneDescription(name="gltf")
         images = [self.image(i) for i in range(self.info["images"])]

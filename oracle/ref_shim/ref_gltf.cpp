@@ -4,7 +4,7 @@
 // nlohmann-json, glm and stb_image, by oracle/Makefile into oracle/_ref/ref_gltf. Nothing of the reference is copied into this repository.
 // `#define private public` reaches the converter's private GenerateContent; an overlay copy of LumenRenderer.h (written by the Makefile
 // into oracle/_ref/ov, a sed of the original) replaces the MSVC-only default argument `SceneData a_SceneData = {}`.
-//   ref_gltf <in.gltf|in.glb> <out.bin>
+//   ref_gltf <in.gltf|in.glb> <out.bin> [out.ollad]      (out.ollad: GenerateHeader + OutputToFile :533-594, the reference's cache file itself)
 // out.bin: u32 nMaterials, u32 sizeof(HeaderMaterial), the HeaderMaterial records; u32 nTextures, per texture u64 offset, size, type;
 // u32 nMeshes, per mesh u32 nPrimitives, per primitive u64 vertexBytes, indexBytes, indexSize, materialId + the interleaved 64-byte
 // vertices + the indices; u32 nScenes, per scene u32 nRoots, per node (depth first) f32 transform[16], i32 meshId, u32 nChildren.
@@ -52,6 +52,7 @@ int main(int argc, char** argv) {
     n = (uint32_t)content.m_Scenes.size(); fwrite(&n, 4, 1, f);
     for (auto& s : content.m_Scenes) { uint32_t r = (uint32_t)s.m_RootNodes.size(); fwrite(&r, 4, 1, f); for (auto& rn : s.m_RootNodes) dump_node(f, rn); }
     fclose(f);
+    if (argc > 3) { auto header = LumenPTModelConverter::GenerateHeader(content); LumenPTModelConverter::OutputToFile(header, content.m_Blob, argv[3]); }
     fprintf(stderr, "materials %zu meshes %zu textures %zu scenes %zu blob %llu\n", content.m_Materials.size(), content.m_Meshes.size(), content.m_Textures.size(), content.m_Scenes.size(), (unsigned long long)content.m_Blob.m_Offset);
     return 0;
 }

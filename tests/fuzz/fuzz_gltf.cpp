@@ -21,16 +21,17 @@ int main(int argc, char** argv) {
         FILE* f = fopen(argv[a], "rb"); fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
         std::vector<unsigned char> orig(n); if (fread(orig.data(), 1, n, f) != (size_t)n) return 1; fclose(f);
         const bool glb = strstr(argv[a], ".glb") != nullptr;
-        const std::string tmp = std::string(getenv("FUZZ_TMP") ? getenv("FUZZ_TMP") : "/tmp") + "/fuzz_gltf" + (glb ? ".glb" : ".gltf");
+        const bool ollad = strstr(argv[a], ".ollad") != nullptr;                  // binary cache file: byte mutations only
+        const std::string tmp = std::string(getenv("FUZZ_TMP") ? getenv("FUZZ_TMP") : "/tmp") + "/fuzz_gltf" + (ollad ? ".ollad" : glb ? ".glb" : ".gltf");
         for (int it = 0; it < iters; ++it) {
             std::vector<unsigned char> b = orig;
-            const int kind = rnd() % 5;
+            const int kind = ollad ? (rnd() % 2 ? 0 : 3) : rnd() % 5;
             if (kind == 0) b.resize(rnd() % (b.size() + 1));
             const int edits = 1 + rnd() % 6;
             for (int e = 0; e < edits && !b.empty(); ++e) {
                 size_t at = rnd() % b.size();
                 if (kind == 1) { static const char* tok[] = {"-1", "99999999", "0", "{}", "[]", "null", "1e308", "\"\"", ",", "}"}; const char* t = tok[rnd() % 10]; for (size_t k = 0; t[k] && at + k < b.size(); ++k) b[at + k] = (unsigned char)t[k]; }
-                else if (kind == 2 && !glb) { // digit tweak: hits counts, offsets, indices
+                else if (kind == 2 && !glb && !ollad) { // digit tweak: hits counts, offsets, indices
                     for (size_t k = at; k < b.size() && k < at + 200; ++k) if (b[k] >= '0' && b[k] <= '9') { b[k] = (unsigned char)('0' + rnd() % 10); break; } }
                 else b[at] = (unsigned char)rnd();
             }
@@ -42,6 +43,7 @@ int main(int argc, char** argv) {
                 for (uint32_t m = 0; m < info.meshes; ++m) { uint32_t c = 0; lb_gltf_mesh_primitive_count(g, m, &c); for (uint32_t p = 0; p < c; ++p) { LbPrimitiveDesc d; lb_gltf_primitive(g, m, p, &d); } }
                 for (uint32_t i = 0; i < info.materials; ++i) { LbMaterialDesc d; lb_gltf_material(g, i, &d); }
                 LbHandle first; uint32_t cnt; lb_gltf_upload((LbRenderer)1, g, nullptr, &first, &cnt);
+                if (it % 8 == 0) lb_gltf_save_ollad(g, (tmp + ".out").c_str());
                 lb_gltf_close(g);
             }
         }

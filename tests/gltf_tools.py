@@ -240,7 +240,7 @@ def load_reference_semantics(path):
         return doc["textures"][info["index"]].get("source", -1)
 
     n_images = len(doc.get("images", []))
-    srgb = [False] * n_images; metal_rough = [False] * n_images
+    types = [0] * n_images                                    # TextureType (LumenPTModelConverter.h:66-77): the LAST role assigned wins (:364-521)
     materials = []
     for m in doc.get("materials", []):
         pbr = m.get("pbrMetallicRoughness", {}); ext = m.get("extensions", {})
@@ -266,11 +266,10 @@ def load_reference_semantics(path):
         d["specular_factor"] = F(sp.get("specularFactor", 0.0)) if sp is not None else F(0)
         d["specular_tint_factor"] = F(1 if sp is not None else 0)
         d["tint_texture"] = tex_image(sp.get("specularColorTexture")) if sp is not None else -1
-        for key in ("diffuse_texture", "emissive_texture"):
+        for key, role in (("diffuse_texture", 1), ("normal_texture", 2), ("metallic_roughness_texture", 4), ("emissive_texture", 3), ("transmission_texture", 5),
+                          ("clear_coat_roughness_texture", 7), ("clear_coat_texture", 6), ("tint_texture", 8)):          # in the converter's statement order
             if d[key] >= 0:
-                srgb[d[key]] = True
-        if d["metallic_roughness_texture"] >= 0:
-            metal_rough[d["metallic_roughness_texture"]] = True
+                types[d[key]] = role
         materials.append(d)
 
     meshes = []
@@ -308,4 +307,6 @@ def load_reference_semantics(path):
     for scene in doc.get("scenes", []):
         for r in scene.get("nodes", []):
             visit(r, None)
-    return {"srgb": srgb, "metal_rough": metal_rough, "materials": materials, "meshes": meshes, "instances": instances, "doc": doc, "buffers": buffers}
+    srgb = [t in (1, 3) for t in types]                       # LoadFile :131
+    metal_rough = [t == 4 for t in types]                     # LoadFile :122
+    return {"srgb": srgb, "metal_rough": metal_rough, "texture_types": types, "materials": materials, "meshes": meshes, "instances": instances, "doc": doc, "buffers": buffers}

@@ -1,7 +1,8 @@
 """Golden data from the reference's OWN model converter (LumenPTModelConverter::GenerateContent, compiled for the host in place by
 oracle/Makefile -> oracle/_ref/ref_gltf; needs /root/reference, so this runs in the build container only) for the two glTF assets the
 reference ships: Sandbox/assets/models/CornellBox/scene.gltf (stored completely, 7 KB) and Sponza/Sponza.gltf (262 267 triangles: the
-material table and node table completely, every vertex stream and index buffer as a SHA-256). Writes tests/golden/gltf_reference_converter.npz."""
+material table and node table completely, every vertex stream and index buffer as a SHA-256). Also the `.ollad` cache file the reference writes for each (Cornell: the file itself, tests/golden/cornell_reference.ollad, 7 KB;
+Sponza: its SHA-256 and size). Writes tests/golden/gltf_reference_converter.npz."""
 import hashlib
 import os
 import struct
@@ -16,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 ASSETS = "/root/reference/Lumen_Engine/Sandbox/assets/models"
 FILES = {"cornell": ASSETS + "/CornellBox/scene.gltf", "sponza": ASSETS + "/Sponza/Sponza.gltf"}
 
-# LumenPTModelConverter::HeaderMaterial (LumenPTModelConverter.h:85-137), 144 bytes
+# LumenPTModelConverter::HeaderMaterial (LumenPTModelConverter.h:85-137), 136 bytes
 MATERIAL = np.dtype([("color", "<f4", 4), ("emission", "<f4", 3), ("diffuse_texture", "<i4"), ("normal_texture", "<i4"), ("metallic_roughness_texture", "<i4"),
                      ("emissive_texture", "<i4"), ("transmission_texture", "<i4"), ("clear_coat_texture", "<i4"), ("clear_coat_roughness_texture", "<i4"), ("tint_texture", "<i4"),
                      ("transmission_factor", "<f4"), ("clear_coat_factor", "<f4"), ("clear_coat_roughness_factor", "<f4"), ("index_of_refraction", "<f4"),
@@ -77,7 +78,12 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         for name, path in FILES.items():
             out = os.path.join(tmp, name + ".bin")
-            subprocess.check_call([tool, path, out], stdout=subprocess.DEVNULL)
+            ollad = os.path.join(tmp, name + ".ollad")        # the reference's cache file itself (GenerateHeader + OutputToFile)
+            subprocess.check_call([tool, path, out, ollad], stdout=subprocess.DEVNULL)
+            data = open(ollad, "rb").read()
+            gold[f"{name}/ollad_sha256"] = np.array([hashlib.sha256(data).hexdigest(), str(len(data))])
+            if name == "cornell":
+                open(os.path.join(HERE, "cornell_reference.ollad"), "wb").write(data)
             mats, tex_types, prims, nodes, scenes = read_dump(out)
             gold[f"{name}/materials"] = mats
             gold[f"{name}/texture_types"] = tex_types

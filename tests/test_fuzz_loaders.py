@@ -39,6 +39,11 @@ def test_gltf_loader_survives_mutated_files(tmp_path):
     import test_gltf
     exe = _build(tmp_path, "fuzz_gltf", "lb_gltf.cpp")
     files = [test_gltf.build_test_document(str(tmp_path / "scene.gltf"), "embedded"), test_gltf.build_test_document(str(tmp_path / "scene.glb"), "glb")]
+    # the `.ollad` cache reader: the reference's own cache file of its Cornell box, and the cache of the synthetic document (images, names, hierarchy)
+    from lumenrenderer_b200.gltf import GltfDocument
+    with GltfDocument(files[1]) as doc:
+        doc.save_ollad(str(tmp_path / "scene.ollad"))
+    files += [os.path.join(GOLDEN, "cornell_reference.ollad"), str(tmp_path / "scene.ollad")]
     env = dict(os.environ, FUZZ_TMP=str(tmp_path))
     res = subprocess.run([exe, "700", "4711", *files], capture_output=True, text=True, timeout=600, env=env)
-    assert res.returncode == 0 and "fuzzed 1400 inputs" in res.stdout, (res.stdout[-500:], res.stderr[-3000:])
+    assert res.returncode == 0 and "fuzzed 2800 inputs" in res.stdout, (res.stdout[-500:], res.stderr[-3000:])

@@ -39,24 +39,25 @@ def build_test_document(path, flavour):
     for mesh in cb.meshes:                                    # Cornell geometry: no uvs, no tangents -> default-uv tangent generation
         meshes.append([{"positions": p["positions"], "normals": p["normals"], "indices": p["indices"], "material": p["material"]} for p in mesh])
     n_cornell = len(meshes)
-    textured = _quad((-0.6, 0.02, 0.4), (0.5, 0, 0), (0, 0.3, -0.3), 3, 2); textured["material"] = 4
-    degenerate = _quad((0.2, 0.02, 0.5), (0.4, 0, 0), (0, 0.25, -0.2), 1, 1); degenerate["uvs"][:] = 0.25; degenerate["material"] = 5      # collapsed uvs -> defaults
+    textured = _quad((-0.6, 0.02, 0.4), (0.5, 0, 0), (0, 0.3, -0.3), 3, 2); textured["material"] = 5
+    degenerate = _quad((0.2, 0.02, 0.5), (0.4, 0, 0), (0, 0.25, -0.2), 1, 1); degenerate["uvs"][:] = 0.25; degenerate["material"] = 4      # collapsed uvs -> defaults
     with_tangents = _quad((-0.9, 0.9, -0.9), (0.4, 0, 0), (0, 0.4, 0), 1, 1); with_tangents["tangents"] = np.tile(np.array([1, 0, 0, -1], F), (4, 1)); with_tangents["material"] = 6
-    bytes_idx = _quad((0.5, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); bytes_idx["index_type"] = np.uint8; bytes_idx["material"] = 5
-    wide_idx = _quad((-0.2, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); wide_idx["index_type"] = np.uint32; wide_idx["interleave_pos_normal"] = True; wide_idx["material"] = 4
+    bytes_idx = _quad((0.5, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); bytes_idx["index_type"] = np.uint8; bytes_idx["material"] = 4
+    wide_idx = _quad((-0.2, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); wide_idx["index_type"] = np.uint32; wide_idx["interleave_pos_normal"] = True; wide_idx["material"] = 5
     no_normals = _quad((0.0, 0.6, 0.2), (0.2, 0, 0), (0, 0.2, 0.05), 1, 1); del no_normals["normals"]; no_normals["material"] = None
-    jitter = _quad((0.0, 0.0, 0.0), (1, 0, 0), (0, 0, -1), 4, 4, 2.0); jitter["positions"][:, 1] += rng.random(25).astype(F) * F(0.05); jitter["material"] = 4
+    jitter = _quad((0.0, 0.0, 0.0), (1, 0, 0), (0, 0, -1), 4, 4, 2.0); jitter["positions"][:, 1] += rng.random(25).astype(F) * F(0.05); jitter["material"] = 5
     meshes += [[textured, degenerate], [with_tangents], [bytes_idx, wide_idx], [no_normals], [jitter]]
 
     def m(c):
         return {"pbrMetallicRoughness": {"baseColorFactor": [*c, 1.0], "metallicFactor": 0.0, "roughnessFactor": 1.0}}
     materials = [dict(m(c["diffuse_color"][:3]), emissiveFactor=list(c.get("emission", (0, 0, 0)))) for c in cb.materials]
-    materials.append({"name": "textured", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}, "roughnessFactor": 0.0},
-                      "normalTexture": {"index": 2}, "emissiveTexture": {"index": 0}, "emissiveFactor": [0.0, 0.0, 0.0]})
+    # 'disney' comes first: it gives images 0 and 1 the roles tint / transmission / clear coat, 'textured' then re-assigns them (the last role wins)
     materials.append({"name": "disney", "pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.6, 0.4, 1.0], "metallicFactor": 0.25, "roughnessFactor": 0.35},
                       "extensions": {"KHR_materials_transmission": {"transmissionFactor": 0.4, "transmissionTexture": {"index": 1}}, "KHR_materials_sheen": {"sheenRoughnessFactor": 0.3},
                                      "KHR_materials_ior": {"ior": 1.45}, "KHR_materials_clearcoat": {"clearcoatFactor": 0.7, "clearcoatRoughnessFactor": 0.2, "clearcoatTexture": {"index": 1}},
                                      "KHR_materials_specular": {"specularFactor": 0.6, "specularColorTexture": {"index": 0}}}})
+    materials.append({"name": "textured", "pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}, "roughnessFactor": 0.0},
+                      "normalTexture": {"index": 2}, "emissiveTexture": {"index": 0}, "emissiveFactor": [0.0, 0.0, 0.0]})
     materials.append({"name": "defaults"})
     tex = np.zeros((3, 16, 24, 4), np.uint8)
     tex[0] = rng.integers(0, 256, (16, 24, 4)); tex[0, ..., 3] = 255
@@ -268,6 +269,109 @@ def test_loader_matches_the_reference_converter(name):
         for i, (mesh, m) in enumerate(world):
             inst = doc.instance(i)
             assert inst["mesh"] == mesh and np.array_equal(inst["transform"].view(np.uint32), m.view(np.uint32)), f"instance {i}"
+
+
+@pytest.mark.parametrize("name", ["cornell", "sponza"])
+def test_ollad_is_the_reference_cache_file(name, tmp_path):
+    """lb_gltf_save_ollad writes, byte for byte, the `.ollad` cache the reference's converter (GenerateHeader + OutputToFile, run in place by
+    oracle/_ref/ref_gltf) writes for its own assets: Cornell against the committed file, Sponza (56.9 MB) against its SHA-256."""
+    if not os.path.exists(REF_ASSETS[name]):
+        pytest.skip("the reference's Sandbox assets are not on this machine")
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "gltf_reference_converter.npz"))
+    out = os.path.join(tmp_path, name + ".ollad")
+    with GltfDocument(REF_ASSETS[name]) as doc:
+        doc.save_ollad(out)
+    data = open(out, "rb").read()
+    assert [hashlib.sha256(data).hexdigest(), str(len(data))] == list(g[f"{name}/ollad_sha256"])
+    if name == "cornell":
+        assert data == open(os.path.join(GOLDEN, "cornell_reference.ollad"), "rb").read()
+
+
+def test_reading_the_reference_ollad(tmp_path):
+    """The `.ollad` file the REFERENCE wrote for its Cornell box (tests/golden/cornell_reference.ollad, made by make_golden_gltf_ref.py) read by
+    lb_gltf_open: the same document as the golden fixture of the glTF source, and saving it again reproduces the file."""
+    path = os.path.join(GOLDEN, "cornell_reference.ollad")
+    gold = golden_cornell()
+    with GltfDocument(path) as doc:
+        assert doc.info["triangles"] == 32 and doc.info["meshes"] == 8 and doc.info["images"] == 0 and doc.info["instances"] == 8 and doc.info["materials"] == 8
+        s = doc.to_scene_description()
+        again = os.path.join(tmp_path, "again.ollad"); doc.save_ollad(again)
+    assert open(again, "rb").read() == open(path, "rb").read()
+    for a, b in zip(s.meshes, gold.meshes):
+        for k in ("positions", "normals", "uvs", "tangents", "indices"):
+            assert np.array_equal(a[0][k], b[0][k]), k
+        assert a[0]["material"] == b[0]["material"]
+    assert len(s.instances) == len(gold.instances)
+    for a, b in zip(s.instances, gold.instances):
+        assert a["mesh"] == b["mesh"] and np.array_equal(a["transform"], b["transform"])
+    for a, b in zip(s.materials, gold.materials):
+        for k in ("diffuse_color", "emission", "metallic_factor", "roughness_factor"):
+            assert np.array_equal(np.asarray(a[k], F), np.asarray(b[k], F))
+
+
+@pytest.mark.parametrize("flavour", ["embedded", "glb"])
+def test_ollad_round_trip(tmp_path, flavour):
+    """glTF -> `.ollad` -> document: everything the renderer is fed (materials, decoded images and their colour space, vertex streams,
+    indices at their source width, instance matrices incl. the mesh-node quirk) survives bit for bit; the record layout is the
+    reference's (LumenPTModelConverter.h:79-186), walked here with struct."""
+    import struct
+    path = build_test_document(os.path.join(tmp_path, "scene.glb" if flavour == "glb" else "scene.gltf"), flavour)
+    ref = gt.load_reference_semantics(path)
+    cache = os.path.join(tmp_path, "scene.ollad")
+    with GltfDocument(path) as doc:
+        doc.save_ollad(cache)
+        images = [doc.image(i) for i in range(doc.info["images"])]
+        info = dict(doc.info)
+    with GltfDocument(cache) as doc:
+        assert doc.info == info
+        _compare(doc, ref)
+        for i, want in enumerate(images):
+            got = doc.image(i)
+            assert got["srgb"] == want["srgb"] == ref["srgb"][i] and got["decoded"] and np.array_equal(got["pixels"], want["pixels"])
+        again = os.path.join(tmp_path, "again.ollad"); doc.save_ollad(again)
+    b = open(cache, "rb").read()
+    assert open(again, "rb").read() == b
+    # header walk: u64 size | u64 nTex, (offset, size, type)[] | u64 nMat, 136-byte materials | u64 nMesh, { u32 nPrim, 40-byte primitives } | u64 nScenes ...
+    header_size, ntex = struct.unpack_from("<QQ", b, 0)
+    tex = np.frombuffer(b, "<u8", ntex * 3, 16).reshape(-1, 3)
+    assert list(tex[:, 2]) == ref["texture_types"] == [3, 4, 2]                # image 0: tint -> diffuse -> emissive, image 1: transmission, clear coat -> metal-roughness
+    blob = 8 + header_size
+    for off, size, _ in tex:
+        assert b[blob + off: blob + off + 8] == b"\x89PNG\r\n\x1a\n" and off + size <= len(b) - blob       # the encoded files, not pixels
+    at = 16 + 24 * ntex
+    nmat, = struct.unpack_from("<Q", b, at); at += 8 + 136 * nmat
+    assert nmat == len(ref["materials"])
+    nmesh, = struct.unpack_from("<Q", b, at); at += 8
+    widths = []
+    for mi in range(nmesh):
+        nprim, = struct.unpack_from("<I", b, at); at += 4
+        for pi in range(nprim):
+            vo, vs, io, isz, width, mat = struct.unpack_from("<4Q2I", b, at); at += 40
+            want = ref["meshes"][mi][pi]
+            v = np.frombuffer(b, "<f4", vs // 4, blob + vo).reshape(-1, 16)
+            assert np.array_equal(v[:, 0:3], want["positions"]) and np.array_equal(v[:, 4:6], want["uvs"]) and np.array_equal(v[:, 6:9], want["normals"])
+            assert np.array_equal(v[:, 12:16].view(np.uint32), want["tangents"].view(np.uint32)) and not v[:, [3, 9, 10, 11]].any()
+            idx = np.frombuffer(b, {1: "u1", 2: "<u2", 4: "<u4"}[width], isz // width, blob + io)
+            assert np.array_equal(idx, want["indices"]) and np.int32(np.uint32(mat)) == want["material"]
+            widths.append(width)
+    assert {1, 2, 4} <= set(widths)                                              # u8, u16 and u32 index buffers keep their width
+    nscenes, = struct.unpack_from("<Q", b, at)
+    assert nscenes == len(ref["doc"]["scenes"])
+
+
+def test_ollad_errors(tmp_path):
+    data = open(os.path.join(GOLDEN, "cornell_reference.ollad"), "rb").read()
+    bad = os.path.join(tmp_path, "bad.ollad")
+    for cut in (0, 7, 8, 100, 2500, len(data) - 1):
+        open(bad, "wb").write(data[:cut])
+        with pytest.raises(GltfError):
+            GltfDocument(bad)
+    open(bad, "wb").write(b"\xff" * 8 + data[8:])                               # header size beyond the file
+    with pytest.raises(GltfError):
+        GltfDocument(bad)
+    with GltfDocument(os.path.join(GOLDEN, "cornell_reference.ollad")) as doc, pytest.raises(GltfError):
+        doc.save_ollad(os.path.join(tmp_path, "no_such_directory", "x.ollad"))
 
 
 @pytest.mark.gpu
