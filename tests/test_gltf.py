@@ -420,3 +420,24 @@ def test_uploaded_document_renders_like_the_restatement(oracle, tmp_path):
         assert np.array_equal(g.read_surface(), c.read_surface())
         assert rel_l1(g.read_hdr()[..., :3], c.read_hdr()[..., :3]) < 1e-3
         assert g.frame_counters()["triangles"] == doc.info["triangles"]
+
+
+@pytest.mark.gpu
+def test_ollad_upload_renders_like_the_gltf(tmp_path):
+    """The same document uploaded from its glTF source and from the `.ollad` cache written from it: identical frames, bit for bit."""
+    path = build_test_document(os.path.join(tmp_path, "scene.glb"), "glb")
+    cache = os.path.join(tmp_path, "scene.ollad")
+    st = lr.Settings(width=200, height=150, depth=3, restir=True)
+    cam = scenes.cornell_box().camera
+    frames = []
+    with GltfDocument(path) as doc:
+        doc.save_ollad(cache)
+    for source in (path, cache):
+        with lr.Renderer(st) as g, GltfDocument(source) as doc:
+            first, count = doc.upload(g)
+            assert first == 0 and count == doc.info["instances"]
+            g.set_camera(cam["position"], cam["rotation"])
+            g.render_frames(2)
+            frames.append((g.read_hdr().copy(), g.read_surface(), g.frame_counters()["triangles"]))
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1]) and frames[0][2] == frames[1][2] > 0
+    assert frames[0][0][..., :3].max() > 0
