@@ -147,12 +147,18 @@ void floor_roughness(LbGltfOpaque& g) {
 }
 // LoadNode (:275-317): a mesh node's instance transform is parented to the enclosing node's transform, but the children of a MESH node
 // are parented to that node's own (unparented) transform. `parent_world`: world matrix of the parent node's transform object.
+// A ROOT mesh node's instance keeps an IDENTITY world matrix: `m->m_Transform = node->m_Transform` (:293) is Transform::operator=
+// (LM/ModelLoading/Transform.cpp:58-75), which copies the local matrix and a clean dirty flag but not the world matrix, and only
+// AddChild (:298-299, parented nodes) raises the flag again. This is what the reference renders (its Sponza, one root mesh node with
+// scale 0.008, appears unscaled; Sandbox/src/Application.cpp:146 places the camera accordingly) and what running the reference's own
+// LoadFile shows (tests/test_adapter.py::test_reference_ollad_loader_over_the_adapter_cpu).
 void flatten_node(LbGltfOpaque& g, const Node& n, const Mat4* parent_world) {
     const Mat4 with_parent = parent_world ? mat_mul(*parent_world, n.local) : n.local;
     Mat4 own_world;
     if (n.mesh >= 0) {
         Instance in; in.mesh = (uint32_t)n.mesh;
-        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) in.m[r * 4 + c] = with_parent.m[c * 4 + r];
+        const Mat4 shown = parent_world ? with_parent : mat_identity();
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) in.m[r * 4 + c] = shown.m[c * 4 + r];
         g.instances.push_back(in);
         own_world = n.local;
     } else own_world = with_parent;

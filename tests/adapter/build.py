@@ -42,8 +42,9 @@ def build(force: bool = False) -> dict:
     """Returns {"oracle": path, "b200": path}. Rebuilds when a source is newer than the executables."""
     sys.path.insert(0, ROOT)
     from lumenrenderer_b200.api import C_ABI_SYMBOLS
-    exes = {"oracle": os.path.join(OUT, "adapter_driver_oracle"), "b200": os.path.join(OUT, "adapter_driver_b200")}
-    srcs = [os.path.join(HERE, "adapter_driver.cpp"), os.path.join(ROOT, "include", "lumen_b200_adapter.hpp"), os.path.join(ROOT, "include", "lumen_b200.h"),
+    exes = {"oracle": os.path.join(OUT, "adapter_driver_oracle"), "b200": os.path.join(OUT, "adapter_driver_b200"),
+            "ollad_oracle": os.path.join(OUT, "ollad_driver_oracle"), "ollad_b200": os.path.join(OUT, "ollad_driver_b200")}
+    srcs = [os.path.join(HERE, "adapter_driver.cpp"), os.path.join(HERE, "ollad_driver.cpp"), os.path.join(ROOT, "include", "lumen_b200_adapter.hpp"), os.path.join(ROOT, "include", "lumen_b200.h"),
             os.path.join(ROOT, "lumenrenderer_b200", "csrc", "lb_nanovdb.cpp"), __file__]
     if not force and all(os.path.exists(e) and os.path.getmtime(e) > max(os.path.getmtime(s) for s in srcs) for e in exes.values()):
         return exes
@@ -54,7 +55,8 @@ def build(force: bool = False) -> dict:
         open(os.path.join(ov, "Windows.h"), "w").write("/* stub */\n")
         open(os.path.join(ov, "Glad", "glad.h"), "w").write("#include <glad/glad.h>\n")
         hdr = open(os.path.join(REF, "Lumen/src/Lumen/Renderer/LumenRenderer.h")).read()
-        patched, n = re.subn(r"CreateScene\(SceneData a_SceneData = \{\}\)", "CreateScene(SceneData a_SceneData)", hdr)
+        # ... and an overload for the reference's own argument-less calls (LumenPTModelConverter::LoadFile), defined in ollad_driver.cpp
+        patched, n = re.subn(r"CreateScene\(SceneData a_SceneData = \{\}\);", "CreateScene(SceneData a_SceneData); std::shared_ptr<Lumen::ILumenScene> CreateScene();", hdr)
         assert n == 1, "LumenRenderer.h changed: CreateScene default argument not found"
         open(os.path.join(ov, "Lumen", "Renderer", "LumenRenderer.h"), "w").write(patched)
         shutil.copy(os.path.join(REF, "Lumen/src/Lumen/Renderer/LumenRenderer.cpp"), os.path.join(ov, "Lumen", "Renderer", "LumenRenderer.cpp"))
@@ -83,6 +85,12 @@ def build(force: bool = False) -> dict:
                 _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", *extra, "-c", os.path.join(ROOT, "lumenrenderer_b200", "csrc", "lb_nanovdb.cpp"), "-o", more[0]])
             rel = os.path.relpath(libdir, OUT)
             _run(["g++", obj, *more, *objs, "-o", exes[kind], f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,$ORIGIN/{rel}", "-lpthread"])
+            # the reference's own `.ollad` loader (LumenPTModelConverter.cpp + stb_image, in place) in front of the adapter
+            obj = os.path.join(tmp, f"ollad_{kind}.o")
+            os.makedirs(os.path.join(ov, "Renderer"), exist_ok=True)          # the converter spells the include "Renderer/LumenRenderer.h"
+            open(os.path.join(ov, "Renderer", "LumenRenderer.h"), "w").write('#include "../Lumen/Renderer/LumenRenderer.h"\n')
+            _run(["g++", *flags, f"-I{REF}/Lumen/src/Lumen/ModelLoading", f"-I{REF}/Lumen", "-fpermissive", "-DSTB_IMAGE_IMPLEMENTATION", "-include", "cstring", *extra, "-c", os.path.join(HERE, "ollad_driver.cpp"), "-o", obj])
+            _run(["g++", obj, *more, *objs, "-o", exes["ollad_" + kind], f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,$ORIGIN/{rel}", "-lpthread"])
     return exes
 
 

@@ -298,7 +298,10 @@ def load_reference_semantics(path):
         local = _node_local(n)
         with_parent = _mat_mul(parent_world, local) if parent_world is not None else local
         if "mesh" in n:
-            instances.append({"mesh": n["mesh"], "transform": with_parent.T.copy()})      # row-major
+            # a ROOT mesh node's instance keeps an identity world matrix: Transform::operator= (Transform.cpp:58-75) copies the local matrix
+            # and a clean dirty flag but not the world matrix; only AddChild (parented nodes) raises the flag again
+            shown = with_parent if parent_world is not None else np.eye(4, dtype=F)
+            instances.append({"mesh": n["mesh"], "transform": shown.T.copy()})      # row-major
             own = local                                                                       # :296-306 quirk
         else:
             own = with_parent

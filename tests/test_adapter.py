@@ -158,3 +158,78 @@ def test_adapter_over_reference_interface_gpu(gpu, tmp_path):
         pytest.skip("tests/adapter/_build/adapter_driver_b200 was not prebuilt (needs /root/reference at build time)")
     run_case(exe, gpu, tmp_path, moved_cornell(), 96, 64, 3, True, 2, True)
     run_case(exe, gpu, tmp_path, room_with_nanovdb_volume(), 96, 64, 3, False, 2, False)
+
+
+def run_ollad_case(exe, bindings, tmp_path, cache, width, height, depth, restir, frames, exact_worlds=True):
+    """The reference's own LumenPTModelConverter::LoadFile (tests/adapter/ollad_driver.cpp) in front of the adapter, against the same
+    `.ollad` file opened by lb_gltf_open and uploaded by lb_gltf_upload through the plain C ABI."""
+    from lumenrenderer_b200.gltf import GltfDocument
+    out = str(tmp_path / "ollad_out")
+    cam = scenes.cornell_box().camera
+    args = [str(v) for v in (width, height, depth, int(restir), frames, *cam["position"], *cam["rotation"])]
+    res = subprocess.run([exe, cache, out, *args], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    worlds = np.fromfile(out + ".worlds", np.float32).reshape(-1, 4, 4)
+    hdr = np.fromfile(out + ".hdr", np.float32).reshape(height, width, 4)
+    ldr = np.fromfile(out + ".ldr", np.uint8).reshape(height, width, 4)
+    with GltfDocument(cache) as doc, api.Renderer(bindings, api.Settings(width=width, height=height, depth=depth, restir=restir)) as r:
+        info = doc.info
+        assert f"loaded {info['materials']} materials {info['meshes']} meshes {info['instances']} instances, resolution {width}x{height}" in res.stdout, res.stdout
+        assert len(worlds) == info["instances"] + 1
+        # the node table through the reference's Transform hierarchy (LoadNode :275-317, Transform::AddChild / GetWorldTransformationMatrix)
+        # against lb_gltf_instance: the mesh-node quirk included
+        for i in range(info["instances"]):
+            t = doc.instance(i)["transform"]
+            if exact_worlds:
+                assert np.array_equal(t.view(np.uint32), worlds[i].view(np.uint32)), f"instance {i}"
+            else:
+                assert np.allclose(t, worlds[i], rtol=0, atol=2e-6 * max(1.0, np.abs(t).max())), f"instance {i}"
+        if bindings.prefix == "lb_":
+            doc.upload(r)
+        else:                                    # lb_gltf_upload is product code; the oracle gets the same document call by call
+            r.load_scene(doc.to_scene_description())
+        for k in range(info["instances"]):
+            r.set_instance_transform(k, worlds[k])
+        r.set_camera_matrix(worlds[-1])
+        r.render_frames(frames)
+        ref_hdr, ref_ldr = r.read_hdr(), np.asarray(r.read_ldr()).reshape(ldr.shape)
+    assert np.isfinite(hdr).all() and hdr[..., :3].sum() > 0
+    return hdr, ref_hdr, ldr, ref_ldr
+
+
+@pytest.mark.skipif(not adapter_build.available(), reason="needs the reference tree (/root/reference) to compile against")
+@pytest.mark.parametrize("case", ["reference_cornell_cache", "textured_hierarchy"])
+def test_reference_ollad_loader_over_the_adapter_cpu(oracle, tmp_path, case):
+    exe = adapter_build.build()["ollad_oracle"]
+    if case == "reference_cornell_cache":
+        cache = os.path.join(ROOT, "tests", "golden", "cornell_reference.ollad")
+        hdr, ref_hdr, ldr, ref_ldr = run_ollad_case(exe, oracle, tmp_path, cache, 48, 40, 3, False, 1)
+    else:
+        import test_gltf
+        from lumenrenderer_b200.gltf import GltfDocument
+        src = test_gltf.build_test_document(str(tmp_path / "scene.glb"), "glb", reference_safe=True)
+        cache = str(tmp_path / "scene.ollad")
+        with GltfDocument(src) as doc:
+            doc.save_ollad(cache)
+        # parented, rotated and scaled nodes: the reference's Transform decomposes every matrix it is given and recomposes it (1 ulp apart)
+        hdr, ref_hdr, ldr, ref_ldr = run_ollad_case(exe, oracle, tmp_path, cache, 48, 36, 3, True, 2, exact_worlds=False)
+    assert np.array_equal(hdr, ref_hdr), f"reference loader + adapter and lb_gltf differ: {np.abs(hdr - ref_hdr).max()}"
+    assert np.array_equal(ldr, ref_ldr)
+
+
+@pytest.mark.gpu
+def test_reference_ollad_loader_over_the_adapter_gpu(gpu, tmp_path):
+    """The reference's LoadFile (prebuilt here against liblumen_b200.so) in front of the GPU renderer vs lb_gltf_open + lb_gltf_upload."""
+    exe = os.path.join(ROOT, "tests", "adapter", "_build", "ollad_driver_b200")
+    if not os.path.exists(exe):
+        pytest.skip("tests/adapter/_build/ollad_driver_b200 was not prebuilt (needs /root/reference at build time)")
+    import test_gltf
+    from lumenrenderer_b200.gltf import GltfDocument
+    hdr, ref_hdr, ldr, ref_ldr = run_ollad_case(exe, gpu, tmp_path, os.path.join(ROOT, "tests", "golden", "cornell_reference.ollad"), 96, 64, 3, False, 1)
+    assert np.array_equal(hdr, ref_hdr) and np.array_equal(ldr, ref_ldr)
+    src = test_gltf.build_test_document(str(tmp_path / "scene.glb"), "glb", reference_safe=True)
+    cache = str(tmp_path / "scene.ollad")
+    with GltfDocument(src) as doc:
+        doc.save_ollad(cache)
+    hdr, ref_hdr, ldr, ref_ldr = run_ollad_case(exe, gpu, tmp_path, cache, 96, 64, 3, True, 2, exact_worlds=False)
+    assert np.array_equal(hdr, ref_hdr) and np.array_equal(ldr, ref_ldr)

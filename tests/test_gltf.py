@@ -32,7 +32,10 @@ def _quad(origin, eu, ev, nu=2, nv=2, uv_scale=1.0):
     return {"positions": np.array(pos, F), "normals": np.tile(n.astype(F), (len(pos), 1)), "uvs": np.array(uv, F), "indices": np.array(idx)}
 
 
-def build_test_document(path, flavour):
+def build_test_document(path, flavour, reference_safe=False):
+    """reference_safe: without the two things the reference's own LoadFile / CreatePrimitive cannot take — a primitive with the glTF default
+    material (LoadFile indexes its pool with -1, :218) and 8-bit indices (CreatePrimitive reads every non-32-bit buffer as 16 bit,
+    WaveFrontRenderer.cpp:1161-1169)."""
     rng = np.random.default_rng(7)
     cb = scenes.cornell_box()
     meshes = []
@@ -42,9 +45,9 @@ def build_test_document(path, flavour):
     textured = _quad((-0.6, 0.02, 0.4), (0.5, 0, 0), (0, 0.3, -0.3), 3, 2); textured["material"] = 5
     degenerate = _quad((0.2, 0.02, 0.5), (0.4, 0, 0), (0, 0.25, -0.2), 1, 1); degenerate["uvs"][:] = 0.25; degenerate["material"] = 4      # collapsed uvs -> defaults
     with_tangents = _quad((-0.9, 0.9, -0.9), (0.4, 0, 0), (0, 0.4, 0), 1, 1); with_tangents["tangents"] = np.tile(np.array([1, 0, 0, -1], F), (4, 1)); with_tangents["material"] = 6
-    bytes_idx = _quad((0.5, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); bytes_idx["index_type"] = np.uint8; bytes_idx["material"] = 4
+    bytes_idx = _quad((0.5, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); bytes_idx["index_type"] = np.uint16 if reference_safe else np.uint8; bytes_idx["material"] = 4
     wide_idx = _quad((-0.2, 1.2, -0.95), (0.3, 0, 0), (0, 0.3, 0), 2, 2); wide_idx["index_type"] = np.uint32; wide_idx["interleave_pos_normal"] = True; wide_idx["material"] = 5
-    no_normals = _quad((0.0, 0.6, 0.2), (0.2, 0, 0), (0, 0.2, 0.05), 1, 1); del no_normals["normals"]; no_normals["material"] = None
+    no_normals = _quad((0.0, 0.6, 0.2), (0.2, 0, 0), (0, 0.2, 0.05), 1, 1); del no_normals["normals"]; no_normals["material"] = 6 if reference_safe else None
     jitter = _quad((0.0, 0.0, 0.0), (1, 0, 0), (0, 0, -1), 4, 4, 2.0); jitter["positions"][:, 1] += rng.random(25).astype(F) * F(0.05); jitter["material"] = 5
     meshes += [[textured, degenerate], [with_tangents], [bytes_idx, wide_idx], [no_normals], [jitter]]
 
@@ -256,8 +259,8 @@ def test_loader_matches_the_reference_converter(name):
             assert np.array_equal(gt._node_local(n).view(np.uint32), local.view(np.uint32)), f"node {i}"
             assert tuple(g[f"{name}/node_mesh_children"][row]) == (n.get("mesh", -1), len(n.get("children", [])))
             with_parent = gt._mat_mul(parent, local) if parent is not None else local
-            if "mesh" in n:
-                world.append((n["mesh"], with_parent.T.copy()))
+            if "mesh" in n:                                   # a root mesh node's instance keeps an identity world matrix (Transform.cpp:58-75)
+                world.append((n["mesh"], (with_parent if parent is not None else np.eye(4, dtype=F)).T.copy()))
             for c in n.get("children", []):
                 visit(c, local if "mesh" in n else with_parent)
         scenes_ = ref["doc"]["scenes"]
