@@ -115,6 +115,9 @@ private:
         const std::string tok(s, p_);
         char* e = nullptr; v.num = strtod(tok.c_str(), &e);
         if (e != tok.c_str() + tok.size()) err("bad number");
+        // an INTEGER token is an integer in nlohmann-json (which the reference's fx-gltf reads with): "-0" is the integer 0 and becomes +0.0f,
+        // "-0.0" keeps its sign. Exporters write both (the reference's skycastle asset holds 1 659 "-0" matrix elements).
+        if (v.num == 0.0 && tok.find_first_of(".eE") == std::string::npos) v.num = 0.0;
         v.kind = Value::Number;
         return v;
     }

@@ -2,7 +2,7 @@
 oracle/Makefile -> oracle/_ref/ref_gltf; needs /root/reference, so this runs in the build container only) for the two glTF assets the
 reference ships: Sandbox/assets/models/CornellBox/scene.gltf (stored completely, 7 KB) and Sponza/Sponza.gltf (262 267 triangles: the
 material table and node table completely, every vertex stream and index buffer as a SHA-256). Also the `.ollad` cache file the reference writes for each (Cornell: the file itself, tests/golden/cornell_reference.ollad, 7 KB;
-Sponza: its SHA-256 and size). Writes tests/golden/gltf_reference_converter.npz."""
+Sponza: its SHA-256 and size), and the SHA-256 of the cache file of EVERY glTF / GLB asset under Sandbox/assets/models. Writes tests/golden/gltf_reference_converter.npz."""
 import hashlib
 import os
 import struct
@@ -97,6 +97,22 @@ def main():
             if name == "cornell":
                 for k, p in enumerate(prims):
                     gold[f"cornell/vertices{k}"] = p["vertices"]; gold[f"cornell/indices{k}"] = p["indices"]
+        # every glTF / GLB asset the reference ships (29 files, 186 MB of caches): SHA-256 and size of the cache file its converter writes;
+        # an empty hash where the reference's converter does not survive the file (Draco-compressed variants, a truncated sample)
+        table = []
+        for dirpath, _, files in sorted(os.walk(ASSETS)):
+            for f in sorted(files):
+                if not f.endswith((".gltf", ".glb")):
+                    continue
+                path = os.path.join(dirpath, f); ollad = os.path.join(tmp, "any.ollad")
+                try:
+                    ok = subprocess.run([tool, path, os.path.join(tmp, "any.bin"), ollad], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600).returncode == 0
+                except subprocess.TimeoutExpired:
+                    ok = False
+                data = open(ollad, "rb").read() if ok else b""
+                table.append([os.path.relpath(path, ASSETS), hashlib.sha256(data).hexdigest() if ok else "", str(len(data))])
+                print(table[-1])
+        gold["assets/ollad_sha256"] = np.array(table)
     np.savez_compressed(os.path.join(HERE, "gltf_reference_converter.npz"), **gold)
     print("wrote", os.path.join(HERE, "gltf_reference_converter.npz"))
 
