@@ -119,7 +119,7 @@ inline std::vector<uint8_t> encode_rgba8(const uint8_t* rgba8, uint32_t w, uint3
 
 
 // ---------------------------------------------------------------- decoding (glTF ingest: the reference decodes with stbi_load_from_memory(..., 4),
-// LumenPT/src/Tools/LumenPTModelConverter.cpp:121). Non-interlaced PNG of bit depth 8 or 16, every colour type; output RGBA8.
+// LumenPT/src/Tools/LumenPTModelConverter.cpp:121). Non-interlaced PNG of every bit depth (1, 2, 4, 8, 16) and colour type, palette and colour-key transparency; output RGBA8.
 struct BitReader {
     const uint8_t* p; size_t n, pos = 0; uint64_t acc = 0; int bits = 0;
     BitReader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
@@ -216,7 +216,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, siz
     return true;
 }
 inline bool is_png(const uint8_t* p, size_t n) { static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A}; return n >= 8 && memcmp(p, sig, 8) == 0; }
-// false = not a PNG this decoder handles (interlaced, bit depth < 8, damaged)
+// false = not a PNG this decoder handles (interlaced, damaged)
 inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rgba, uint32_t& w, uint32_t& h) {
     if (!is_png(file, n)) return false;
     size_t pos = 8; std::vector<uint8_t> idat, plte, trns; int depth = 0, colour = 0, lace = 0; w = h = 0;
@@ -231,11 +231,12 @@ inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rg
         else if (!memcmp(type, "IEND", 4)) break;
         pos += 12 + (size_t)len;
     }
-    if (!w || !h || lace || (depth != 8 && depth != 16)) return false;
+    if (!w || !h || lace || (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16)) return false;
     if (w > 65536u || h > 65536u || (uint64_t)w * h > ((uint64_t)1 << 28)) return false;      // a corrupt header must not turn into a giant allocation
     const int channels = colour == 0 ? 1 : colour == 2 ? 3 : colour == 3 ? 1 : colour == 4 ? 2 : colour == 6 ? 4 : 0;
-    if (!channels || (colour == 3 && depth != 8)) return false;
-    const size_t bpp = (size_t)channels * (depth / 8), stride = bpp * w;
+    if (!channels || (colour == 3 && depth == 16) || (depth < 8 && colour != 0 && colour != 3)) return false;
+    // sub-byte samples (grey and palette images of depth 1, 2, 4): rows are bit-packed, the filters work on whole bytes
+    const size_t bits = (size_t)channels * depth, bpp = bits >= 8 ? bits / 8 : 1, stride = ((size_t)w * bits + 7) / 8;
     std::vector<uint8_t> raw; raw.reserve((stride + 1) * h);
     if (!inflate(idat.data(), idat.size(), raw, (stride + 1) * (size_t)h) || raw.size() < (stride + 1) * h) return false;
     std::vector<uint8_t> img(stride * h);
@@ -252,12 +253,26 @@ inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rg
         }
     }
     rgba.resize((size_t)w * h * 4);
-    const size_t step = depth / 8;                            // 16-bit samples: the high byte (what stb's 8-bit interface returns)
-    for (size_t i = 0; i < (size_t)w * h; ++i) {
-        const uint8_t* s = img.data() + i * bpp; uint8_t* d = rgba.data() + i * 4;
+    const size_t step = depth == 16 ? 2 : 1;                  // 16-bit samples: the high byte (what stb's 8-bit interface returns)
+    // tRNS of a grey / RGB image is a colour key (stb_image: stbi__compute_transparency on the 8-bit samples — sub-byte grey after scaling —
+    // and stbi__compute_transparency16 on the 16-bit ones)
+    static const int scale_of_depth[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
+    const bool keyed = (colour == 0 && trns.size() >= 2) || (colour == 2 && trns.size() >= 6);
+    uint32_t key[3] = {0, 0, 0};
+    if (keyed) for (int k = 0; k < (colour == 0 ? 1 : 3); ++k) {
+        const uint32_t v16 = ((uint32_t)trns[2 * k] << 8) | trns[2 * k + 1];
+        key[k] = depth == 16 ? v16 : (v16 & 255u) * (uint32_t)scale_of_depth[depth];
+    }
+    for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x) {
+        const uint8_t* row = img.data() + (size_t)y * stride; uint8_t* d = rgba.data() + ((size_t)y * w + x) * 4;
+        uint8_t sub = 0;
+        if (depth < 8) { const size_t bit = (size_t)x * depth; sub = (uint8_t)((row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1)); }
+        const uint8_t* s = depth < 8 ? &sub : row + (size_t)x * bpp;
+        auto full = [&](int c) { return depth == 16 ? ((uint32_t)s[2 * c] << 8) | s[2 * c + 1] : (uint32_t)s[c]; };
         switch (colour) {
-            case 0: d[0] = d[1] = d[2] = s[0]; d[3] = 255; break;
-            case 2: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = 255; break;
+            case 0: { const uint8_t g = depth < 8 ? (uint8_t)(sub * scale_of_depth[depth]) : s[0]; d[0] = d[1] = d[2] = g;
+                      d[3] = keyed && (depth == 16 ? full(0) : (uint32_t)g) == key[0] ? 0 : 255; break; }
+            case 2: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = keyed && full(0) == key[0] && full(1) == key[1] && full(2) == key[2] ? 0 : 255; break;
             case 3: { const size_t k = s[0]; d[0] = 3 * k + 2 < plte.size() ? plte[3 * k] : 0; d[1] = 3 * k + 2 < plte.size() ? plte[3 * k + 1] : 0; d[2] = 3 * k + 2 < plte.size() ? plte[3 * k + 2] : 0; d[3] = k < trns.size() ? trns[k] : 255; break; }
             case 4: d[0] = d[1] = d[2] = s[0]; d[3] = s[step]; break;
             default: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = s[3 * step]; break;

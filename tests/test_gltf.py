@@ -500,3 +500,45 @@ def test_ollad_upload_renders_like_the_gltf(tmp_path):
             frames.append((g.read_hdr().copy(), g.read_surface(), g.frame_counters()["triangles"]))
     assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1]) and frames[0][2] == frames[1][2] > 0
     assert frames[0][0][..., :3].max() > 0
+
+
+def test_png_decoder_matches_stb_image_on_every_shipped_png(tmp_path):
+    """csrc/lb_png.h against the stb_image the reference decodes its textures with (compiled in place -> oracle/_ref/ref_stb; table in
+    tests/golden/png_reference.npz, made by tests/golden/make_golden_png.py): all 67 PNG files under the reference's Sandbox/assets/models —
+    RGB, RGBA and palette images of depth 1, 2, 4 and 8 up to 2048 x 2048 — decode to the same RGBA8 pixels (SHA-256)."""
+    import hashlib
+    root = os.path.dirname(os.path.dirname(REF_CORNELL))
+    if not os.path.isdir(root):
+        pytest.skip("the reference's Sandbox assets are not on this machine")
+    table = np.load(os.path.join(GOLDEN, "png_reference.npz"))["table"]
+    assert len(table) == 67 and {(int(r[3]), int(r[4])) for r in table} >= {(8, 2), (8, 6), (8, 3), (4, 3), (2, 3), (1, 3)}
+    seen = set()
+    for k, (rel, w, h, depth, colour, sha) in enumerate(table):
+        if sha in seen:                                          # the asset variants share most textures
+            continue
+        seen.add(sha)
+        link = os.path.join(tmp_path, f"img{k}.png"); os.symlink(os.path.join(root, rel), link)
+        path = os.path.join(tmp_path, f"doc{k}.gltf")
+        open(path, "w").write('{"asset": {"version": "2.0"}, "images": [{"uri": "img%d.png"}]}' % k)
+        with GltfDocument(path) as doc:
+            im = doc.image(0)
+        assert im["decoded"], f"{rel} (depth {depth}, colour type {colour}) was not decoded"
+        assert im["pixels"].shape == (int(h), int(w), 4) and hashlib.sha256(im["pixels"].tobytes()).hexdigest() == sha, rel
+    assert len(seen) >= 30
+
+
+def test_png_decoder_corner_cases_against_stb_image(tmp_path):
+    """21 small synthetic PNG files (tests/golden/png_cases.npz, made by tests/golden/make_golden_png_cases.py) with the pixels the reference's
+    stb_image decodes them to: grey images of depth 1 / 2 / 4 / 8 / 16 with and without a tRNS colour key, RGB 8 / 16 with a colour key,
+    grey + alpha, RGBA, palette images of depth 1 / 2 / 4 / 8 with per-entry alpha, random row filters, IDAT split in two. Needs no reference tree."""
+    g = np.load(os.path.join(GOLDEN, "png_cases.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 21
+    for name in names:
+        open(os.path.join(tmp_path, name + ".png"), "wb").write(g[name + "/file"].tobytes())
+        path = os.path.join(tmp_path, name + ".gltf")
+        open(path, "w").write('{"asset": {"version": "2.0"}, "images": [{"uri": "%s.png"}]}' % name)
+        with GltfDocument(path) as doc:
+            im = doc.image(0)
+        assert im["decoded"], name
+        assert np.array_equal(im["pixels"], g[name + "/rgba"]), name
