@@ -119,7 +119,7 @@ inline std::vector<uint8_t> encode_rgba8(const uint8_t* rgba8, uint32_t w, uint3
 
 
 // ---------------------------------------------------------------- decoding (glTF ingest: the reference decodes with stbi_load_from_memory(..., 4),
-// LumenPT/src/Tools/LumenPTModelConverter.cpp:121). Non-interlaced PNG of every bit depth (1, 2, 4, 8, 16) and colour type, palette and colour-key transparency; output RGBA8.
+// LumenPT/src/Tools/LumenPTModelConverter.cpp:121). PNG (plain or Adam7-interlaced) of every bit depth (1, 2, 4, 8, 16) and colour type, palette and colour-key transparency; output RGBA8.
 struct BitReader {
     const uint8_t* p; size_t n, pos = 0; uint64_t acc = 0; int bits = 0;
     BitReader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
@@ -216,7 +216,27 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, siz
     return true;
 }
 inline bool is_png(const uint8_t* p, size_t n) { static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A}; return n >= 8 && memcmp(p, sig, 8) == 0; }
-// false = not a PNG this decoder handles (interlaced, damaged)
+// reverses the row filters of one (sub-)image: `in` = h rows of (filter byte + stride bytes), `out` = h rows of stride bytes
+inline bool unfilter(const uint8_t* in, uint8_t* out, size_t stride, uint32_t h, size_t bpp) {
+    for (uint32_t y = 0; y < h; ++y) {
+        const int f = in[0]; ++in;
+        uint8_t* row = out + (size_t)y * stride; const uint8_t* up = y ? row - stride : nullptr;
+        if (f < 0 || f > 4) return false;
+        for (size_t x = 0; x < stride; ++x) {
+            const int a = x >= bpp ? row[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+            int pred = 0;
+            if (f == 1) pred = a; else if (f == 2) pred = b; else if (f == 3) pred = (a + b) >> 1;
+            else if (f == 4) { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+            row[x] = (uint8_t)(in[x] + pred);
+        }
+        in += stride;
+    }
+    return true;
+}
+// false = not a PNG this decoder handles (damaged)
+#if defined(__GNUC__) && !defined(__clang__)
+__attribute__((optimize("no-tree-slp-vectorize")))            // g++ 13.3 -O2 dies in its SLP vectoriser on this function (compute_live_loop_exits)
+#endif
 inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rgba, uint32_t& w, uint32_t& h) {
     if (!is_png(file, n)) return false;
     size_t pos = 8; std::vector<uint8_t> idat, plte, trns; int depth = 0, colour = 0, lace = 0; w = h = 0;
@@ -231,26 +251,31 @@ inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rg
         else if (!memcmp(type, "IEND", 4)) break;
         pos += 12 + (size_t)len;
     }
-    if (!w || !h || lace || (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16)) return false;
+    if (!w || !h || lace > 1 || (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16)) return false;
     if (w > 65536u || h > 65536u || (uint64_t)w * h > ((uint64_t)1 << 28)) return false;      // a corrupt header must not turn into a giant allocation
     const int channels = colour == 0 ? 1 : colour == 2 ? 3 : colour == 3 ? 1 : colour == 4 ? 2 : colour == 6 ? 4 : 0;
     if (!channels || (colour == 3 && depth == 16) || (depth < 8 && colour != 0 && colour != 3)) return false;
     // sub-byte samples (grey and palette images of depth 1, 2, 4): rows are bit-packed, the filters work on whole bytes
-    const size_t bits = (size_t)channels * depth, bpp = bits >= 8 ? bits / 8 : 1, stride = ((size_t)w * bits + 7) / 8;
-    std::vector<uint8_t> raw; raw.reserve((stride + 1) * h);
-    if (!inflate(idat.data(), idat.size(), raw, (stride + 1) * (size_t)h) || raw.size() < (stride + 1) * h) return false;
-    std::vector<uint8_t> img(stride * h);
-    for (uint32_t y = 0; y < h; ++y) {
-        const uint8_t* in = raw.data() + (size_t)y * (stride + 1); const int f = in[0]; ++in;
-        uint8_t* row = img.data() + (size_t)y * stride; const uint8_t* up = y ? row - stride : nullptr;
-        for (size_t x = 0; x < stride; ++x) {
-            const int a = x >= bpp ? row[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
-            int pred = 0;
-            if (f == 1) pred = a; else if (f == 2) pred = b; else if (f == 3) pred = (a + b) >> 1;
-            else if (f == 4) { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
-            else if (f != 0) return false;
-            row[x] = (uint8_t)(in[x] + pred);
-        }
+    const size_t bits = (size_t)channels * depth, bpp = bits >= 8 ? bits / 8 : 1;
+    // passes: one for a plain image, the seven Adam7 sub-images (each filtered on its own) for an interlaced one
+    static const uint32_t x0[7] = {0, 4, 0, 2, 0, 1, 0}, y0[7] = {0, 0, 4, 0, 2, 0, 1}, dx[7] = {8, 8, 4, 4, 2, 2, 1}, dy[7] = {8, 8, 8, 4, 4, 2, 2};
+    struct Pass { uint32_t x0, y0, dx, dy, w, h; size_t stride, at; };
+    std::vector<Pass> passes; size_t total = 0, plain = 0;
+    for (int k = 0; k < (lace ? 7 : 1); ++k) {
+        Pass q = lace ? Pass{x0[k], y0[k], dx[k], dy[k], (w - x0[k] + dx[k] - 1) / dx[k], (h - y0[k] + dy[k] - 1) / dy[k], 0, 0} : Pass{0, 0, 1, 1, w, h, 0, 0};
+        if (!q.w || !q.h) continue;
+        q.stride = ((size_t)q.w * bits + 7) / 8; q.at = plain;
+        total += (q.stride + 1) * q.h; plain += q.stride * q.h;
+        passes.push_back(q);
+    }
+    std::vector<uint8_t> raw; raw.reserve(total);
+    if (!inflate(idat.data(), idat.size(), raw, total) || raw.size() < total) return false;
+    std::vector<uint8_t> img(plain);
+    const uint8_t* in = raw.data();
+    for (size_t k = 0; k < passes.size(); ++k) {
+        const Pass& q = passes[k];
+        if (!unfilter(in, img.data() + q.at, q.stride, q.h, bpp)) return false;
+        in += (q.stride + 1) * q.h;
     }
     rgba.resize((size_t)w * h * 4);
     const size_t step = depth == 16 ? 2 : 1;                  // 16-bit samples: the high byte (what stb's 8-bit interface returns)
@@ -263,19 +288,31 @@ inline bool decode_rgba8(const uint8_t* file, size_t n, std::vector<uint8_t>& rg
         const uint32_t v16 = ((uint32_t)trns[2 * k] << 8) | trns[2 * k + 1];
         key[k] = depth == 16 ? v16 : (v16 & 255u) * (uint32_t)scale_of_depth[depth];
     }
-    for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x) {
-        const uint8_t* row = img.data() + (size_t)y * stride; uint8_t* d = rgba.data() + ((size_t)y * w + x) * 4;
-        uint8_t sub = 0;
-        if (depth < 8) { const size_t bit = (size_t)x * depth; sub = (uint8_t)((row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1)); }
-        const uint8_t* s = depth < 8 ? &sub : row + (size_t)x * bpp;
-        auto full = [&](int c) { return depth == 16 ? ((uint32_t)s[2 * c] << 8) | s[2 * c + 1] : (uint32_t)s[c]; };
-        switch (colour) {
-            case 0: { const uint8_t g = depth < 8 ? (uint8_t)(sub * scale_of_depth[depth]) : s[0]; d[0] = d[1] = d[2] = g;
-                      d[3] = keyed && (depth == 16 ? full(0) : (uint32_t)g) == key[0] ? 0 : 255; break; }
-            case 2: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = keyed && full(0) == key[0] && full(1) == key[1] && full(2) == key[2] ? 0 : 255; break;
-            case 3: { const size_t k = s[0]; d[0] = 3 * k + 2 < plte.size() ? plte[3 * k] : 0; d[1] = 3 * k + 2 < plte.size() ? plte[3 * k + 1] : 0; d[2] = 3 * k + 2 < plte.size() ? plte[3 * k + 2] : 0; d[3] = k < trns.size() ? trns[k] : 255; break; }
-            case 4: d[0] = d[1] = d[2] = s[0]; d[3] = s[step]; break;
-            default: d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = s[3 * step]; break;
+    // one pixel: samples at `s` (sub-byte samples already extracted into s[0]) -> RGBA8 at `d`
+    auto pixel = [&](const uint8_t* s, uint8_t* d) {
+        const uint32_t f0 = depth == 16 ? ((uint32_t)s[0] << 8) | s[1] : s[0];
+        if (colour == 0) {
+            const uint8_t g = depth < 8 ? (uint8_t)(s[0] * scale_of_depth[depth]) : s[0];
+            d[0] = d[1] = d[2] = g; d[3] = keyed && (depth == 16 ? f0 : (uint32_t)g) == key[0] ? 0 : 255;
+        } else if (colour == 2) {
+            const uint32_t f1 = depth == 16 ? ((uint32_t)s[2] << 8) | s[3] : s[1], f2 = depth == 16 ? ((uint32_t)s[4] << 8) | s[5] : s[2];
+            d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = keyed && f0 == key[0] && f1 == key[1] && f2 == key[2] ? 0 : 255;
+        } else if (colour == 3) {
+            const size_t k = s[0]; const bool in_table = 3 * k + 2 < plte.size();
+            d[0] = in_table ? plte[3 * k] : 0; d[1] = in_table ? plte[3 * k + 1] : 0; d[2] = in_table ? plte[3 * k + 2] : 0; d[3] = k < trns.size() ? trns[k] : 255;
+        } else if (colour == 4) { d[0] = d[1] = d[2] = s[0]; d[3] = s[step]; }
+        else { d[0] = s[0]; d[1] = s[step]; d[2] = s[2 * step]; d[3] = s[3 * step]; }
+    };
+    for (size_t k = 0; k < passes.size(); ++k) {
+        const Pass q = passes[k];
+        for (uint32_t y = 0; y < q.h; ++y) {
+            const uint8_t* row = img.data() + q.at + (size_t)y * q.stride;
+            uint8_t* out = rgba.data() + ((size_t)(q.y0 + y * q.dy) * w + q.x0) * 4;
+            for (uint32_t x = 0; x < q.w; ++x) {
+                uint8_t sub = 0;
+                if (depth < 8) { const size_t bit = (size_t)x * depth; sub = (uint8_t)((row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1)); }
+                pixel(depth < 8 ? &sub : row + (size_t)x * bpp, out + (size_t)x * q.dx * 4);
+            }
         }
     }
     return true;

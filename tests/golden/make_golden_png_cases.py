@@ -1,5 +1,5 @@
 """Small synthetic PNG files for the corners the reference's shipped textures do not reach — grey images of depth 1, 2, 4, 8, 16 and RGB
-images of depth 8, 16 with a tRNS colour key, grey + alpha, palette with tRNS at depth 2, all five row filters — decoded by the stb_image
+images of depth 8, 16 with a tRNS colour key, grey + alpha, palette with tRNS, Adam7 interlacing (incl. sizes with empty passes), all five row filters — decoded by the stb_image
 the reference vendors (oracle/_ref/ref_stb; needs /root/reference). Writes tests/golden/png_cases.npz: the files and stb's RGBA8 pixels."""
 import os
 import struct
@@ -17,9 +17,9 @@ def chunk(kind, body):
     return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
 
 
-def png(w, h, depth, colour, samples, rng, plte=None, trns=None):
-    """samples: (h, w, channels) integers below 2**depth. Rows are packed MSB first, each with a random filter type (encoded properly)."""
-    channels = samples.shape[2]
+def filtered_rows(samples, depth, rng):
+    """One (sub-)image: rows packed MSB first, each with a random filter type (encoded properly)."""
+    h, w, channels = samples.shape
     bits = channels * depth; stride = (w * bits + 7) // 8; bpp = max(1, bits // 8)
     rows = np.zeros((h, stride), np.uint8)
     for y in range(h):
@@ -41,7 +41,20 @@ def png(w, h, depth, colour, samples, rng, plte=None, trns=None):
             else:
                 pred = (0, a, b, (a + b) >> 1)[f]
             raw.append((int(rows[y, x]) - pred) & 255)
-    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, colour, 0, 0, 0))
+    return raw
+
+
+def png(w, h, depth, colour, samples, rng, plte=None, trns=None, interlace=False):
+    """samples: (h, w, channels) integers below 2**depth."""
+    if interlace:                                             # Adam7: seven sub-images, empty ones left out
+        raw = bytearray()
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = samples[y0::dy, x0::dx]
+            if sub.shape[0] and sub.shape[1]:
+                raw += filtered_rows(sub, depth, rng)
+    else:
+        raw = filtered_rows(samples, depth, rng)
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, colour, 0, 0, int(interlace)))
     if plte is not None:
         data += chunk(b"PLTE", bytes(plte))
     if trns is not None:
@@ -67,6 +80,12 @@ def main():
     for depth in (1, 2, 4, 8):
         n = min(2 ** depth, 11)
         cases[f"palette{depth}_trns"] = png(11, 5, depth, 3, rng.integers(0, n, (5, 11, 1)), rng, plte=rng.integers(0, 256, 3 * n).astype(np.uint8), trns=rng.integers(0, 256, max(1, n - 1)).astype(np.uint8))
+    # Adam7-interlaced files, including sizes that leave some of the seven passes empty
+    for (w, h) in ((1, 1), (3, 2), (5, 9), (17, 11)):
+        cases[f"lace_rgba8_{w}x{h}"] = png(w, h, 8, 6, rng.integers(0, 256, (h, w, 4)), rng, interlace=True)
+        cases[f"lace_palette2_{w}x{h}"] = png(w, h, 2, 3, rng.integers(0, 4, (h, w, 1)), rng, plte=rng.integers(0, 256, 12).astype(np.uint8), interlace=True)
+    cases["lace_grey1_19x10"] = png(19, 10, 1, 0, rng.integers(0, 2, (10, 19, 1)), rng, interlace=True)
+    cases["lace_rgb16_9x9_key"] = png(9, 9, 16, 2, rng.integers(0, 2, (9, 9, 3)), rng, trns=struct.pack(">3H", 1, 0, 1), interlace=True)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     tool = os.path.join(ROOT, "oracle", "_ref", "ref_stb")
     gold = {}

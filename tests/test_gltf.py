@@ -528,12 +528,12 @@ def test_png_decoder_matches_stb_image_on_every_shipped_png(tmp_path):
 
 
 def test_png_decoder_corner_cases_against_stb_image(tmp_path):
-    """21 small synthetic PNG files (tests/golden/png_cases.npz, made by tests/golden/make_golden_png_cases.py) with the pixels the reference's
+    """31 small synthetic PNG files (tests/golden/png_cases.npz, made by tests/golden/make_golden_png_cases.py) with the pixels the reference's
     stb_image decodes them to: grey images of depth 1 / 2 / 4 / 8 / 16 with and without a tRNS colour key, RGB 8 / 16 with a colour key,
-    grey + alpha, RGBA, palette images of depth 1 / 2 / 4 / 8 with per-entry alpha, random row filters, IDAT split in two. Needs no reference tree."""
+    grey + alpha, RGBA, palette images of depth 1 / 2 / 4 / 8 with per-entry alpha, random row filters, IDAT split in two, Adam7-interlaced files (also sizes that leave passes empty). Needs no reference tree."""
     g = np.load(os.path.join(GOLDEN, "png_cases.npz"))
     names = sorted({k.split("/")[0] for k in g.files})
-    assert len(names) == 21
+    assert len(names) == 31
     for name in names:
         open(os.path.join(tmp_path, name + ".png"), "wb").write(g[name + "/file"].tobytes())
         path = os.path.join(tmp_path, name + ".gltf")
