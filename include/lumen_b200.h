@@ -262,6 +262,10 @@ LB_API int lb_gltf_close(LbGltf g);
  * the file the reference writes for the same asset. lb_gltf_open reads a path ending in ".ollad" back (LoadFile :70-273) instead of
  * parsing glTF, as SceneManager does when the cache exists. */
 LB_API int lb_gltf_save_ollad(LbGltf g, const char* path);
+/* SceneManager::LoadGLTF's cache protocol (LM/ModelLoading/SceneManager.cpp:55-76 over WaveFrontRenderer::OpenCustomFileFormat /
+ * CreateCustomFileFormat, PT/Framework/WaveFrontRenderer.cpp:1135-1146): reads `<path without extension>.ollad` when it exists, otherwise
+ * parses the glTF source and writes that cache next to it (a directory that cannot be written is not an error). */
+LB_API int lb_gltf_open_cached(const char* path, LbImageDecodeFn decoder /* may be NULL */, void* user, LbGltf* out);
 LB_API const char* lb_gltf_last_error(void);
 LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out);
 /* Inspection; returned pointers stay valid until lb_gltf_close. Texture members of the material are IMAGE indices of this document

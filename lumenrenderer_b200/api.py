@@ -207,6 +207,7 @@ class LbNanoVdbInfo(C.Structure):
 IMAGE_DECODE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p)
 _HOST_SIGS = {
     "gltf_open": [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
+    "gltf_open_cached": [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
     "gltf_close": [C.c_void_p],
     "gltf_save_ollad": [C.c_void_p, C.c_char_p],
     "gltf_info": [C.c_void_p, C.POINTER(LbGltfInfo)],

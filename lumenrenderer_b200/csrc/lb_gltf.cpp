@@ -628,6 +628,23 @@ LB_API int lb_gltf_save_ollad(LbGltf g, const char* path) {
         return LB_OK;
     } catch (const std::exception& e) { return gfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
 }
+// SceneManager::LoadGLTF's first two steps (LM/ModelLoading/SceneManager.cpp:55-76) with WaveFrontRenderer's hooks behind them
+// (WaveFrontRenderer.cpp:1135-1146): OpenCustomFileFormat = LoadFile(<path with the extension replaced by .ollad>), else
+// CreateCustomFileFormat = ConvertGLTF (convert, write the cache next to the source, :27-68).
+LB_API int lb_gltf_open_cached(const char* path, LbImageDecodeFn decoder, void* user, LbGltf* out) {
+    if (!path || !out) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument");
+    std::string cache(path);
+    const size_t slash = cache.find_last_of("/\\"), dot = cache.find_last_of('.');
+    if (dot != std::string::npos && (slash == std::string::npos || dot > slash + 1)) cache.erase(dot);      // std::filesystem::path::replace_extension
+    cache += ".ollad";
+    if (FILE* f = fopen(cache.c_str(), "rb")) {
+        fclose(f);
+        if (lb_gltf_open(cache.c_str(), decoder, user, out) == LB_OK) return LB_OK;      // an unreadable cache is rebuilt (the reference would crash on it)
+    }
+    const int rc = lb_gltf_open(path, decoder, user, out);
+    if (rc == LB_OK && !has_extension(std::string(path), ".ollad")) lb_gltf_save_ollad(*out, cache.c_str());   // a read-only asset directory is not an error
+    return rc;
+}
 LB_API int lb_gltf_close(LbGltf g) { delete g; return LB_OK; }
 LB_API int lb_gltf_info(LbGltf g, LbGltfInfo* out) { if (!g || !out) return gfail(LB_ERR_INVALID_ARGUMENT, "null argument"); *out = g->info; return LB_OK; }
 LB_API int lb_gltf_image(LbGltf g, uint32_t i, const uint8_t** rgba8, uint32_t* w, uint32_t* h, int* srgb, int* decoded) {

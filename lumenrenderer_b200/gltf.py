@@ -25,14 +25,14 @@ class GltfError(RuntimeError):
 
 
 class GltfDocument:
-    def __init__(self, path: str, bindings: Optional[api.Bindings] = None, image_decoder=None):
+    def __init__(self, path: str, bindings: Optional[api.Bindings] = None, image_decoder=None, cached: bool = False):
         if bindings is None:
             from . import bindings as _b
             bindings = _b()
         self.b = bindings
         self._h = C.c_void_p()
         self._decoder = api.IMAGE_DECODE_FN(image_decoder) if image_decoder is not None else None       # keep the thunk alive
-        rc = self.b.gltf_open(os.fsencode(path), C.cast(self._decoder, C.c_void_p) if self._decoder else None, None, C.byref(self._h))
+        rc = (self.b.gltf_open_cached if cached else self.b.gltf_open)(os.fsencode(path), C.cast(self._decoder, C.c_void_p) if self._decoder else None, None, C.byref(self._h))
         if rc != 0:
             raise GltfError(f"[{rc}] {(self.b.gltf_last_error() or b'').decode()}")
         info = api.LbGltfInfo()

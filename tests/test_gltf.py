@@ -419,6 +419,27 @@ def test_ollad_round_trip(tmp_path, flavour):
     assert nscenes == len(ref["doc"]["scenes"])
 
 
+def test_open_cached_follows_the_reference_cache_protocol(tmp_path):
+    """lb_gltf_open_cached = OpenCustomFileFormat, else CreateCustomFileFormat (SceneManager.cpp:55-76): the first call converts and leaves
+    `scene.ollad` beside `scene.gltf`, the second one reads only the cache (the source is gone by then), a damaged cache is rebuilt."""
+    path = build_test_document(os.path.join(tmp_path, "scene.gltf"), "embedded")
+    cache = os.path.join(tmp_path, "scene.ollad")
+    ref = gt.load_reference_semantics(path)
+    with GltfDocument(path, cached=True) as doc:
+        _compare(doc, ref)
+    first = open(cache, "rb").read()
+    hidden = path + ".hidden"; os.rename(path, hidden)
+    with GltfDocument(path, cached=True) as doc:                 # only the cache is there
+        _compare(doc, ref)
+    with pytest.raises(GltfError):
+        GltfDocument(path)
+    os.rename(hidden, path)
+    open(cache, "wb").write(first[:len(first) // 2])
+    with GltfDocument(path, cached=True) as doc:
+        _compare(doc, ref)
+    assert open(cache, "rb").read() == first
+
+
 def test_ollad_errors(tmp_path):
     data = open(os.path.join(GOLDEN, "cornell_reference.ollad"), "rb").read()
     bad = os.path.join(tmp_path, "bad.ollad")
