@@ -85,6 +85,9 @@ struct Renderer {
     DevBuf<float4> d_rays[2][3], d_shadow[3], d_surf[2], d_res[4], d_channels, d_combined, d_accum, d_vol_hits, d_vol_shadow[3];
     DevBuf<uint4> d_hits, d_primary_hits; DevBuf<float2> d_motion; DevBuf<uchar4> d_ldr;
     DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags, d_ris_order;
+    DevBuf<float4> d_vis_rays[2];          // direction-binned queue of the ReSTIR visibility rays (lb_restir.cu k_vis_bin); LB_VIS_SORT=0 turns it off
+    bool vis_sort = vis_sort_default();
+    static bool vis_sort_default() { const char* e = getenv("LB_VIS_SORT"); return !e || atoi(e) != 0; }
     uint64_t counters[12]{};
 
     // ---- FrameStats (LumenRenderer.h:29-34): CUDA events instead of host wall clock around forced syncs
@@ -161,13 +164,14 @@ struct Renderer {
         LB_CUDA(cudaStreamSynchronize(stream));
         HostTexture white; white.px = {255, 255, 255, 255}; HostTexture nrm; nrm.px = {128, 128, 255, 255};   // LumenRenderer.cpp:50-58
         textures.push_back(white); textures.push_back(nrm);
-        d_counters.reserve(kNumCounters); d_stats.reserve(kNumStats); d_bags.reserve(50 * 1000);
+        d_counters.reserve(kNumCounters); d_counters.zero(stream); d_stats.reserve(kNumStats); d_stats.zero(stream); d_bags.reserve(50 * 1000);
         resize();
     }
 
     void resize() {
         const size_t n = npix();
-        d_ris_order.reserve((n + 255) / 256 + 128);          // + per-bag {start, count} and work tickets (lb_restir.cu k_ris_order)
+        d_ris_order.reserve((n + 255) / 256 + 128);
+        if (vis_sort) for (auto& p : d_vis_rays) p.reserve(n);          // + per-bag {start, count} and work tickets (lb_restir.cu k_ris_order)
         for (auto& q : d_rays) for (auto& p : q) p.reserve(n);
         for (auto& p : d_shadow) p.reserve(n);
         for (auto& p : d_surf) { p.reserve(n * kSurfPlanes); p.zero(stream); }
@@ -287,6 +291,9 @@ struct Renderer {
             dual_bvh = !(a && !strcmp(a, "same")) && total_tris > 1u;
             if (dual_bvh) bvh_build(stream, d_flat.p, total_tris, bvh_any, BvhBuilder::PLOC, a && !strcmp(a, "ploc64") ? 64 : 128);
         }
+        // the traversal keeps one pending sibling group per level (+ one transient entry) on a kTraceStack-entry stack: refuse a hierarchy it
+        // cannot walk without dropping groups instead of rendering wrong hits
+        if (std::max(bvh.levels, dual_bvh ? bvh_any.levels : 0u) + 2u > 64u) throw std::runtime_error("BVH deeper than the traversal stack (62 levels)");
         lights.num_lights = 0; lights.cdf_sum = 0.f;
         if (total_tris) build_lights(cfg(), scene_view(), in, d_prim_flags.p, lights);
         // volumes
@@ -380,7 +387,8 @@ struct Renderer {
         const LaunchCfg c = cfg();
         FrameView fv = frame_view();
         const SceneView sc = scene_view();
-        const BvhView bv = bvh.view(), bva = dual_bvh ? bvh_any.view() : bvh.view();
+        uint32_t* const ovf = d_counters.p + CNT_STACK_OVERFLOW;
+        const BvhView bv = bvh.view(ovf), bva = dual_bvh ? bvh_any.view(ovf) : bvh.view(ovf);
         const uint32_t stride = st.frame_count_stride ? st.frame_count_stride : 2u;
         const uint32_t frame_count = st.first_frame_count + 1u + stride * frame_index;      // the reference's counter advances twice per frame
         uint32_t launches = 0;
@@ -390,6 +398,9 @@ struct Renderer {
         lap("raygen");
         uint32_t seed = wang_hash(frame_count);
         uint32_t ticket = 0;
+        // every trace launch of a frame owns one device ticket; a schedule that needs more than the counter block holds is refused here, not
+        // left to index past d_counters
+        auto take_ticket = [&]() { if (ticket >= kMaxTickets) throw std::runtime_error("frame schedule needs more than kMaxTickets device tickets"); return ticket++; };
         ShadeArgs a{}; a.max_depth = st.depth;
         a.volumes = d_volumes.p; a.num_volumes = (uint32_t)vinstances.size(); a.volume_mode = (int)st.volume_mode;
         prev_view_proj(a.prev_view_proj);
@@ -401,7 +412,9 @@ struct Renderer {
         const uint32_t seed0 = seed;
         auto run_restir = [&](bool on_side) {
             RestirArgs ra{seed0, (int)st.restir_temporal, (int)st.restir_spatial};
-            RestirBuffers rb{d_bags.p, d_ris_order.p};
+            static const int ris_simple = []() { const char* e = getenv("LB_RIS_SIMPLE"); return (!e || atoi(e) != 0) ? 1 : 0; }();
+            ra.ris_simple = ris_simple;
+            RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr};
             LaunchCfg cr = c;
             if (on_side) {
                 need_side_stream();
@@ -410,15 +423,16 @@ struct Renderer {
                 ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 1); };
             } else ra.lap = [](void* user, const char* stage) { static_cast<Renderer*>(user)->lap(stage, 0); };
             ra.lap_user = this;
+            if (ticket + 6u > kMaxTickets) throw std::runtime_error("frame schedule needs more than kMaxTickets device tickets");
             launch_restir(cr, fv, sc, bva, rb, ra, ticket);
             if (on_side) LB_CUDA(cudaEventRecord(ev_join, restir_stream));
-            if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u);
+            if (sc.num_lights) launches += 4u + (st.restir_temporal ? 1u : 0u) + (st.restir_spatial ? 4u : 0u) + (vis_sort ? (st.restir_spatial ? 2u : 1u) : 0u);
         };
         for (uint32_t depth = 0; depth < st.depth; ++depth) {
             const int queue = (int)(depth & 1u);
             LaunchCfg cb = c; if (tail_forked) cb.stream = restir_stream;         // stream of the bounce chain
             const int chain = tail_forked ? 1 : 0;
-            launch_extend(cb, fv, bv, queue, ticket++, depth == 0, 0.01f, 5000.f); ++launches;
+            launch_extend(cb, fv, bv, queue, take_ticket(), depth == 0, 0.01f, 5000.f); ++launches;
             lap("extend", chain);
             // the previous wave's shadow rays (side stream) read the shadow queue this wave's shade kernel is about to refill
             if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
@@ -457,11 +471,11 @@ struct Renderer {
                     need_side_stream();
                     LB_CUDA(cudaEventRecord(ev_fork, stream)); LB_CUDA(cudaStreamWaitEvent(restir_stream, ev_fork, 0));
                     LaunchCfg cs = c; cs.stream = restir_stream; last_lap[1] = last_lap[0];
-                    launch_shadow(cs, fv, bva, ticket++, 0.01f); ++launches; lap("shadow", 1);
+                    launch_shadow(cs, fv, bva, take_ticket(), 0.01f); ++launches; lap("shadow", 1);
                     LB_CUDA(cudaEventRecord(ev_shadow, restir_stream)); shadow_in_flight = true;
-                } else { launch_shadow(cb, fv, bva, ticket++, 0.01f); ++launches; lap("shadow", chain_s); }
+                } else { launch_shadow(cb, fv, bva, take_ticket(), 0.01f); ++launches; lap("shadow", chain_s); }
             }
-            if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bva, ticket++, 0.01f); ++launches; lap("volume_shadow"); }
+            if (a.do_nee && a.num_volumes && st.volume_mode == LB_VOLUME_COMPAT) { launch_volume_shadow(c, fv, bva, take_ticket(), 0.01f); ++launches; lap("volume_shadow"); }
             seed = wang_hash(seed);
         }
         if (tail_forked) { LB_CUDA(cudaEventRecord(ev_join, restir_stream)); forked = true; }
@@ -718,9 +732,11 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
     });
 }
 static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uint32_t* count) {     // caller holds R->mu
-    unsigned long long s[kNumStats];
+    unsigned long long s[kNumStats]; uint32_t overflows = 0;
     LB_CUDA(cudaMemcpyAsync(s, R->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R->stream));
+    LB_CUDA(cudaMemcpyAsync(&overflows, R->d_counters.p + CNT_STACK_OVERFLOW, sizeof overflows, cudaMemcpyDeviceToHost, R->stream));
     LB_CUDA(cudaStreamSynchronize(R->stream));
+    R->counters[11] = overflows;              // traversal-stack overflows since the last frame began (debug traces included): must be 0
     R->counters[0] = s[STAT_EXTEND]; R->counters[1] = s[STAT_SHADOW]; R->counters[2] = s[STAT_VIS]; R->counters[3] = R->launches_last_frame;
     const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
 }
@@ -740,8 +756,8 @@ LB_API int lb_save_png(LbRenderer r, const char* path) {
 }
 LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* needed) {
     return guarded(R_, [&]() {
-        static const char* kCounterNames[11] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
-                                                "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds"};
+        static const char* kCounterNames[12] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
+                                                "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds", "stack_overflows"};
         uint64_t cnt[12]; uint32_t n = 0;
         int rc = frame_counters_locked(R_, cnt, 12, &n); if (rc) return rc;
         LB_CUDA(cudaStreamSynchronize(R_->stream));
@@ -756,7 +772,7 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
         std::string o = "{\"frame_id\": " + std::to_string(R_->frame_index) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
         for (size_t i = 0; i < times.size(); ++i) { snprintf(num, sizeof num, "%.3f", times[i].second); o += (i ? ", \"" : "\"") + times[i].first + "\": " + num; }
         o += "}, \"counters\": {";
-        for (uint32_t i = 0; i < n && i < 11; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);
+        for (uint32_t i = 0; i < n && i < 12; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);
         o += "}}";
         if (needed) *needed = o.size() + 1;
         if (!json || cap < o.size() + 1) return (json || cap) ? fail(LB_ERR_INVALID_ARGUMENT, "buffer too small") : (needed ? (int)LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "null"));
@@ -787,7 +803,7 @@ LB_API int lb_debug_trace_closest(LbRenderer r, const float* rays6, uint32_t n, 
         if (!n) return (int)LB_OK;
         DevBuf<float> d_rays; DevBuf<unsigned char> d_hits;
         d_rays.upload(rays6, (size_t)n * 6, R_->stream); d_hits.reserve((size_t)n * 20);
-        launch_debug_trace(R_->cfg(), R_->bvh.view(), d_rays.p, nullptr, n, tmin, tmax, d_hits.p, nullptr);
+        launch_debug_trace(R_->cfg(), R_->bvh.view(R_->d_counters.p + CNT_STACK_OVERFLOW), d_rays.p, nullptr, n, tmin, tmax, d_hits.p, nullptr);
         return read_back(R_, d_hits.p, (size_t)n * 20, hits20, (size_t)n * 20);
     });
 }
@@ -797,7 +813,7 @@ LB_API int lb_debug_trace_any(LbRenderer r, const float* rays6, const float* tma
         if (!n) return (int)LB_OK;
         DevBuf<float> d_rays, d_tmax; DevBuf<uint8_t> d_occ;
         d_rays.upload(rays6, (size_t)n * 6, R_->stream); d_tmax.upload(tmaxs, n, R_->stream); d_occ.reserve(n);
-        launch_debug_trace(R_->cfg(), R_->dual_bvh ? R_->bvh_any.view() : R_->bvh.view(), d_rays.p, d_tmax.p, n, tmin, 0.f, nullptr, d_occ.p);
+        launch_debug_trace(R_->cfg(), R_->dual_bvh ? R_->bvh_any.view(R_->d_counters.p + CNT_STACK_OVERFLOW) : R_->bvh.view(R_->d_counters.p + CNT_STACK_OVERFLOW), d_rays.p, d_tmax.p, n, tmin, 0.f, nullptr, d_occ.p);
         return read_back(R_, d_occ.p, n, occ, n);
     });
 }

@@ -354,6 +354,40 @@ struct BsdfCtx {
         return 1.0f / (2 * kPi);
     }
 
+    // Materials without transmission, sheen, clear coat, anisotropy and subsurface scattering — most of a typical scene — keep only the diffuse
+    // and the isotropic GGX lobe. eval_simple() is eval() with the branches such a material never takes removed: the same expressions in the
+    // same order for what is left (bit-identical to eval() in the exact-arithmetic unit: the debug tap of lb_debug.cu poisons its output on a
+    // mismatch, so the golden-vector tests of tests/test_gpu_bsdf.py check it for every simple material they hold). The callers
+    // that evaluate many samples per pixel (RIS: 32) pick it per WARP, so the warp runs a loop body without the predicated-off lobes.
+    LB_D bool is_simple() const { return s.transmission == 0.f && w[1] == 0.f && w[3] == 0.f && ax == ay && s.subsurface == 0.f && s.roughness > 0.001f; }
+    LB_D float3 eval_simple(const float3& wiw, float& pdf) const {
+        pdf = 0; float3 value = f3(0.f);
+        if (w[0] > 0) {
+            const float3 m = normalize(wiw + wow);
+            const float cos_in = dot(N, wiw), cos_ih = dot(wiw, m);
+            const float fl = schlick_w(cos_in);
+            const float fd90 = 0.5f + 2.0f * sq(cos_ih) * s.roughness;
+            const float fd = mixf(1.f, fd90, fl) * mixf(1.f, fd90, fv);
+            value = s.color * fd * kInvPi * (1.0f - s.metallic);
+            pdf += w[0] * (fabsf(cos_in) * kInvPi);
+        }
+        if (w[2] > 0) {
+            const float3 wil = to_local(wiw, N, T, B);
+            const float3 m = normalize(wol + wil);
+            if (wol.z != 0 && wil.z != 0) {
+                const float cos_oh = dot(wol, m);
+                if (cos_oh != 0) {
+                    const float D = ggx_D(m, ax, ax), G = 1.0f / (1.0f + lam_wo_ggx + ggx_Lambda(wil, ax, ax));
+                    float3 c = fresnel_spec_at(m);
+                    c *= D * G / fabsf(4.0f * wol.z * wil.z);
+                    const float p = (g1_wo_ggx * fabsf(cos_oh) * D / fabsf(wol.z)) / fabsf(4.0f * cos_oh);
+                    if (p > 0) { pdf += w[2] * p; value += c; }
+                }
+            }
+        }
+        return value;
+    }
+
     LB_D float3 eval(const float3& wiw, float& pdf) const {
         float3 trans_bsdf = f3(0.f); float trans_pdf = 0.f;
         if (s.transmission > 0.f) {

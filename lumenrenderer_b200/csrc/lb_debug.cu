@@ -38,7 +38,16 @@ __global__ void k_debug_bsdf(const float* __restrict__ mat24, const float* __res
     const float* v = v12 + 12 * i;
     const float3 nrm = f3(v[0], v[1], v[2]), tan = f3(v[3], v[4], v[5]), wo = f3(v[6], v[7], v[8]);
     if (!sample) {
-        float pdf = 0.f; const float3 b = bsdf_eval(m, nrm, tan, wo, f3(v[9], v[10], v[11]), pdf);
+        const BsdfCtx c(m, nrm, tan, wo); const float3 wi = f3(v[9], v[10], v[11]);
+        float pdf = 0.f; float3 b = c.eval(wi, pdf);
+        // the lean evaluation RIS uses for materials without transmission / sheen / clear coat / anisotropy / subsurface must reproduce the general
+        // one exactly in this unit (no contraction, IEEE division): a mismatch poisons the output, which fails the golden-vector tests
+        if (c.is_simple()) {
+            float p2 = 0.f; const float3 b2 = c.eval_simple(wi, p2);
+            const bool same = __float_as_uint(b2.x + 0.f) == __float_as_uint(b.x + 0.f) && __float_as_uint(b2.y + 0.f) == __float_as_uint(b.y + 0.f) &&
+                              __float_as_uint(b2.z + 0.f) == __float_as_uint(b.z + 0.f) && __float_as_uint(p2 + 0.f) == __float_as_uint(pdf + 0.f);
+            if (!same) { b = f3(__int_as_float(0x7fc00000)); pdf = __int_as_float(0x7fc00000); }
+        }
         out[4 * i] = b.x; out[4 * i + 1] = b.y; out[4 * i + 2] = b.z; out[4 * i + 3] = pdf;
     } else {
         float pdf = 0.f; bool spec = false; float3 wi = f3(0.f);

@@ -146,6 +146,7 @@ struct BvhView {
     const Bvh8Node* nodes;
     const DevTri* tris;
     uint32_t num_tris;
+    uint32_t* overflow;               // device counter of traversal-stack overflows (nullptr = not counted)
 };
 
 struct SceneView {

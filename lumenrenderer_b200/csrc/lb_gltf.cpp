@@ -25,6 +25,7 @@
 // stb_image); without one the image becomes the 1x1 default and is counted in LbGltfInfo::undecoded_images.
 #include "../../include/lumen_b200.h"
 #include "lb_json.h"
+#include <unistd.h>
 #include "lb_png.h"
 #include <cmath>
 #include <cstdio>
@@ -244,8 +245,12 @@ struct Loader {
             if (imgs[i].has("uri")) have = load_uri(imgs[i]["uri"].string(), bytes);
             else if (imgs[i].has("bufferView")) {
                 const Value& view = doc["bufferViews"][(size_t)imgs[i]["bufferView"].integer(-1)];
-                const size_t buf = (size_t)view["buffer"].integer(0), off = (size_t)view["byteOffset"].integer(0), len = (size_t)view["byteLength"].integer(0);
-                if (!view.is_null() && buf < buffers.size() && off + len <= buffers[buf].size()) { bytes.assign(buffers[buf].begin() + off, buffers[buf].begin() + off + len); have = true; }
+                // signed reads + the overflow-safe range test of accessor_bytes: a negative or huge byteOffset / byteLength must not wrap
+                const int64_t buf = view["buffer"].integer(0), off = view["byteOffset"].integer(0), len = view["byteLength"].integer(0);
+                if (!view.is_null() && buf >= 0 && (uint64_t)buf < buffers.size() && off >= 0 && len >= 0) {
+                    const std::vector<uint8_t>& src = buffers[(size_t)buf];
+                    if ((uint64_t)off <= src.size() && (uint64_t)len <= src.size() - (uint64_t)off) { bytes.assign(src.begin() + off, src.begin() + off + len); have = true; }
+                }
             }
             Image& im = g.images[i];
             if (have) im.raw = std::move(bytes);
@@ -392,10 +397,16 @@ struct Loader {
         for (int k = 0; k < 4; ++k) q[k] = (float)n["rotation"][(size_t)k].number(k == 3 ? 1.0 : 0.0);
         return mat_trs(t, q, s);
     }
+    // glTF requires a strict tree: a node reached twice (a DAG expands exponentially: 26 nodes listing each other twice are 2^26 copies)
+    // or a cycle is rejected
+    std::vector<uint8_t> node_seen;
     Node load_node(int64_t index, int depth) {
         const Value& n = doc["nodes"][(size_t)index];
         if (index < 0 || n.is_null()) bad("node index out of range");
         if (depth > 512) bad("node hierarchy too deep (cycle?)");
+        if (node_seen.size() < doc["nodes"].size()) node_seen.resize(doc["nodes"].size(), 0);
+        if (node_seen[(size_t)index]) bad("node referenced more than once (glTF node hierarchies are strict trees)");
+        node_seen[(size_t)index] = 1;
         Node out; out.name = n["name"].is_null() ? std::string() : n["name"].string(); out.local = node_local(n);
         const int64_t mesh = n["mesh"].integer(-1);
         if (mesh >= (int64_t)g.meshes.size()) bad("mesh index out of range");
@@ -409,6 +420,7 @@ struct Loader {
         for (size_t s = 0; s < scenes.size(); ++s) {
             Scene sc; sc.name = scenes[s]["name"].is_null() ? std::string() : scenes[s]["name"].string();
             const Value& roots = scenes[s]["nodes"];
+            node_seen.assign(doc["nodes"].size(), 0);          // per scene: two scenes may share nodes, one scene may not visit a node twice
             for (size_t k = 0; k < roots.size(); ++k) sc.roots.push_back(load_node(roots[k].integer(-1), 0));
             g.scenes.push_back(std::move(sc));
         }
@@ -620,11 +632,16 @@ LB_API int lb_gltf_save_ollad(LbGltf g, const char* path) {
             put(header, &h, sizeof h); put(header, sc.name.data(), sc.name.size());
             for (const Node& n : sc.roots) put_node(header, n);
         }
-        FILE* f = fopen(path, "wb");
+        // Written to a temporary file in the same directory and renamed over the target: every rank of a multi-GPU job converts the same
+        // asset, and a reader must never see a cache whose header is complete while its blob is still being written (such a file passes
+        // every span check and loads zeroed geometry). rename() within one directory is atomic.
+        const std::string tmp = std::string(path) + ".tmp." + std::to_string((unsigned long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)g);
+        FILE* f = fopen(tmp.c_str(), "wb");
         if (!f) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("cannot write ") + path);
         const uint64_t header_size = header.size();
         const bool ok = fwrite(&header_size, 8, 1, f) == 1 && (header.empty() || fwrite(header.data(), 1, header.size(), f) == header.size()) && (blob.empty() || fwrite(blob.data(), 1, blob.size(), f) == blob.size());
-        if (fclose(f) != 0 || !ok) return gfail(LB_ERR_INVALID_ARGUMENT, std::string("short write to ") + path);
+        if (fclose(f) != 0 || !ok) { remove(tmp.c_str()); return gfail(LB_ERR_INVALID_ARGUMENT, std::string("short write to ") + path); }
+        if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return gfail(LB_ERR_INVALID_ARGUMENT, std::string("cannot replace ") + path); }
         return LB_OK;
     } catch (const std::exception& e) { return gfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
 }

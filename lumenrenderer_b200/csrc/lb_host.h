@@ -66,7 +66,7 @@ struct DeviceBvh {
     DevBuf<Bvh8Node> nodes; DevBuf<DevTri> tris;
     uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0;
     float build_ms = 0.f;
-    BvhView view() const { return BvhView{nodes.p, tris.p, num_tris}; }
+    BvhView view(uint32_t* overflow = nullptr) const { return BvhView{nodes.p, tris.p, num_tris, overflow}; }
     size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + 3 * (size_t)num_tris * sizeof(DevTri); }      // three rotated triangle copies
 };
 

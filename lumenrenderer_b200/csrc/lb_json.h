@@ -31,7 +31,13 @@ struct Value {
     const Value& operator[](size_t i) const { static const Value none; return (kind == Array && i < arr.size()) ? arr[i] : none; }
     size_t size() const { return kind == Array ? arr.size() : (kind == Object ? obj.size() : 0); }
     double number(double dflt) const { return kind == Number ? num : dflt; }
-    int64_t integer(int64_t dflt) const { return kind == Number ? (int64_t)num : dflt; }
+    // clamped to +-2^62: the double -> int64 cast is undefined outside the int64 range (1e30, NaN), and callers only ever compare the
+    // result with sizes and counts
+    int64_t integer(int64_t dflt) const {
+        if (kind != Number || num != num) return dflt;
+        const double lim = 4611686018427387904.0;
+        return num >= lim ? (int64_t)1 << 62 : (num <= -lim ? -((int64_t)1 << 62) : (int64_t)num);
+    }
     const std::string& string() const { return str; }
 };
 

@@ -9,8 +9,11 @@ namespace lb {
 // device counters (uint32): wavefront queue sizes + per-launch tickets for the dynamic ray fetch
 enum : uint32_t {
     CNT_RAYS_A = 0, CNT_RAYS_B = 1, CNT_SHADOW = 2, CNT_VIS = 3, CNT_VOL_SHADOW = 4,
+    CNT_STACK_OVERFLOW = 5, CNT_VIS2 = 6,   // CNT_VIS / CNT_VIS2: sizes of the binned visibility-ray queue of the two ReSTIR visibility passes
+             // traversal-stack entries dropped this frame (Tracer::push at kTraceStack): must stay 0, surfaced in lb_frame_counters
     CNT_TICKET0 = 8,                 // tickets CNT_TICKET0 .. CNT_TICKET0+kMaxTickets-1, one per trace launch of a frame
-    kMaxTickets = 56, kNumCounters = 64
+    // worst case of the schedule lb_create accepts (depth 24, LB_VOLUME_COMPAT: extend + shadow + volume shadow per wave, 5 ReSTIR tickets) is 77
+    kMaxTickets = 120, kNumCounters = 128
 };
 // device statistics (uint64): rays traced per kind this frame
 enum : uint32_t { STAT_EXTEND = 0, STAT_SHADOW = 1, STAT_VIS = 2, kNumStats = 4 };
@@ -54,6 +57,7 @@ struct ShadeArgs {
 
 struct RestirArgs {
     uint32_t seed; int temporal, spatial;
+    int ris_simple = 1;               // RIS may take the lean BSDF evaluation for rows of simple materials (LB_RIS_SIMPLE=0: always the general one)
     void (*lap)(void* user, const char* stage) = nullptr; void* lap_user = nullptr;      // per-kernel timing marks (CUDA events of the renderer)
 };
 
@@ -76,7 +80,7 @@ void launch_debug_reservoirs(const LaunchCfg&, const float4* planes, uint32_t np
 void launch_debug_hits(const LaunchCfg&, const uint4* hits, uint32_t n, void* hits20);
 
 // ---- ReSTIR (lb_restir.cu)
-struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; };      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
+struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; float4* vis_ray_o = nullptr; float4* vis_ray_d = nullptr; };      // vis_ray_*: binned visibility-ray queue (o.xyz, tmax | d.xyz, pixel), nullptr = trace straight from the reservoirs      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
 void launch_restir(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView&, const RestirBuffers&, const RestirArgs&, uint32_t& ticket);
 
 // ---- scene preparation (lb_scene.cu)

@@ -295,7 +295,16 @@ LB_API int lb_nanovdb_dense(LbNanoVdb g, int as_density, float* out, size_t capa
     if (!g || !out) return vfail(LB_ERR_INVALID_ARGUMENT, "null argument");
     const LbNanoVdbInfo& i = g->info;
     if (i.index_max[0] < i.index_min[0]) return LB_OK;
-    const uint64_t need = ((uint64_t)(i.index_max[0] - (int64_t)i.index_min[0]) + 1) * ((uint64_t)(i.index_max[1] - (int64_t)i.index_min[1]) + 1) * ((uint64_t)(i.index_max[2] - (int64_t)i.index_min[2]) + 1);
+    // index_min / index_max come unchecked from the file's root bounding box: cap every extent (as lb_volume_create_nanovdb does) before the
+    // product, which would otherwise wrap (2^32 x 2^32 x 1 -> 0) and let dense() write outside `out`
+    uint64_t ext[3];
+    for (int a = 0; a < 3; ++a) {
+        if (i.index_max[a] < i.index_min[a]) return LB_OK;
+        ext[a] = (uint64_t)((int64_t)i.index_max[a] - (int64_t)i.index_min[a]) + 1;
+        if (ext[a] > 8192) return vfail(LB_ERR_OUT_OF_MEMORY, "dense box of the grid exceeds 8192 voxels along an axis");
+    }
+    const uint64_t need = ext[0] * ext[1] * ext[2];
+    if (need > ((uint64_t)1 << 33)) return vfail(LB_ERR_OUT_OF_MEMORY, "dense box of the grid exceeds 2^33 voxels");
     if (capacity_floats < need) return vfail(LB_ERR_INVALID_ARGUMENT, "dense buffer too small: " + std::to_string(need) + " floats needed");
     try { g->dense(out, as_density != 0); return LB_OK; } catch (const std::exception& e) { return vfail(LB_ERR_INVALID_ARGUMENT, e.what()); }
 }

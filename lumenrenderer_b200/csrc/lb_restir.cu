@@ -162,13 +162,38 @@ __global__ void __launch_bounds__(1024) k_ris_order(uint32_t seed, uint32_t npix
     }
 }
 
+// Phase B of k_ris for one 32-pixel row: the survivors of every lane in candidate order, one per lane per round, the lanes aligned on the
+// BSDF evaluation. SIMPLE = every pixel of the row has a material without transmission / sheen / clear coat / anisotropy / subsurface
+// (voted by the warp): the round then runs the lean evaluation — no predicated-off lobes, no transmission branch.
+template <bool SIMPLE>
+LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kBlock], const BsdfCtx& ctx, const Surface& px, uint32_t mask, uint32_t s0, Reservoir& fresh) {
+    uint32_t sb = s0;
+    while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+        const bool active = mask != 0u;
+        BagCandidate c; ResampleGeom g; bool have_g = false;
+        c.ls.radiance = f3(0.f); c.ls.normal = f3(0.f); c.ls.position = f3(0.f); c.ls.contribution = f3(0.f); c.ls.area = 0.f; c.ls.pdf = 0.f; c.bag_pdf = 1.f;
+        g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
+        if (active) {
+            const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
+            sb = s_state[k][threadIdx.x];
+            const uint32_t slot = draw_candidate_geom(bag, sb, c);
+            c.ls.radiance = f3(bag.rad[slot]);
+            have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
+        }
+        __syncwarp();
+        if (have_g) resample_shade<SIMPLE>(ctx, g, c.ls);
+        if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
+        __syncwarp();
+    }
+}
+
 // Work item = one 32-pixel row of a 256-pixel group, taken by WARPS from the work ticket of ONE bag: a block stages a bag (1000 entries
 // with the full light record, 72 KB of shared memory) and its 8 warps then work through that bag's rows without ever waiting for one
 // another. Blocks start on bag (blockIdx mod 50) — about six blocks per bag at 2 blocks per SM — and, when their bag is exhausted, move
 // on to the next bag that still has rows (work stealing; costs one more staging). The first version handed whole 256-pixel groups to
 // blocks in image order and re-staged the bag for every group (14 400 times per frame at 1440p): barrier stalls 0.46 and
 // long-scoreboard 0.64 warps per issue (profiles/r01_u_kernels.md).
-__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed) {
+__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed, int allow_simple) {
     static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
     static_assert(kBlock == 256, "8 warps = the 8 rows of a 256-pixel bag group");
     constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -250,24 +275,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 
         // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation
         const BsdfCtx ctx = surface_ctx(px);
-        uint32_t sb = s0;
-        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
-            const bool active = mask != 0u;
-            BagCandidate c; ResampleGeom g; bool have_g = false;
-            c.ls.radiance = f3(0.f); c.ls.normal = f3(0.f); c.ls.position = f3(0.f); c.ls.contribution = f3(0.f); c.ls.area = 0.f; c.ls.pdf = 0.f; c.bag_pdf = 1.f;
-            g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
-            if (active) {
-                const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
-                sb = s_state[k][threadIdx.x];
-                const uint32_t slot = draw_candidate_geom(bag, sb, c);
-                c.ls.radiance = f3(bag.rad[slot]);
-                have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
-            }
-            __syncwarp();
-            if (have_g) resample_shade(ctx, g, c.ls);
-            if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
-            __syncwarp();
-        }
+        if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_simple()))) ris_phase_b<true>(bag, s_state, ctx, px, mask, s0, fresh);
+        else ris_phase_b<false>(bag, s_state, ctx, px, mask, s0, fresh);
         if (valid) {
             reservoir_update_weight(fresh);
             reservoir_store(fv.res_cur, np, i, fresh);
@@ -305,6 +314,103 @@ __global__ void __launch_bounds__(kBlock, 4) k_visibility_shade(FrameView fv, Bv
     trace_queue<true>(bvh, fv.npix, ticket, job, tune);
     const uint32_t traced = __reduce_add_sync(0xFFFFFFFFu, job.traced);
     if ((threadIdx.x & 31u) == 0u && traced) atomicAdd(stat, (unsigned long long)traced);
+}
+
+// ------------------------------------------------------------------ visibility rays binned by direction (RestirShadowRay queue, ReSTIRKernels.cu:546-582)
+// The reservoir samples of neighbouring pixels point at different lights, so a warp that takes 32 consecutive pixels traces 32 rays that
+// leave the same spot in 32 directions: its lanes walk different nodes (19 of 32 lanes active in the first version) and the warp lasts
+// as long as its longest ray. The reference materialises the rays (32-byte RestirShadowRay, atomic append); here a pre-pass does the
+// same — but per 64x32-pixel tile, counting-sorted in shared memory by the ray's DIRECTION (octahedral map, 32x32 bins in Morton order) —
+// and appends the tile's rays, bin after bin, to one compact queue. Consecutive queue entries then share origin region and direction: a
+// warp's 32 rays visit the same nodes. Occlusion is a pure function of (ray, triangle set), so the order changes no result.
+constexpr uint32_t kBinTileW = 64, kBinTileH = 32, kBinTile = kBinTileW * kBinTileH, kBinPer = kBinTile / kBlock, kDirBins = 1024;
+LB_D uint32_t spread5(uint32_t v) { v &= 31u; v = (v | (v << 4)) & 0x10Fu; v = (v | (v << 2)) & 0x133u; v = (v | (v << 1)) & 0x155u; return v; }
+LB_D uint32_t direction_bin(const float3& d) {
+    const float inv = 1.f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float px = d.x * inv, py = d.y * inv;
+    if (d.z < 0.f) { const float ox = (1.f - fabsf(py)) * (px < 0.f ? -1.f : 1.f), oy = (1.f - fabsf(px)) * (py < 0.f ? -1.f : 1.f); px = ox; py = oy; }
+    const uint32_t bx = (uint32_t)fminf(fmaxf((px * 0.5f + 0.5f) * 32.f, 0.f), 31.f), by = (uint32_t)fminf(fmaxf((py * 0.5f + 0.5f) * 32.f, 0.f), 31.f);
+    return spread5(bx) | (spread5(by) << 1);
+}
+__global__ void __launch_bounds__(kBlock) k_vis_bin(FrameView fv, float4* __restrict__ ray_o, float4* __restrict__ ray_d, uint32_t* __restrict__ count) {
+    __shared__ uint32_t s_hist[kDirBins];
+    __shared__ uint32_t s_warp[kBlock / 32];
+    __shared__ uint32_t s_base;
+    const size_t np = fv.npix;
+    const uint32_t tiles_x = (fv.width + kBinTileW - 1u) / kBinTileW, tiles_y = (fv.height + kBinTileH - 1u) / kBinTileH;
+    for (uint32_t tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        for (uint32_t b = threadIdx.x; b < kDirBins; b += kBlock) s_hist[b] = 0u;
+        __syncthreads();
+        float4 o4[kBinPer], d4[kBinPer]; uint32_t bin[kBinPer];
+#pragma unroll
+        for (uint32_t k = 0; k < kBinPer; ++k) {
+            const uint32_t local = k * kBlock + threadIdx.x;
+            const uint32_t x = tx * kBinTileW + (local & (kBinTileW - 1u)), y = ty * kBinTileH + local / kBinTileW;
+            bin[k] = 0xFFFFFFFFu;
+            if (x < fv.width && y < fv.height) {
+                const uint32_t i = y * fv.width + x;
+                const float4 r0 = fv.res_cur[i], sp = fv.surf_cur[i];
+                if (!__float_as_uint(sp.w) && r0.y > 0.f) {
+                    const float3 o = f3(sp);
+                    float3 d = f3(fv.res_cur[np + i]) - o; const float l = length(d); d /= l;
+                    o4[k] = f4(o, l - 0.05f); d4[k] = f4(d, __uint_as_float(i));
+                    bin[k] = direction_bin(d);
+                    atomicAdd(&s_hist[bin[k]], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the 1024 bin counts: 4 per thread, warp scan, scan of the 8 warp totals
+        uint32_t c[4], run = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c[j] = s_hist[threadIdx.x * 4u + j]; run += c[j]; }
+        uint32_t incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off); if ((threadIdx.x & 31u) >= (uint32_t)off) incl += v; }
+        if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t before = 0u, total = 0u;
+#pragma unroll
+        for (uint32_t w = 0; w < kBlock / 32; ++w) { const uint32_t v = s_warp[w]; if (w < (threadIdx.x >> 5)) before += v; total += v; }
+        if (threadIdx.x == 0u) s_base = atomicAdd(count, total);
+        uint32_t excl = before + incl - run;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_hist[threadIdx.x * 4u + j] = excl; excl += c[j]; }
+        __syncthreads();
+        const uint32_t base = s_base;
+#pragma unroll
+        for (uint32_t k = 0; k < kBinPer; ++k) {
+            if (bin[k] != 0xFFFFFFFFu) {
+                const uint32_t at = base + atomicAdd(&s_hist[bin[k]], 1u);
+                ray_o[at] = o4[k]; ray_d[at] = d4[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+struct SortedVisibilityJob {
+    static constexpr bool kDeferDone = true;
+    FrameView fv; float shaded; const float4* __restrict__ ray_o; const float4* __restrict__ ray_d;
+    uint32_t pixel;                                             // lane state between load and done
+    LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) {
+        const float4 o4 = ray_o[i], d4 = ray_d[i];
+        o = f3(o4); d = f3(d4); t0 = 0.1f; t1 = o4.w; pixel = __float_as_uint(d4.w);
+        return true;
+    }
+    LB_D void done(uint32_t, bool occluded, const Tracer&) {
+        float* weight = reinterpret_cast<float*>(fv.res_cur + pixel) + 1;
+        if (occluded) { *weight = 0.f; return; }
+        const float3 c = f3(fv.res_cur[4 * (size_t)fv.npix + pixel]) * (*weight / shaded);
+        float4 o = fv.channels[pixel]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[pixel] = o;
+    }
+};
+__global__ void __launch_bounds__(kBlock, 4) k_visibility_sorted(FrameView fv, BvhView bvh, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const uint32_t* __restrict__ count,
+                                                                uint32_t* ticket, float shaded, unsigned long long* stat, TraceTuning tune) {
+    const uint32_t n = *count;
+    SortedVisibilityJob job{fv, shaded, ray_o, ray_d, 0u};
+    trace_queue<true>(bvh, n, ticket, job, tune);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
 __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
@@ -422,11 +528,21 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     seed = wang_hash(seed);
     LB_CUDA(cudaFuncSetAttribute(k_ris, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRisSmemBytes));      // per device; a host-side setting, no launch
     k_ris_order<<<1, 1024, 0, st>>>(seed, fv.npix, fv.pix0, rb.ris_order); LB_LAUNCH_CHECK();
-    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed); LB_LAUNCH_CHECK();
+    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed, a.ris_simple); LB_LAUNCH_CHECK();
     lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
-    k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
-    lap("restir_visibility");
+    int vis_pass = 0;
+    auto visibility = [&]() {
+        if (rb.vis_ray_o) {
+            uint32_t* count = &fv.counters[vis_pass++ ? CNT_VIS2 : CNT_VIS];
+            k_vis_bin<<<cfg.sms * 3, kBlock, 0, st>>>(fv, rb.vis_ray_o, rb.vis_ray_d, count); LB_LAUNCH_CHECK();
+            k_visibility_sorted<<<grid, kBlock, 0, st>>>(fv, bvh, rb.vis_ray_o, rb.vis_ray_d, count, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
+        } else {
+            k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
+        }
+        lap("restir_visibility");
+    };
+    visibility();
     if (a.temporal) {
         seed = wang_hash(seed);
         k_temporal<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
@@ -440,8 +556,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
         lap("restir_spatial");
-        k_visibility_shade<<<grid, kBlock, 0, st>>>(fv, bvh, &fv.counters[CNT_TICKET0 + ticket++], shaded, &fv.stats[STAT_VIS], cfg.trace_any); LB_LAUNCH_CHECK();
-        lap("restir_visibility");
+        visibility();
         k_combine<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, from, wang_hash(seed)); LB_LAUNCH_CHECK();
         lap("restir_combine");
     }

@@ -101,6 +101,7 @@ struct Tracer {
     uint2 cur;
     int sp;
     bool found; uint32_t bi, bp; float bu, bv;
+    bool dropped;               // set by push() on overflow; owned by the driver (not reset per ray)
     uint2* stack;               // kTraceStack entries of thread-local memory owned by the driver (kept out of this struct so that the
                                 // scalar state above is promoted to registers)
 
@@ -116,7 +117,10 @@ struct Tracer {
     }
     LB_D bool is_node() const { return cur.y > 0x00FFFFFFu; }
     LB_D bool is_tri() const { return cur.y != 0u && cur.y <= 0x00FFFFFFu; }
-    LB_D void push(const uint2& g) { if (sp < kTraceStack) stack[sp++] = g; }
+    // A full stack drops the group — a possibly wrong hit — so it is never silent: `dropped` reaches the frame's CNT_STACK_OVERFLOW counter
+    // (lb_frame_counters "stack_overflows", asserted 0 by the tests), and the scene commit refuses hierarchies deeper than the stack can
+    // hold (one pending sibling group per level + one transient entry: levels + 2 <= kTraceStack, lb_api.cu commit_scene).
+    LB_D void push(const uint2& g) { if (sp < kTraceStack) stack[sp++] = g; else dropped = true; }
     // makes `cur` non-empty from the stack; false = traversal finished
     LB_D bool refill_group() {
         if (cur.y != 0u) return true;
@@ -215,11 +219,12 @@ struct Tracer {
 template <bool ANY>
 LB_D bool bvh8_trace(const BvhView& bvh, const float3& o, const float3& d, float tmin, float tmax, HitInfo& hit) {
     uint2 stack_mem[kTraceStack];
-    Tracer tr; tr.stack = stack_mem; tr.begin(bvh, o, d, tmin, tmax);
+    Tracer tr; tr.stack = stack_mem; tr.dropped = false; tr.begin(bvh, o, d, tmin, tmax);
     while (tr.refill_group()) {
         if (tr.is_node()) tr.node_step(bvh);
         else if (tr.template tri_step<ANY>(bvh)) return true;
     }
+    if (tr.dropped && bvh.overflow) atomicAdd(bvh.overflow, 1u);
     if (ANY) return false;
     if (tr.found) tr.result(hit);
     return tr.found;
@@ -236,7 +241,7 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint2 stack_mem[kTraceStack];
-    Tracer tr; tr.stack = stack_mem; tr.cur = make_uint2(0u, 0u); tr.sp = 0;
+    Tracer tr; tr.stack = stack_mem; tr.cur = make_uint2(0u, 0u); tr.sp = 0; tr.dropped = false;
     uint32_t item = 0u; bool live = false, exhausted = false;
     // A finished ray's result is consumed (job.done: for shadow / visibility rays a dependent load + read-modify-write) when its lane is
     // refilled, together with the other finished lanes of the warp, not at the moment it finishes: the warp then waits for that memory
@@ -282,6 +287,7 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
         if (live && !tr.refill_group()) { if (Job::kDeferDone) { fin = true; fin_hit = ANY ? false : tr.found; } else job.done(item, ANY ? false : tr.found, tr); live = false; }
     }
     if (fin) job.done(item, fin_hit, tr);
+    if (tr.dropped && bvh.overflow) atomicAdd(bvh.overflow, 1u);
 }
 
 } // namespace lb
