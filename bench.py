@@ -13,7 +13,8 @@ with temporal + spatial reuse, static camera (temporal reuse active after the wa
   N > 1  : sample sharding — every rank renders its own K frames with a disjoint frameCount stream into its
            fp32 accumulation buffer; ONE NCCL reduce of that buffer (inside the timed region) produces the image. scaling=weak.
   --impl reference : the CPU implementation of the same path (the oracle port; the reference itself has no CPU renderer and
-           its OptiX trace cannot be built here) on all host threads, each step one frame of a bounded sample (320x180).
+           its OptiX trace cannot be built here) on all host threads, on the SAME configuration: every step one full 2560x1440 frame
+           (about 3 s on 16 threads; --sample-width / --sample-height shrink it on a small host).
 """
 from __future__ import annotations
 
@@ -32,7 +33,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 METRIC = "Mrays/sec @1440p 1spp 3-bounce ReSTIR (ms/frame in ms_per_step)"
-SAMPLE_W, SAMPLE_H = 320, 180
+HISTORY_FRAMES = 8          # frames rendered before the warm-up on both arms: the temporal ReSTIR history of a static camera is filled
 # algorithmic bytes per unit (DESIGN.md "roofline"): what a stage must move per ray / pixel, fp32 payloads, every field once
 ALG_BYTES = {"raygen": 40.0, "extend": 40.0, "shadow": 44.0, "extract": 232.0, "motion": 20.0, "nee": 224.0, "bounce": 216.0,
              "ris": 256.0, "vis_gen": 288.0, "vis_trace": 32.0, "res_shade": 96.0, "temporal": 612.0, "spatial": 336.0, "combine": 416.0, "merge": 84.0}
@@ -73,8 +74,11 @@ def stage_table(stage_ms, fc, npix, depth, peak, traffic):
         kernel, nbytes, how = units[stage]
         gbs = nbytes / (ms * 1e-3) / 1e9
         t = traffic.get(kernel)
+        # dram_frac: the measured DRAM traffic of the stage (ncu capture named in traffic_capture) over this run's stage time, as a fraction of
+        # the measured HBM peak — the honest utilisation figure where the algorithmic bytes (the reference's AoS records) exceed what the SoA
+        # planes actually move
         rows.append({"stage": stage, "kernel": kernel, "ms_per_frame": ms, "share_of_frame": ms / total, "alg_bytes": nbytes, "alg_bytes_how": how,
-                     "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "traffic": t})
+                     "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "traffic": t, "dram_frac": (t / (ms * 1e-3) / 1e9 / peak) if t else None})
     return rows
 
 
@@ -140,8 +144,8 @@ class DevPtr:
         self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
 
 
-def cpu_run(args, steps, warmup, threads=None):
-    """The CPU port of the path (oracle) on a bounded sample of the workload: same scene, 320x180."""
+def cpu_run(args, steps, warmup, width, height, threads=None, history=HISTORY_FRAMES):
+    """The CPU port of the path (oracle) on the workload's scene at width x height: `history` + `warmup` untimed frames, then `steps` timed."""
     import __graft_entry__ as ge
     from lumenrenderer_b200 import api
     ob = ge.oracle_bindings()
@@ -150,38 +154,44 @@ def cpu_run(args, steps, warmup, threads=None):
     lib.lo_set_num_threads(int(threads or os.cpu_count() or 1))       # torchrun exports OMP_NUM_THREADS=1: ask for all host threads explicitly
     cores = int(lib.lo_num_threads())
     scene = workload_scene(args)
-    r = api.Renderer(ob, settings(args, SAMPLE_W, SAMPLE_H))
+    r = api.Renderer(ob, settings(args, width, height))
     r.load_scene(scene)
     t_build = time.time(); r.read_lights(); t_build = time.time() - t_build       # commits the scene (BVH build, light list)
-    r.render_frames(max(warmup, 1))
+    r.render_frames(history + max(warmup, 1))
     rays, t0 = 0, time.time()
     for _ in range(steps):
         r.render_frames(1); rays += rays_of(r.frame_counters())
     dt = time.time() - t0
     r.close()
+    full = (width, height) == (args.width, args.height)
     return {"mrays": rays / dt / 1e6, "ms_per_step": dt / steps * 1e3, "cores": cores, "rays_per_step": rays / steps, "scene_build_s": t_build,
-            "sample": f"same atrium scene, {SAMPLE_W}x{SAMPLE_H} (1/64 of the pixels), depth {args.depth}, ReSTIR, {steps} frames after {max(warmup, 1)} warm-up"}
+            "sample": (f"the full workload: same atrium scene, {width}x{height}" if full else
+                       f"same atrium scene, {width}x{height} ({width * height / (args.width * args.height):.4f} of the pixels)") +
+                      f", depth {args.depth}, ReSTIR, {steps} timed frames after {history} history + {max(warmup, 1)} warm-up frames, {cores} thread(s)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_run(args, args.steps, args.warmup)
+    w, h = args.sample_width or args.width, args.sample_height or args.height
+    # history frames cost ~3 s each on the CPU: two are enough for the temporal pass to find a previous frame; the timed frames are steady state
+    res = cpu_run(args, args.steps, args.warmup, w, h, history=2)
     line = {"impl": "reference", "metric": METRIC, "value": res["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_of(args, SAMPLE_W, SAMPLE_H, "cpu"),
+            "config": config_of(args, w, h),
             "cpu_baseline": {"value": res["mrays"], "unit": "Mrays/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
             "e2e": {"value": res["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "threads": res["cores"], "scene_build_s": res["scene_build_s"],
             "note": "the reference has no CPU renderer and its ray tracing is closed-source OptiX (SURVEY 8c): this arm is the scalar C++ port of the same wavefront algorithm (oracle/), OpenMP over all host threads"}
     print(json.dumps(line), flush=True)
 
 
-def config_of(args, w, h, where):
+def config_of(args, w, h):
+    """The workload, identical on both arms (the GPU arm and --impl reference): how each arm parallelises is not part of it."""
     return {"workload": f"C2 procedural Sponza-class atrium (detail {args.detail}), {w}x{h}, 1 spp, depth {args.depth} (3 bounces), ReSTIR 32 candidates + temporal + 2x spatial, static camera",
             "resolution": [w, h], "depth": args.depth, "restir": True, "textures": f"16 x {args.texture_size}^2 RGBA8",
-            "l2": "per-frame working set (~0.9 KB/pixel of SoA planes, 3.3 GB at 1440p) is far larger than the 126 MB L2; no explicit flush",
-            "parallelism": f"sample-sharded x{args.gpus}" if where == "gpu" else "OpenMP"}
+            "l2": "per-frame working set (~0.9 KB/pixel of SoA planes, 3.3 GB at 1440p) is far larger than the 126 MB L2; no explicit flush"}
 
 
 def run_gpu(args):
@@ -216,7 +226,8 @@ def run_gpu(args):
         accum = torch.as_tensor(DevPtr(ptr, nbytes // 4), device=torch.device("cuda", local))
         warm = torch.zeros(1024, device="cuda"); dist.all_reduce(warm)          # NCCL communicator warm-up outside the timed region
 
-    r.render_frames(max(args.warmup, 3))            # >= 3 warm-up frames; also fills the temporal ReSTIR history
+    r.render_frames(HISTORY_FRAMES)                 # temporal ReSTIR history of the static camera (>= 8 frames), before the warm-up proper
+    r.render_frames(max(args.warmup, 3))            # >= 3 warm-up frames
     r.synchronize()
     counters = r.frame_counters()
     tris, lights, bvh_bytes, launches = counters["triangles"], counters["lights"], counters["bvh_bytes"], counters["kernel_launches"]
@@ -292,9 +303,10 @@ def run_gpu(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = {}
+        traffic, traffic_capture = {}, None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum per frame and kernel, from the committed `ncu --set full` capture of this bench command
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_frame"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic, traffic_capture = tj["dram_bytes_per_frame"], {"source": tj.get("source"), "note": tj.get("note")}
         except Exception:
             pass
         stage_ms["restir"] = sum(v for k, v in stage_ms.items() if k.startswith("restir_"))
@@ -307,26 +319,36 @@ def run_gpu(args):
         # `roofline`: the kernel where most of the frame goes. `roofline_extend`: the traversal kernel the north star asks to be reported
         # against HBM (it is latency / issue bound on an L2-resident BVH; see profiles/ for the stall breakdown).
         roofline = {"kernel": top["kernel"], "stage": top["stage"], "bound": "hbm", "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
-                    "peak_source": peak_source, "traffic": top["traffic"], "alg_bytes_per_frame": top["alg_bytes"], "alg_bytes_how": top["alg_bytes_how"],
+                    "peak_source": peak_source, "traffic": top["traffic"], "traffic_capture": traffic_capture, "dram_frac": top["dram_frac"], "alg_bytes_per_frame": top["alg_bytes"], "alg_bytes_how": top["alg_bytes_how"],
                     "ms_per_frame": top["ms_per_frame"], "share_of_frame": top["share_of_frame"],
                     "note": STAGE_NOTES.get(top["stage"], "") + "; reported against HBM because no stage is a dense contraction"}
         roofline_extend = {"kernel": "k_extend (BVH8 traversal, all waves of a frame)", "bound": "hbm", "achieved": ext["achieved"], "peak": peak, "unit": "GB/s", "frac": ext["frac"],
-                           "peak_source": peak_source, "traffic": ext["traffic"], "alg_bytes_per_ray": ALG_BYTES["extend"], "rays_per_launch_avg": fc["extend_rays"] / args.depth,
+                           "peak_source": peak_source, "traffic": ext["traffic"], "traffic_capture": traffic_capture, "dram_frac": ext["dram_frac"], "alg_bytes_per_ray": ALG_BYTES["extend"], "rays_per_launch_avg": fc["extend_rays"] / args.depth,
                            "ms_per_frame": ext["ms_per_frame"], "share_of_frame": ext["share_of_frame"], "mrays_per_s": fc["extend_rays"] / (ext["ms_per_frame"] * 1e-3) / 1e6}
+        # the whole frame against HBM: every stage's algorithmic bytes over the device time of a frame (the timed region above, not the sum of stages)
+        frame_ms = ms / args.steps
+        alg_total = sum(r["alg_bytes"] for r in table)
+        dram_total = sum(r["traffic"] for r in table if r["traffic"]) or None
+        roofline_frame = {"bound": "hbm", "alg_bytes_per_frame": alg_total, "achieved": alg_total / (frame_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": alg_total / (frame_ms * 1e-3) / 1e9 / peak, "traffic": dram_total, "traffic_capture": traffic_capture,
+                          "dram_frac": (dram_total / (frame_ms * 1e-3) / 1e9 / peak) if dram_total else None, "ms_per_frame": frame_ms}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            c = cpu_run(args, 3, 1)
-            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "ms_per_sample_frame": c["ms_per_step"]}
+            # all host threads on the full workload (3 frames of about 3 s), one thread on 1/16 of the pixels (3 frames of about 2.5 s)
+            c = cpu_run(args, 3, 1, W, H, history=2)
+            c1 = cpu_run(args, 3, 1, W // 4, H // 4, threads=1, history=2)
+            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "ms_per_sample_frame": c["ms_per_step"],
+                   "single_thread": {"value": c1["mrays"], "unit": "Mrays/s", "cores": 1, "sample": c1["sample"], "ms_per_sample_frame": c1["ms_per_step"]}}
         line = {"metric": METRIC, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_of(args, W, H, "gpu"),
+                "config": config_of(args, W, H), "parallelism": f"sample-sharded x{world}", "history_fill_frames": HISTORY_FRAMES,
                 "fps": args.steps / (ms * 1e-3), "samples_per_s": W * H * args.steps * world / (ms * 1e-3), "rays_per_frame": rays_per_frame,
                 "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
                 "overlap": {"mode": int(os.environ.get("LB_OVERLAP", "5")), "ms_per_frame_serialised": serial_ms,
                             "note": "mask: bit 0 = shadow rays of bounce wave d on a side stream under the extend launch of wave d+1; bit 2 = ReSTIR chain launched after the first bounce wave, later waves beside it (default 5); bit 1 (off, measured slower) = ReSTIR chain beside all bounce waves; stage_ms / roofline_kernels are always exclusive times measured with mode 0"},
-                "roofline": roofline, "roofline_extend": roofline_extend, "roofline_kernels": table, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
+                "roofline": roofline, "roofline_frame": roofline_frame, "roofline_extend": roofline_extend, "roofline_kernels": table, "stage_ms": stage_ms, "cpu_baseline": cpu, "clocks": clocks, "output_finite": finite}
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
@@ -387,7 +409,7 @@ def run_bands(args):
         rendered_rows = sum(b[3] - b[2] for b in bands)
         line = {"metric": METRIC, "mode": "bands", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "fps": args.steps / (ms * 1e-3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config_of(args, W, H, "gpu"), parallelism=f"row bands x{world} with a {sharding.RESTIR_HALO}-row ReSTIR halo, gather on rank 0"),
+                "config": dict(config_of(args, W, H), parallelism=f"row bands x{world} with a {sharding.RESTIR_HALO}-row ReSTIR halo, gather on rank 0"),
                 "bands": [list(b) for b in bands], "rows_rendered_over_rows_owned": rendered_rows / H, "gather_bytes_per_step": (H - (y1 - y0)) * W * 16,
                 "gpu_launches": fc["kernel_launches"] * args.steps, "clocks": clocks, "output_finite": finite}
         print(json.dumps(line), flush=True)
@@ -408,6 +430,8 @@ def main():
     ap.add_argument("--detail", type=float, default=0.78)
     ap.add_argument("--texture-size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-width", type=int, default=0, help="--impl reference: render this width instead of --width (a bounded sample for small hosts)")
+    ap.add_argument("--sample-height", type=int, default=0)
     ap.add_argument("--mode", default="samples", choices=["samples", "bands"],
                     help="multi-GPU partitioning: independent sample streams + one reduce (default, weak scaling) or row bands of one frame + one gather (strong scaling)")
     args = ap.parse_args()

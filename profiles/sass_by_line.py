@@ -32,7 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rep", required=True); ap.add_argument("--obj", required=True); ap.add_argument("--kernel", required=True)
     ap.add_argument("--instance", type=int, default=0); ap.add_argument("--top", type=int, default=40)
-    ap.add_argument("--symbol", help="substring of the mangled function name in the object (defaults to --kernel); needed for template instances")
+    ap.add_argument("--by-samples", action="store_true"); ap.add_argument("--symbol", help="substring of the mangled function name in the object (defaults to --kernel); needed for template instances")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", "--kernel-name", f"regex:{a.kernel}", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -49,7 +49,7 @@ def main():
         e = agg[loc]; n = int(r[ia]); e[0] += n; e[1] += n * float(r[it]); e[2] += int(r[isamp])
     print(f"{a.kernel} instance {a.instance}: {tot / 1e6:.1f} M warp instructions, {stot} samples")
     src_cache = {}
-    for loc, (n, thr, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[: a.top]:
+    for loc, (n, thr, s) in sorted(agg.items(), key=lambda kv: -(kv[1][2] if a.by_samples else kv[1][0]))[: a.top]:
         text = ""
         if loc:
             path = os.path.join("lumenrenderer_b200/csrc", loc[0])
