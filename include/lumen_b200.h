@@ -79,7 +79,9 @@ typedef struct LbSettings {
      * band_row0 * width must be a multiple of 256 (the RIS light-bag group, ReSTIRKernels.cu:423). */
     uint32_t band_row0;
     uint32_t band_full_height;
-    uint32_t reserved[3];
+    uint32_t restir_unbiased;  /* !ReSTIRSettings::enableBiased (ReSTIRData.h:63; the reference ships `enableBiased = true`, so 0 is its behaviour):
+                                  1 = temporal and spatial reuse take the CombineUnbiased branches, ReSTIRKernels.cu:905-970, :1123-1198 */
+    uint32_t reserved[2];
 } LbSettings;
 
 /* LumenRenderer::MaterialData, LM/Renderer/LumenRenderer.h:64-112 (defaults :66-82).

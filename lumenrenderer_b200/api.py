@@ -30,7 +30,7 @@ class LbSettings(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("blend_output", C.c_uint32),
                 ("restir", C.c_uint32), ("restir_temporal", C.c_uint32), ("restir_spatial", C.c_uint32),
                 ("device", C.c_int32), ("volume_mode", C.c_uint32), ("first_frame_count", C.c_uint32),
-                ("frame_count_stride", C.c_uint32), ("band_row0", C.c_uint32), ("band_full_height", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("frame_count_stride", C.c_uint32), ("band_row0", C.c_uint32), ("band_full_height", C.c_uint32), ("restir_unbiased", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class LbMaterialDesc(C.Structure):
@@ -121,6 +121,7 @@ class Settings:
     frame_count_stride: int = 0
     band_row0: int = 0
     band_full_height: int = 0
+    restir_unbiased: bool = False
 
     def to_c(self) -> LbSettings:
         s = LbSettings()

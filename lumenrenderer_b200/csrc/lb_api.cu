@@ -415,7 +415,7 @@ struct Renderer {
         auto run_restir = [&](bool on_side) {
             RestirArgs ra{seed0, (int)st.restir_temporal, (int)st.restir_spatial};
             static const int ris_simple = []() { const char* e = getenv("LB_RIS_SIMPLE"); return (!e || atoi(e) != 0) ? 1 : 0; }();
-            ra.ris_simple = ris_simple;
+            ra.ris_simple = ris_simple; ra.unbiased = st.restir_unbiased ? 1 : 0;
             RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr};
             LaunchCfg cr = c;
             if (on_side) {

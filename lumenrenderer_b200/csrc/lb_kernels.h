@@ -57,6 +57,7 @@ struct ShadeArgs {
 
 struct RestirArgs {
     uint32_t seed; int temporal, spatial;
+    int unbiased = 0;                 // LbSettings::restir_unbiased: the CombineUnbiased branches of temporal / spatial reuse
     int ris_simple = 1;               // RIS may take the lean BSDF evaluation for rows of simple materials (LB_RIS_SIMPLE=0: always the general one)
     void (*lap)(void* user, const char* stage) = nullptr; void* lap_user = nullptr;      // per-kernel timing marks (CUDA events of the renderer)
 };

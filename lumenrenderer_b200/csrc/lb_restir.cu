@@ -56,6 +56,34 @@ LB_D Reservoir combine_pair(const Reservoir& a, const Reservoir& b, const Surfac
     return out;
 }
 
+// CombineUnbiased over two reservoirs (ReSTIRKernels.cu:1123-1198; LbSettings::restir_unbiased — dead in the reference's shipped build): the
+// selected sample is re-evaluated at the pixel each reservoir was generated at, and only reservoirs for whose pixel it has a non-zero target
+// pdf count towards the normalisation
+LB_D Reservoir combine_pair_unbiased(const Reservoir& a, const Reservoir& b, const Surface& px, const Surface& from_a, const Surface& from_b, uint32_t seed) {
+    Reservoir out = reservoir_zero(); int total = 0;
+    {
+        const BsdfCtx ctx = surface_ctx(px);
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            const Reservoir& q = k ? b : a;
+            LightSample rs; resample(q.s, px.pos, px.normal, ctx, rs);
+            reservoir_update(out, rs, (float)q.count * q.weight * rs.pdf, seed); total += q.count;
+        }
+    }
+    out.count = total;
+    int correction = 0;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const Surface& f = k ? from_b : from_a;
+        const BsdfCtx ctx = surface_ctx(f);
+        LightSample rs; resample(out.s, f.pos, f.normal, ctx, rs);
+        if (rs.pdf > 0) correction += k ? b.count : a.count;
+    }
+    const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);
+    out.weight = (1.f / fmaxf(out.s.pdf, FLT_EPSILON)) * (m * out.weight_sum);
+    return out;
+}
+
 // Pixel order of the gather kernels (temporal / spatial reuse): the image is cut into 32x8-pixel tiles walked in vertical strips
 // 16 tiles (512 px) wide; the unit of work is one 32-pixel ROW of a tile, handed out to WARPS by a device ticket in tile order (row r of
 // tile t is item 8 t + r). The warps in flight therefore always hold consecutive rows of a few consecutive tiles, whatever the grid /
@@ -413,6 +441,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_visibility_sorted(FrameView fv, B
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
+template <bool UNBIASED>
 __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView fv, uint32_t* ticket, uint32_t seed, float shaded) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
@@ -437,7 +466,10 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView
             float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
         }
         prev.count = min(prev.count, cur.count * 20);
-        reservoir_store(fv.res_cur, np, i, combine_pair(prev, cur, sc, wang_hash(seed + i + fv.pix0)));
+        if (UNBIASED) {
+            Surface sp; surface_load_shading(fv.surf_prev, np, ti, sp);
+            reservoir_store(fv.res_cur, np, i, combine_pair_unbiased(prev, cur, sc, sp, sc, wang_hash(seed + i + fv.pix0)));
+        } else reservoir_store(fv.res_cur, np, i, combine_pair(prev, cur, sc, wang_hash(seed + i + fv.pix0)));
     }
 }
 
@@ -448,6 +480,7 @@ LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i)
     return p;
 }
 
+template <bool UNBIASED>
 __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
@@ -496,7 +529,23 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView 
                 total += qcount;
                 cur = nxt;
             }
-            acc.count = total; reservoir_update_weight(acc);
+            acc.count = total;
+            if (!UNBIASED) reservoir_update_weight(acc);
+            else {
+                // the unbiased branch, ReSTIRKernels.cu:905-970: the selected sample re-evaluated at every accepted neighbour; the reference adds
+                // the sample count of the OUTPUT buffer's stale reservoir of this pixel (a_ReservoirsOut[index].sampleCount, :951) — as written
+                const int stale = __float_as_int(out[i].z);
+                int correction = 0;
+#pragma unroll 1
+                for (int k = 0; k < count; ++k) {
+                    Surface pk; surface_load_shading(fv.surf_cur, np, nb[k], pk);
+                    const BsdfCtx ck = surface_ctx(pk);
+                    LightSample rs; resample(acc.s, pk.pos, pk.normal, ck, rs);
+                    if (rs.pdf > 0) correction += stale;
+                }
+                const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);
+                acc.weight = (1.f / fmaxf(acc.s.pdf, FLT_EPSILON)) * (m * acc.weight_sum);
+            }
             reservoir_store(out, np, i, acc);
         } else {
             const float4 r0 = out[i];                                   // Reservoir::Reset keeps the stored sample
@@ -545,14 +594,18 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     visibility();
     if (a.temporal) {
         seed = wang_hash(seed);
-        k_temporal<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded); LB_LAUNCH_CHECK();
+        if (a.unbiased) k_temporal<true><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded);
+        else k_temporal<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], seed, shaded);
+        LB_LAUNCH_CHECK();
         lap("restir_temporal");
     }
     if (a.spatial) {
         seed = wang_hash(seed);
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-            k_spatial<<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed); LB_LAUNCH_CHECK();
+            if (a.unbiased) k_spatial<true><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            else k_spatial<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
         lap("restir_spatial");

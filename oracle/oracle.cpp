@@ -12,6 +12,7 @@
 #include "lo_math.h"
 #include "lo_bsdf.h"
 #include "lo_trace.h"
+#include <cfloat>
 #include <vector>
 #include <string>
 #include <memory>
@@ -75,6 +76,11 @@ struct VolumeHit { float t0 = -1, t1 = -1; float density = 0; int vinst = -1; };
 
 constexpr uint32_t kNumBags = 50, kLightsPerBag = 1000, kPrimarySamples = 32, kSpatialSamples = 5, kSpatialRadius = 30, kSpatialIterations = 2;   // ReSTIRData.h:34-56
 constexpr float kSimilarCos = 0.72222222223f;
+
+// lo_kat_rand_right_to_left(1) (tests only): the three RandomFloat(seed) ARGUMENTS of the reference's SampleBSDF call (GPUShadeIndirect.cu:99-101)
+// are evaluated in unspecified order (hazard 3) — the canonical choice is left to right, the host build of the reference (g++, x86-64) evaluates
+// them right to left. With the switch the oracle's ShadeIndirect is bit-identical to that host build, which pins everything around the call.
+static bool g_kat_rand_right_to_left = false;
 
 struct Renderer {
     LbSettings st{};
@@ -421,6 +427,27 @@ struct Renderer {
         out.count = total; out.update_weight(); dst = out;
     }
 
+    // CombineUnbiased, ReSTIRKernels.cu:1123-1198 (dead in the reference's build: `constexpr bool enableBiased = true`, ReSTIRKernels.cu:880 —
+    // restated and pinned for completeness, selected by LbSettings::restir_unbiased). `from[i]` is the pixel reservoir i was generated at:
+    // the selected sample is re-evaluated there, and only reservoirs for whose pixel it has a non-zero target pdf count towards M.
+    static void combine_unbiased(Reservoir& dst, const Surface& px, int n, const Reservoir* in, const Surface* from, uint32_t seed) {
+        Reservoir out; int total = 0;
+        for (int i = 0; i < n; ++i) {
+            LightSample rs; resample(in[i].sample, px, rs);
+            const float w = (float)in[i].count * in[i].weight * rs.pdf;
+            out.update(rs, w, seed); total += (int)in[i].count;
+        }
+        out.count = total;
+        int correction = 0;
+        for (int i = 0; i < n; ++i) {
+            LightSample rs; resample(out.sample, from[i], rs);
+            if (rs.pdf > 0) correction += (int)in[i].count;
+        }
+        const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);                 // MINFLOAT = std::numeric_limits<float>::epsilon(), ReSTIRData.h:12
+        out.weight = (1.f / fmaxf(out.sample.pdf, FLT_EPSILON)) * (m * out.weight_sum);
+        dst = out;
+    }
+
     // ------------------------------------------------------------------ NEE: ShadeDirect, GPUShadeDirect.cu:42-153
     bool shade_direct_pixel(const Surface& s, uint32_t pixel_index, uint32_t seed_in, int chan, const VolumeHit* vh, std::vector<ShadowRay>* vol_rays, ShadowRay& out) {
         uint32_t seed = wang_hash(seed_in + pixel_index + pix0());
@@ -484,7 +511,9 @@ struct Renderer {
         if (s.flags) return false;
         if (fabsf(dot(s.normal, s.incoming)) < 3.f * kBsdfEps) return false;
         V3 wi = v3(0); float pdf = 0.f; bool specular = false;
-        const float r0 = rand_f(seed), r1 = rand_f(seed), r2 = rand_f(seed);   // left to right, hazard 3
+        float r0, r1, r2;
+        if (!g_kat_rand_right_to_left) { r0 = rand_f(seed); r1 = rand_f(seed); r2 = rand_f(seed); }      // left to right, hazard 3 (canonical; what nvcc's device front end does)
+        else { r2 = rand_f(seed); r1 = rand_f(seed); r0 = rand_f(seed); }                                // what g++ makes of the same call in the host build of the reference (tests only)
         const V3 bsdf = disney_sample(s.mat, s.normal, s.normal, s.tangent, -s.incoming, 1.f, r0, r1, r2, wi, pdf, specular);
         if (pdf <= kBsdfEps || std::isnan(pdf + bsdf.x + bsdf.y + bsdf.z)) return false;
         const float rr = specular ? 1.f : fminf(fmaxf(bsdf.x, fmaxf(bsdf.y, bsdf.z)), 1.f);
@@ -497,6 +526,13 @@ struct Renderer {
     }
 
     // ------------------------------------------------------------------ ReSTIR::Run, PT/Framework/ReSTIR.cpp:65-233
+    // GenerateShadowRay, ReSTIRKernels.cu:546-582: the ray of a reservoir's sample (origin = the surface position); false = no ray
+    static bool visibility_ray(const Surface& s, const Reservoir& r, V3& d, float& tmax) {
+        if (s.flags || !(r.weight > 0.f)) return false;
+        d = r.sample.position - s.pos; const float l = length(d); d /= l;
+        tmax = l - 0.05f;
+        return true;
+    }
     void visibility_and_shade(std::vector<Reservoir>& res, const std::vector<Surface>& surf) {
         // GenerateShadowRay ReSTIRKernels.cu:546-582 + ReSTIRRayGen WaveFrontShaders.cu:181-216 + ShadeReservoirs :600-665
         const float shaded = 1.f + (st.restir_temporal ? 1.f : 0.f) + (st.restir_spatial ? 1.f : 0.f);
@@ -504,10 +540,10 @@ struct Renderer {
         #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nrays)
         for (int64_t i = 0; i < (int64_t)npix(); ++i) {
             const Surface& s = surf[i]; Reservoir& r = res[i];
-            if (!s.flags && r.weight > 0.f) {
-                V3 d = r.sample.position - s.pos; const float l = length(d); d /= l;
+            V3 d; float tmax;
+            if (visibility_ray(s, r, d, tmax)) {
                 ++nrays;
-                if (bvh.any(s.pos, d, 0.1f, l - 0.05f)) r.weight = 0.f;
+                if (bvh.any(s.pos, d, 0.1f, tmax)) r.weight = 0.f;
             }
             if (r.weight > 0.f) {
                 const V3 c = r.sample.contribution * (r.weight / shaded);
@@ -516,15 +552,16 @@ struct Renderer {
         }
         counters[2] += nrays;
     }
-    void restir_run(const std::vector<Surface>& cur, const std::vector<Surface>& prev, uint32_t a_seed) {
-        const uint32_t n = npix();
-        std::vector<Reservoir>& R = reservoirs[res_cur]; std::vector<Reservoir>& Rprev = reservoirs[res_cur == 1 ? 0 : 1];
-        uint32_t seed = wang_hash(a_seed);
-        // FillLightBagsInternal, ReSTIRKernels.cu:343-370
+    // ---- the passes of ReSTIR::Run as separate stages over explicit buffers (restir_run below chains them; the known-answer taps at the end
+    //      of this file call them one by one against the reference's kernels compiled in place)
+    // FillLightBagsInternal, ReSTIRKernels.cu:343-370
+    void fill_bags(uint32_t a_seed) {
         bags.resize(kNumBags * kLightsPerBag);
         for (uint32_t i = 0; i < kNumBags * kLightsPerBag; ++i) { uint32_t s = wang_hash(a_seed + wang_hash(i)); const float r = rand_f(s); cdf_get(r, bags[i].light, bags[i].pdf); }
-        // PickPrimarySamplesInternal, ReSTIRKernels.cu:402-522
-        seed = wang_hash(seed);
+    }
+    // PickPrimarySamplesInternal, ReSTIRKernels.cu:402-522
+    void ris_stage(const std::vector<Surface>& cur, std::vector<Reservoir>& R, uint32_t seed) const {
+        const uint32_t n = (uint32_t)cur.size();
         #pragma omp parallel for schedule(dynamic, 256)
         for (int64_t i = 0; i < (int64_t)n; ++i) {
             uint32_t bag_seed = wang_hash(seed + ((uint32_t)i + pix0()) / 256u);                       // hazard 1: block index instead of %smid
@@ -546,74 +583,101 @@ struct Renderer {
             }
             fresh.update_weight(); R[i] = fresh;
         }
+    }
+    // CombineTemporalSamplesInternal, ReSTIRKernels.cu:1015-1121. `direct` receives the shading of the previous reservoir (:1105, ShadeReservoirs)
+    void temporal_stage(const std::vector<Surface>& cur, const std::vector<Surface>& prev, std::vector<Reservoir>& R, const std::vector<Reservoir>& Rprev,
+                        const std::vector<V2>& mv, std::vector<V4>& direct, uint32_t seed, float shaded) const {
+        const uint32_t n = (uint32_t)cur.size();
+        #pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const int cy = (int)(i / st.width), cx = (int)(i - (int64_t)cy * st.width);
+            const int mx = (int)roundf((float)st.width * mv[i].x), my = (int)roundf((float)full_height() * mv[i].y);
+            int ty = cy + my, tx = cx + mx; int64_t ti = i;
+            if (ty >= 0 && ty < (int)st.height && tx >= 0 && tx < (int)st.width) ti = (int64_t)ty * st.width + tx;
+            const Surface& sp = prev[ti]; const Surface& sc = cur[i];
+            if (sp.flags || sc.flags) continue;
+            Reservoir pair[2] = {Rprev[ti], R[i]};
+            const float d1 = sp.t, d2 = sc.t; const float pct = fabsf(d1 - d2) / ((d1 + d2) / 2.f);
+            const float ang = dot(sp.normal, sc.normal);
+            if (!(pct < 0.10f && ang > kSimilarCos)) continue;
+            if (Rprev[ti].weight > 0.f) { const V3 c = Rprev[ti].sample.contribution * (Rprev[ti].weight / shaded); V4& o = direct[i]; o.x += c.x; o.y += c.y; o.z += c.z; }
+            pair[0].count = std::min(pair[0].count, pair[1].count * 20);
+            if (st.restir_unbiased) { const Surface from[2] = {sp, sc}; combine_unbiased(R[i], sc, 2, pair, from, wang_hash(seed + (uint32_t)i + pix0())); }
+            else combine_biased(R[i], 2, pair, sc, wang_hash(seed + (uint32_t)i + pix0()));
+        }
+    }
+    // SpatialNeighbourSamplingInternal, ReSTIRKernels.cu:787-980 (one iteration; driver :745-785)
+    void spatial_pass(const std::vector<Surface>& cur, const std::vector<Reservoir>& In, std::vector<Reservoir>& Out, uint32_t seed) const {
+        const uint32_t n = (uint32_t)cur.size();
+        #pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const Surface& sc = cur[i]; if (sc.flags) continue;
+            uint32_t s = wang_hash(seed + (uint32_t)i + pix0());
+            const int y = (int)(i / st.width), x = (int)(i - (int64_t)y * st.width);
+            const Surface* pd[kSpatialSamples]; const Reservoir* pr[kSpatialSamples]; int count = 0;
+            for (uint32_t k = 0; k < kSpatialSamples; ++k) {
+                const int ny = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + y;
+                const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
+                if (nx < 0 || nx >= (int)st.width || ny < 0 || ny >= (int)st.height) continue;
+                const int64_t ni = (int64_t)ny * st.width + nx;
+                pd[count] = &cur[ni];
+                if (pd[count]->flags) continue;
+                pr[count] = &In[ni];
+                const float d1 = pd[count]->t, d2 = sc.t; const float pct = fabsf(d1 - d2) / ((d1 + d2) / 2.f);
+                const float ang = dot(pd[count]->normal, sc.normal);
+                if (pct < 0.10f && ang > kSimilarCos) ++count;
+            }
+            if (count > 1) {
+                Reservoir out; long long total = 0;
+                for (int k = 0; k < count; ++k) {
+                    LightSample rs; resample(pr[k]->sample, *pd[0], rs);   // against the FIRST accepted neighbour
+                    const float w = (float)pr[k]->count * pr[k]->weight * rs.pdf;
+                    out.update(rs, w, seed); total += pr[k]->count;        // kernel-wide seed by value (hazard 14)
+                }
+                if (!st.restir_unbiased) { out.count = total; out.update_weight(); }
+                else {
+                    // the unbiased branch (:905-970, dead at the reference's enableBiased = true): the selected sample is re-evaluated at every
+                    // accepted neighbour; the reference adds the sample count of the OUTPUT buffer's stale reservoir of this pixel
+                    // (a_ReservoirsOut[index].sampleCount, :951), not the neighbour's — restated as written
+                    out.count = (int)total; int correction = 0;
+                    for (int k = 0; k < count; ++k) { LightSample rs; resample(out.sample, *pd[k], rs); if (rs.pdf > 0) correction += (int)Out[i].count; }
+                    const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);
+                    out.weight = (1.f / fmaxf(out.sample.pdf, FLT_EPSILON)) * (m * out.weight_sum);
+                }
+                Out[i] = out;
+            } else Out[i].reset();
+        }
+    }
+    // CombineReservoirBuffersInternal, ReSTIRKernels.cu:1407-1436 (always CombineBiased, :1429-1433)
+    void combine_buffers(const std::vector<Surface>& cur, std::vector<Reservoir>& R, const std::vector<Reservoir>& Nb, uint32_t cseed) const {
+        const uint32_t n = (uint32_t)cur.size();
+        #pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            if (cur[i].flags) continue;
+            Reservoir pair[2] = {R[i], Nb[i]};
+            combine_biased(R[i], 2, pair, cur[i], wang_hash(cseed + (uint32_t)i + pix0()));
+        }
+    }
+    void restir_run(const std::vector<Surface>& cur, const std::vector<Surface>& prev, uint32_t a_seed) {
+        std::vector<Reservoir>& R = reservoirs[res_cur]; std::vector<Reservoir>& Rprev = reservoirs[res_cur == 1 ? 0 : 1];
+        uint32_t seed = wang_hash(a_seed);
+        fill_bags(a_seed);
+        seed = wang_hash(seed);
+        ris_stage(cur, R, seed);
         visibility_and_shade(R, cur);
-        // CombineTemporalSamplesInternal, ReSTIRKernels.cu:1015-1121
         if (st.restir_temporal) {
             seed = wang_hash(seed);
-            const float shaded = 1.f + 1.f + (st.restir_spatial ? 1.f : 0.f);
-            #pragma omp parallel for schedule(dynamic, 256)
-            for (int64_t i = 0; i < (int64_t)n; ++i) {
-                const int cy = (int)(i / st.width), cx = (int)(i - (int64_t)cy * st.width);
-                const int mx = (int)roundf((float)st.width * motion[i].x), my = (int)roundf((float)full_height() * motion[i].y);
-                int ty = cy + my, tx = cx + mx; int64_t ti = i;
-                if (ty >= 0 && ty < (int)st.height && tx >= 0 && tx < (int)st.width) ti = (int64_t)ty * st.width + tx;
-                const Surface& sp = prev[ti]; const Surface& sc = cur[i];
-                if (sp.flags || sc.flags) continue;
-                Reservoir pair[2] = {Rprev[ti], R[i]};
-                const float d1 = sp.t, d2 = sc.t; const float pct = fabsf(d1 - d2) / ((d1 + d2) / 2.f);
-                const float ang = dot(sp.normal, sc.normal);
-                if (!(pct < 0.10f && ang > kSimilarCos)) continue;
-                if (Rprev[ti].weight > 0.f) { const V3 c = Rprev[ti].sample.contribution * (Rprev[ti].weight / shaded); V4& o = channel[LB_CHANNEL_DIRECT][i]; o.x += c.x; o.y += c.y; o.z += c.z; }
-                pair[0].count = std::min(pair[0].count, pair[1].count * 20);
-                combine_biased(R[i], 2, pair, sc, wang_hash(seed + (uint32_t)i + pix0()));
-            }
+            temporal_stage(cur, prev, R, Rprev, motion, channel[LB_CHANNEL_DIRECT], seed, 1.f + 1.f + (st.restir_spatial ? 1.f : 0.f));
         }
         if (st.restir_spatial) {
-            // SpatialNeighbourSamplingInternal, ReSTIRKernels.cu:787-980 (biased branch), driver :745-785
             seed = wang_hash(seed);
             std::vector<Reservoir>* from = &R; std::vector<Reservoir>* to = &reservoirs[2];
             for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-                const std::vector<Reservoir>& In = *from; std::vector<Reservoir>& Out = *to;
-                #pragma omp parallel for schedule(dynamic, 256)
-                for (int64_t i = 0; i < (int64_t)n; ++i) {
-                    const Surface& sc = cur[i]; if (sc.flags) continue;
-                    uint32_t s = wang_hash(seed + (uint32_t)i + pix0());
-                    const int y = (int)(i / st.width), x = (int)(i - (int64_t)y * st.width);
-                    const Surface* pd[kSpatialSamples]; const Reservoir* pr[kSpatialSamples]; int count = 0;
-                    for (uint32_t k = 0; k < kSpatialSamples; ++k) {
-                        const int ny = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + y;
-                        const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
-                        if (nx < 0 || nx >= (int)st.width || ny < 0 || ny >= (int)st.height) continue;
-                        const int64_t ni = (int64_t)ny * st.width + nx;
-                        pd[count] = &cur[ni];
-                        if (pd[count]->flags) continue;
-                        pr[count] = &In[ni];
-                        const float d1 = pd[count]->t, d2 = sc.t; const float pct = fabsf(d1 - d2) / ((d1 + d2) / 2.f);
-                        const float ang = dot(pd[count]->normal, sc.normal);
-                        if (pct < 0.10f && ang > kSimilarCos) ++count;
-                    }
-                    if (count > 1) {
-                        Reservoir out; long long total = 0;
-                        for (int k = 0; k < count; ++k) {
-                            LightSample rs; resample(pr[k]->sample, *pd[0], rs);   // against the FIRST accepted neighbour
-                            const float w = (float)pr[k]->count * pr[k]->weight * rs.pdf;
-                            out.update(rs, w, seed); total += pr[k]->count;        // kernel-wide seed by value (hazard 14)
-                        }
-                        out.count = total; out.update_weight(); Out[i] = out;
-                    } else Out[i].reset();
-                }
+                spatial_pass(cur, *from, *to, seed);
                 if (it == 0) { from = &reservoirs[2]; to = &reservoirs[3]; } else std::swap(from, to);
             }
-            std::vector<Reservoir>& Nb = *from;
             visibility_and_shade(R, cur);                                           // on the CURRENT reservoirs again, ReSTIR.cpp:211-212
-            // CombineReservoirBuffersInternal, ReSTIRKernels.cu:1407-1436
-            const uint32_t cseed = wang_hash(seed);
-            #pragma omp parallel for schedule(dynamic, 256)
-            for (int64_t i = 0; i < (int64_t)n; ++i) {
-                if (cur[i].flags) continue;
-                Reservoir pair[2] = {R[i], Nb[i]};
-                combine_biased(R[i], 2, pair, cur[i], wang_hash(cseed + (uint32_t)i + pix0()));
-            }
+            combine_buffers(cur, R, *from, wang_hash(seed));
         }
     }
 
@@ -1006,6 +1070,133 @@ LB_API int lo_resolve_accum(LbRenderer r, uint32_t total) { CHECK_R; if (!total)
 // ---- known-answer taps of the ReSTIR data structures (oracle only; checked against the reference's own ReSTIRData.h compiled for the host,
 // oracle/ref_shim/ref_restir.cpp -> tests/golden/restir_reference.npz). Same signatures as ref_kat_reservoir / ref_kat_cdf.
 LB_API void lo_kat_use_libm_sincos(int on) { lo::g_libm_sincos = on != 0; }
+LB_API void lo_kat_rand_right_to_left(int on) { g_kat_rand_right_to_left = on != 0; }
+// ---- known-answer taps of the radiance-deciding functions (oracle only; checked against the reference's own Resample / CombineBiased /
+// CombineUnbiased / ShadeIndirect / ShadeDirect compiled for the host in place, oracle/ref_shim/ref_kernels.cpp ->
+// tests/golden/kernels_reference.npz). Same signatures and flat layouts as ref_kat_* there.
+static Mat unpack_mat24(const float* m);
+static Surface kat_surface(const float* s, uint32_t px, uint32_t py) {
+    Surface d; d.px = px; d.py = py;
+    d.pos = {s[0], s[1], s[2]}; d.normal = {s[3], s[4], s[5]}; d.gnormal = d.normal; d.tangent = {s[6], s[7], s[8]}; d.incoming = {s[9], s[10], s[11]};
+    d.transport = {s[12], s[13], s[14]}; d.t = s[15]; d.flags = (uint32_t)s[16]; d.mat = unpack_mat24(s + 20);
+    return d;
+}
+static LightSample kat_sample(const float* s) {
+    LightSample l; l.radiance = {s[0], s[1], s[2]}; l.normal = {s[3], s[4], s[5]}; l.position = {s[6], s[7], s[8]}; l.area = s[9];
+    l.contribution = {s[10], s[11], s[12]}; l.pdf = s[13];
+    return l;
+}
+static void kat_put_sample(const LightSample& l, float* o) {
+    o[0] = l.radiance.x; o[1] = l.radiance.y; o[2] = l.radiance.z; o[3] = l.normal.x; o[4] = l.normal.y; o[5] = l.normal.z;
+    o[6] = l.position.x; o[7] = l.position.y; o[8] = l.position.z; o[9] = l.area; o[10] = l.contribution.x; o[11] = l.contribution.y; o[12] = l.contribution.z; o[13] = l.pdf;
+}
+LB_API void lo_kat_resample(const float* samples14, unsigned n, const float* surf44, float* out14) {
+    const Surface px = kat_surface(surf44, 0, 0);
+    for (unsigned k = 0; k < n; ++k) { LightSample out; Renderer::resample(kat_sample(samples14 + 14 * k), px, out); kat_put_sample(out, out14 + 14 * k); }
+}
+LB_API void lo_kat_combine(const float* res17, unsigned n, const float* surf44, const float* surfs44, unsigned seed, int unbiased, float* out17) {
+    const Surface px = kat_surface(surf44, 0, 0);
+    std::vector<Reservoir> in(n); std::vector<Surface> from(n);
+    for (unsigned k = 0; k < n; ++k) {
+        const float* r = res17 + 17 * k; in[k].weight_sum = r[0]; in[k].count = (long long)r[1]; in[k].weight = r[2]; in[k].sample = kat_sample(r + 3);
+        if (unbiased) from[k] = kat_surface(surfs44 + 44 * k, 0, 0);
+    }
+    Reservoir out;
+    if (unbiased) Renderer::combine_unbiased(out, px, (int)n, in.data(), from.data(), seed); else Renderer::combine_biased(out, (int)n, in.data(), px, seed);
+    out17[0] = out.weight_sum; out17[1] = (float)out.count; out17[2] = out.weight; kat_put_sample(out.sample, out17 + 3);
+}
+static void kat_put_reservoir(const Reservoir& r, float* o) { o[0] = r.weight_sum; o[1] = (float)r.count; o[2] = r.weight; kat_put_sample(r.sample, o + 3); }
+static Reservoir kat_reservoir(const float* r) { Reservoir q; q.weight_sum = r[0]; q.count = (long long)r[1]; q.weight = r[2]; q.sample = kat_sample(r + 3); return q; }
+static std::vector<Surface> kat_surfaces(const float* surfs44, unsigned w, unsigned h) {
+    std::vector<Surface> s((size_t)w * h);
+    for (unsigned i = 0; i < w * h; ++i) s[i] = kat_surface(surfs44 + 44 * (size_t)i, i % w, i / w);
+    return s;
+}
+static std::vector<Reservoir> kat_reservoirs(const float* r17, unsigned n) { std::vector<Reservoir> r(n); for (unsigned i = 0; i < n; ++i) r[i] = kat_reservoir(r17 + 17 * (size_t)i); return r; }
+static void kat_lights(Renderer& R, const float* lights16, const float* cdf_weights, unsigned nlights) {
+    float run = 0.f;
+    for (unsigned k = 0; k < nlights; ++k) {
+        const float* l = lights16 + 16 * k; LightTri t;
+        t.p0 = {l[0], l[1], l[2]}; t.p1 = {l[3], l[4], l[5]}; t.p2 = {l[6], l[7], l[8]}; t.normal = {l[9], l[10], l[11]}; t.radiance = {l[12], l[13], l[14]}; t.area = l[15];
+        R.lights.push_back(t); run += cdf_weights[k]; R.cdf.push_back(run);
+    }
+    R.cdf_sum = run;
+}
+// whole ReSTIR stages over a w x h frame (signatures of ref_kat_ris / _visibility_rays / _temporal / _spatial / _combine_buffers; `unbiased` selects
+// LbSettings::restir_unbiased where the reference build has a branch for it)
+LB_API void lo_kat_ris(const float* surfs44, unsigned w, unsigned h, unsigned bag_seed, unsigned ris_seed, const float* lights16, const float* cdf_weights, unsigned nlights,
+                       float* bag_pdf_out, float* bag_p0x_out, float* reservoirs_out) {
+    Renderer R; R.st.width = w; R.st.height = h; kat_lights(R, lights16, cdf_weights, nlights);
+    R.fill_bags(bag_seed);
+    for (size_t i = 0; i < R.bags.size(); ++i) { bag_pdf_out[i] = R.bags[i].pdf; bag_p0x_out[i] = R.lights[R.bags[i].light].p0.x; }
+    const std::vector<Surface> s = kat_surfaces(surfs44, w, h); std::vector<Reservoir> res((size_t)w * h);
+    R.ris_stage(s, res, ris_seed);
+    for (size_t i = 0; i < res.size(); ++i) kat_put_reservoir(res[i], reservoirs_out + 17 * i);
+}
+LB_API unsigned lo_kat_visibility_rays(const float* surfs44, const float* reservoirs17, unsigned w, unsigned h, float* rays8) {
+    const std::vector<Surface> s = kat_surfaces(surfs44, w, h); const std::vector<Reservoir> res = kat_reservoirs(reservoirs17, w * h);
+    unsigned n = 0;
+    for (unsigned i = 0; i < w * h; ++i) {
+        V3 d; float tmax;
+        if (!Renderer::visibility_ray(s[i], res[i], d, tmax)) continue;
+        float* o = rays8 + 8 * (size_t)n++; o[0] = (float)i; o[1] = s[i].pos.x; o[2] = s[i].pos.y; o[3] = s[i].pos.z; o[4] = d.x; o[5] = d.y; o[6] = d.z; o[7] = tmax;
+    }
+    return n;
+}
+LB_API void lo_kat_temporal(const float* cur44, const float* prev44, const float* cur17, const float* prev17, const float* motion2, unsigned w, unsigned h, unsigned seed, int unbiased,
+                            float* cur_out17, float* direct4) {
+    Renderer R; R.st.width = w; R.st.height = h; R.st.restir_unbiased = unbiased ? 1u : 0u;
+    const std::vector<Surface> sc = kat_surfaces(cur44, w, h), sp = kat_surfaces(prev44, w, h);
+    std::vector<Reservoir> rc = kat_reservoirs(cur17, w * h); const std::vector<Reservoir> rp = kat_reservoirs(prev17, w * h);
+    std::vector<V2> mv((size_t)w * h); for (size_t i = 0; i < mv.size(); ++i) mv[i] = {motion2[2 * i], motion2[2 * i + 1]};
+    std::vector<V4> direct((size_t)w * h); for (size_t i = 0; i < direct.size(); ++i) direct[i] = {direct4[4 * i], direct4[4 * i + 1], direct4[4 * i + 2], direct4[4 * i + 3]};
+    R.temporal_stage(sc, sp, rc, rp, mv, direct, seed, 3.f);
+    for (size_t i = 0; i < rc.size(); ++i) { kat_put_reservoir(rc[i], cur_out17 + 17 * i); direct4[4 * i] = direct[i].x; direct4[4 * i + 1] = direct[i].y; direct4[4 * i + 2] = direct[i].z; direct4[4 * i + 3] = direct[i].w; }
+}
+LB_API void lo_kat_spatial(const float* surfs44, const float* in17, unsigned w, unsigned h, unsigned seed, int unbiased, float* out17) {
+    Renderer R; R.st.width = w; R.st.height = h; R.st.restir_unbiased = unbiased ? 1u : 0u;
+    const std::vector<Surface> s = kat_surfaces(surfs44, w, h); const std::vector<Reservoir> in = kat_reservoirs(in17, w * h); std::vector<Reservoir> out = kat_reservoirs(out17, w * h);
+    R.spatial_pass(s, in, out, seed);
+    for (size_t i = 0; i < out.size(); ++i) kat_put_reservoir(out[i], out17 + 17 * i);
+}
+LB_API void lo_kat_combine_buffers(const float* surfs44, float* a17, const float* b17, unsigned w, unsigned h, unsigned seed) {
+    Renderer R; R.st.width = w; R.st.height = h;
+    const std::vector<Surface> s = kat_surfaces(surfs44, w, h); std::vector<Reservoir> a = kat_reservoirs(a17, w * h); const std::vector<Reservoir> b = kat_reservoirs(b17, w * h);
+    R.combine_buffers(s, a, b, seed);
+    for (size_t i = 0; i < a.size(); ++i) kat_put_reservoir(a[i], a17 + 17 * i);
+}
+LB_API unsigned lo_kat_shade_indirect(const float* surfs44, unsigned w, unsigned h, unsigned seed, float* rays11, unsigned cap) {
+    Renderer R; R.st.width = w; R.st.height = h;
+    unsigned n = 0;
+    for (unsigned i = 0; i < w * h; ++i) {
+        Ray ray;
+        if (!R.shade_indirect_pixel(kat_surface(surfs44 + 44 * (size_t)i, i % w, i / w), i, seed, ray)) continue;
+        if (n < cap) { float* o = rays11 + 11 * n; o[0] = (float)ray.px; o[1] = (float)ray.py; o[2] = ray.o.x; o[3] = ray.o.y; o[4] = ray.o.z; o[5] = ray.d.x; o[6] = ray.d.y; o[7] = ray.d.z;
+            o[8] = ray.contrib.x; o[9] = ray.contrib.y; o[10] = ray.contrib.z; }
+        ++n;
+    }
+    return n;
+}
+LB_API unsigned lo_kat_shade_direct(const float* surfs44, unsigned w, unsigned h, unsigned seed, const float* lights16, const float* cdf_weights, unsigned nlights,
+                                    float* rays12, unsigned cap) {
+    Renderer R; R.st.width = w; R.st.height = h;
+    float run = 0.f;
+    for (unsigned k = 0; k < nlights; ++k) {
+        const float* l = lights16 + 16 * k; LightTri t;
+        t.p0 = {l[0], l[1], l[2]}; t.p1 = {l[3], l[4], l[5]}; t.p2 = {l[6], l[7], l[8]}; t.normal = {l[9], l[10], l[11]}; t.radiance = {l[12], l[13], l[14]}; t.area = l[15];
+        R.lights.push_back(t); run += cdf_weights[k]; R.cdf.push_back(run);
+    }
+    R.cdf_sum = run;
+    unsigned n = 0;
+    for (unsigned i = 0; i < w * h; ++i) {
+        ShadowRay ray;
+        if (!R.shade_direct_pixel(kat_surface(surfs44 + 44 * (size_t)i, i % w, i / w), i, seed, LB_CHANNEL_INDIRECT, nullptr, nullptr, ray)) continue;
+        if (n < cap) { float* o = rays12 + 12 * n; o[0] = (float)ray.px; o[1] = (float)ray.py; o[2] = ray.o.x; o[3] = ray.o.y; o[4] = ray.o.z; o[5] = ray.d.x; o[6] = ray.d.y; o[7] = ray.d.z;
+            o[8] = ray.tmax; o[9] = ray.radiance.x; o[10] = ray.radiance.y; o[11] = ray.radiance.z; }
+        ++n;
+    }
+    return n;
+}
 LB_API void lo_kat_reservoir(const float* weights, const unsigned* seeds, const float* pdfs, unsigned n, float* out5, unsigned char* selected) {
     Reservoir r; r.sample.radiance.x = -1.f;
     for (unsigned k = 0; k < n; ++k) { LightSample s; s.pdf = pdfs[k]; s.radiance.x = (float)k; selected[k] = r.update(s, weights[k], seeds[k]) ? 1 : 0; }

@@ -63,6 +63,42 @@ def test_cornell_restir(oracle, temporal, spatial):
     g.close(); c.close()
 
 
+def test_restir_unbiased_combine(oracle):
+    """LbSettings::restir_unbiased = the reference's ReSTIRSettings::enableBiased = false: temporal and spatial reuse take the CombineUnbiased
+    branches (ReSTIRKernels.cu:905-970, :1123-1198; pinned against the reference compiled with that constant flipped,
+    tests/test_oracle_golden.py). The branch is dead in the shipped reference for a reason: its spatial normalisation counts the stale sample
+    count of the output buffer (:951), 0 on a first frame, so weights come out as weightSum / FLT_EPSILON^2 and the history diverges to inf / NaN
+    within a few frames — reproduced as written. Compared here: the reservoirs after ONE frame (finite), pixel by pixel."""
+    scene = scenes.material_gallery()
+    g, c = _pair(oracle, scene, width=160, height=120, depth=2, restir=True, restir_unbiased=True)
+    biased = lr.Renderer(lr.Settings(width=160, height=120, depth=2, restir=True)); biased.load_scene(scene)
+    for r in (g, c, biased):
+        r.render_frames(1)
+    _check_hits(g, c)
+    assert rel_l1(g.read_hdr()[..., :3], c.read_hdr()[..., :3]) < RADIANCE_TOL          # the frame itself only sees RIS + visibility
+    rg, rc, rb = g.read_reservoirs(), c.read_reservoirs(), biased.read_reservoirs()
+    assert np.isfinite(rc[..., :4]).all() and np.isfinite(rg[..., :4]).all()
+    assert (rg[..., 2] != rc[..., 2]).mean() < 5e-3                                       # sample counts
+    close = np.isclose(rg[..., 1], rc[..., 1], rtol=2e-3, atol=1e-6)
+    assert close.mean() > 0.99, f"{(~close).sum()} of {close.size} reservoir weights differ"
+    assert (rc[..., 1] > 1e6).mean() > 0.01 and not (rb[..., 1] > 1e6).any()              # the unbiased normalisation really ran
+    g.close(); c.close(); biased.close()
+
+
+def test_depth_24_uses_its_own_tickets(oracle):
+    """The deepest schedule lb_create accepts: 24 waves of extend + shadow (+ 5 ReSTIR launches) take 53 device tickets, with media in the
+    default LB_VOLUME_COMPAT mode 77 — more than the 56 of round 1 (the ticket block now holds 120 and the host refuses a schedule that
+    would not fit). Rays of every wave must be the oracle's."""
+    g, c = _pair(oracle, scenes.fog_room(), width=96, height=64, depth=24, restir=True)
+    for frame in range(2):
+        g.render_frames(1); c.render_frames(1)
+    _check_hits(g, c)
+    cg, cc = g.frame_counters(), c.frame_counters()
+    assert cg["extend_rays"] == cc["extend_rays"] and cg["stack_overflows"] == 0
+    assert rel_l1(g.read_hdr()[..., :3], c.read_hdr()[..., :3]) < 5e-3
+    g.close(); c.close()
+
+
 @pytest.mark.parametrize("width,height", [(131, 77), (33, 9), (7, 5), (300, 1)])
 def test_restir_at_ragged_sizes(oracle, width, height):
     """Pixel counts that are not multiples of the 32-pixel rows, 256-pixel bag groups and 32x8 tiles the ReSTIR kernels hand out
