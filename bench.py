@@ -220,14 +220,20 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    accum = None
+    def join_comm(renderer):
+        # the library's own communicator (lb_comm_*, csrc/lb_multigpu.cpp): torch.distributed only carries the 128-byte id to the other ranks
+        box = [lr.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        renderer.comm_init(box[0], rank, world)
+
     if world > 1:
-        ptr, nbytes, _ = r.accum_buffer()
-        accum = torch.as_tensor(DevPtr(ptr, nbytes // 4), device=torch.device("cuda", local))
-        warm = torch.zeros(1024, device="cuda"); dist.all_reduce(warm)          # NCCL communicator warm-up outside the timed region
+        warm = torch.zeros(1024, device="cuda"); dist.all_reduce(warm)          # torch's communicator (timing reductions, barrier) warmed up outside the timed region
+        join_comm(r)
 
     r.render_frames(HISTORY_FRAMES)                 # temporal ReSTIR history of the static camera (>= 8 frames), before the warm-up proper
     r.render_frames(max(args.warmup, 3))            # >= 3 warm-up frames
+    if world > 1:                                   # first use of the library's communicator outside the timed region, then a clean accumulation buffer
+        r.comm_reduce_accum(0, r.accum_buffer()[2] * world); r.set_blend_mode(True)
     r.synchronize()
     counters = r.frame_counters()
     tris, lights, bvh_bytes, launches = counters["triangles"], counters["lights"], counters["bvh_bytes"], counters["kernel_launches"]
@@ -243,7 +249,7 @@ def run_gpu(args):
     for _ in range(args.steps):
         r.render_frames(1)
     if world > 1:
-        dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)                         # the one collective of the path
+        r.comm_reduce_accum(0, args.steps * world)                              # the one collective of the path: ncclReduce on the renderer's stream + resolve on rank 0
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -251,36 +257,55 @@ def run_gpu(args):
     rays_per_frame = rays_of(r.frame_counters())                                # static camera: every timed frame traces the same number of rays
     rays = rays_per_frame * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    reduce_ms = None
     if world > 1:
-        if rank == 0:
-            r.resolve_accum(r.accum_buffer()[2] * world)     # every rank accumulated the same number of frames (warm-up included)
+        # the collective alone (59 MB of fp32 per rank at 1440p), timed on the stream after a barrier
+        r.set_blend_mode(True); r.render_frames(1); barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream); r.comm_reduce_accum(0, world); c1.record(stream); barrier()
+        reduce_ms = c0.elapsed_time(c1)
         t = torch.tensor([ms, float(rays)], device="cuda", dtype=torch.float64)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, rays = float(tmax[0]), float(tsum[1])
 
-    # ---- timed region 2: end to end through the C ABI with host buffers (camera in, HDR frame out, every step). The frame is read
-    # back with the library's asynchronous read-back into two alternating pinned buffers: the copy of frame k overlaps frame k+1, and
-    # every frame has arrived in host memory before the clock stops.
-    hosts = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    host = hosts[0]
-    r.set_camera(cam_pos, cam_rot); r.render_frames(1); r.read_hdr_into(host.data_ptr(), host.numel() * 4)
+    # ---- timed region 2: end to end through the C ABI with host buffers. One GPU: camera in, HDR frame out, every step; the frame is read back
+    # with the library's asynchronous read-back into two alternating pinned buffers (the copy of frame k overlaps frame k+1; every frame has
+    # arrived in host memory before the clock stops). N GPUs: a step is one image of N samples — every rank uploads the camera and renders one
+    # frame into a cleared accumulation buffer, the library reduces the N buffers onto rank 0 (NVLink), and ONLY rank 0 reads the image back
+    # (round 1 read every rank's own frame back: 8 x 59 MB per step into one host).
+    hosts = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else []
+    host = hosts[0] if rank == 0 else None
+
+    def e2e_step(k):
+        if world > 1:
+            r.set_blend_mode(True)                          # clears the accumulation buffer: this step's image is this step's N samples
+        r.set_camera(cam_pos, cam_rot)
+        r.render_frames(1)
+        if world > 1:
+            r.comm_reduce_accum(0, world)
+        if rank == 0:
+            r.readback_wait()                               # image k-1 is now in hosts[(k-1) % 2]
+            r.read_hdr_async(hosts[k % 2].data_ptr(), hosts[0].numel() * 4)
+
+    e2e_step(0)
+    if rank == 0:
+        r.readback_wait()
     barrier()
     t0 = time.time()
     for k in range(args.steps):
-        r.set_camera(cam_pos, cam_rot)
-        r.render_frames(1)
-        r.readback_wait()                                   # frame k-1 is now in hosts[(k-1) % 2]
-        r.read_hdr_async(hosts[k % 2].data_ptr(), host.numel() * 4)
-    r.readback_wait()
+        e2e_step(k)
+    if rank == 0:
+        r.readback_wait()
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
-    host = hosts[(args.steps - 1) % 2]
+    host = hosts[(args.steps - 1) % 2] if rank == 0 else None
     e2e_rays = rays_per_frame * args.steps
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t[0])
         t = torch.tensor([float(e2e_rays)], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM); e2e_rays = float(t[0])
-    finite = bool(np.isfinite(host.numpy()).all())
+        r.set_blend_mode(False)
+    finite = bool(np.isfinite(host.numpy()).all()) if rank == 0 else True
 
     # ---- per-stage device time (CUDA events on the renderer's stream, per frame) for the roofline lines
     # Stage times are taken with the two chains of a frame serialised (lb_set_overlap(0), the default): every stage time is an exclusive
@@ -295,6 +320,8 @@ def run_gpu(args):
     stage_ms = {k: v / stage_frames for k, v in stage_ms.items()}
     serial_ms = sum(stage_ms.values())
     fc = r.frame_counters()
+
+    extras = None if args.no_extras else run_extras(args, lr, torch, dist, rank, world, local, scene, stream, join_comm, barrier)
 
     if rank == 0:
         peaks = {}
@@ -344,7 +371,10 @@ def run_gpu(args):
                 "config": config_of(args, W, H), "parallelism": f"sample-sharded x{world}", "history_fill_frames": HISTORY_FRAMES,
                 "fps": args.steps / (ms * 1e-3), "samples_per_s": W * H * args.steps * world / (ms * 1e-3), "rays_per_frame": rays_per_frame,
                 "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
-                "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3},
+                "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3,
+                        "what": "one GPU: camera upload + frame + HDR read-back per step" if world == 1 else
+                                f"per step: camera upload and one frame on each of the {world} ranks, ncclReduce of the accumulation buffers onto rank 0 inside the library, HDR read-back on rank 0 only"},
+                "reduce_ms": reduce_ms, "extras": extras,
                 "gpu_launches": launches * args.steps, "launches_per_frame": launches,
                 "overlap": {"mode": int(os.environ.get("LB_OVERLAP", "5")), "ms_per_frame_serialised": serial_ms,
                             "note": "mask: bit 0 = shadow rays of bounce wave d on a side stream under the extend launch of wave d+1; bit 2 = ReSTIR chain launched after the first bounce wave, later waves beside it (default 5); bit 1 (off, measured slower) = ReSTIR chain beside all bounce waves; stage_ms / roofline_kernels are always exclusive times measured with mode 0"},
@@ -353,6 +383,73 @@ def run_gpu(args):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, lr, torch, dist, rank, world, local, scene, stream, join_comm, barrier):
+    """Two more measurements on the same ranks, reported beside the headline (never instead of it):
+    strong_bands_ms_per_frame — ONE 2560x1440 frame per step, split into row bands with a 60-row ReSTIR halo across the ranks and gathered on
+        rank 0 by the library (lb_band_settings + lb_comm_gather_bands): strong scaling / single-frame latency;
+    c5_time_to_64spp_s — BASELINE configs[4]: 3840x2160 progressive, 64 samples per pixel in total, sample-sharded (64 / N frames per rank) with
+        one reduce of the fp32 accumulation buffer at the end."""
+    out = {}
+    W, H = args.width, args.height
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(steps); b.record(stream); barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+        return ms
+    # ---- row bands
+    full_st = settings(args, W, H)
+    st, (y0, y1) = lr.band_settings(full_st, rank, world)
+    st.device = local
+    rb = lr.Renderer(st); rb.load_scene(scene); rb.set_stream(stream.cuda_stream)
+    full = torch.zeros((H, W, 4), device="cuda") if rank == 0 else None
+    if world > 1:
+        join_comm(rb)
+    def band_frames(n):
+        for _ in range(n):
+            rb.render_frames(1)
+            if world > 1:
+                rb.comm_gather_bands(0, full.data_ptr() if rank == 0 else 0)
+    band_frames(HISTORY_FRAMES + 3)
+    steps = max(3, min(args.steps, 10))
+    ms = timed(band_frames, steps)
+    rows = torch.tensor([float(st.height)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM)
+    out["strong_bands_ms_per_frame"] = ms / steps
+    out["strong_bands"] = {"frames": steps, "rows_rendered_over_rows_owned": float(rows[0]) / H, "halo_rows": 60, "gather_bytes_per_frame": (H - (y1 - y0)) * W * 16 if rank == 0 else None,
+                           "finite": bool(torch.isfinite(full).all()) if (rank == 0 and world > 1) else True}
+    if world > 1:
+        rb.synchronize(); rb.comm_destroy()
+    rb.close(); del full
+    # ---- C5: 4K, 64 spp in total
+    total_spp = 64
+    frames = total_spp // world + (1 if rank < total_spp % world else 0)
+    st5 = lr.shard_settings(settings(args, 3840, 2160), rank, world); st5.device = local
+    r5 = lr.Renderer(st5); r5.load_scene(scene); r5.set_stream(stream.cuda_stream)
+    if world > 1:
+        join_comm(r5)
+    r5.render_frames(2)
+    if world > 1:
+        r5.comm_reduce_accum(0, 2 * world)
+    r5.set_blend_mode(True)                                 # warm-up done: a clean accumulation buffer
+    def c5(_):
+        r5.render_frames(frames)
+        if world > 1:
+            r5.comm_reduce_accum(0, total_spp)
+        else:
+            r5.resolve_accum(total_spp)
+    ms5 = timed(c5, 1)
+    out["c5_time_to_64spp_s"] = ms5 / 1e3
+    out["c5"] = {"resolution": [3840, 2160], "total_spp": total_spp, "frames_on_this_rank": frames, "reduce_bytes": 3840 * 2160 * 16 if world > 1 else 0}
+    if world > 1:
+        r5.synchronize(); r5.comm_destroy()
+    r5.close()
+    return out
 
 
 def run_bands(args):
@@ -430,6 +527,7 @@ def main():
     ap.add_argument("--detail", type=float, default=0.78)
     ap.add_argument("--texture-size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra measurements (row bands of one frame across the ranks, C5 time to 64 spp at 4K)")
     ap.add_argument("--sample-width", type=int, default=0, help="--impl reference: render this width instead of --width (a bounded sample for small hosts)")
     ap.add_argument("--sample-height", type=int, default=0)
     ap.add_argument("--mode", default="samples", choices=["samples", "bands"],

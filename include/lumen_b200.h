@@ -81,7 +81,11 @@ typedef struct LbSettings {
     uint32_t band_full_height;
     uint32_t restir_unbiased;  /* !ReSTIRSettings::enableBiased (ReSTIRData.h:63; the reference ships `enableBiased = true`, so 0 is its behaviour):
                                   1 = temporal and spatial reuse take the CombineUnbiased branches, ReSTIRKernels.cu:905-970, :1123-1198 */
-    uint32_t reserved[2];
+    /* Rows of the FULL frame whose radiance is wanted from this band renderer (band_own_rows = 0: every rendered row). The other rendered
+     * rows are the ReSTIR halo: they are traced and shaded up to the primary surface record and take part in RIS / temporal / spatial reuse
+     * (that is all a neighbour needs of them), but spawn no NEE shadow rays and no bounce rays. Ignored when the scene holds media. */
+    uint32_t band_own_row0;
+    uint32_t band_own_rows;
 } LbSettings;
 
 /* LumenRenderer::MaterialData, LM/Renderer/LumenRenderer.h:64-112 (defaults :66-82).
@@ -193,6 +197,8 @@ LB_API int lb_camera_set_min_max_distance(LbRenderer r, float min_distance, floa
 /* ---- frame settings: LumenRenderer::Set/GetRenderResolution, SetBlendMode, LM/Renderer/LumenRenderer.h:178-196 ---- */
 LB_API int lb_set_render_resolution(LbRenderer r, uint32_t width, uint32_t height);
 LB_API int lb_get_render_resolution(LbRenderer r, uint32_t* width, uint32_t* height);
+/* The settings the renderer currently runs with (WaveFrontRenderer::m_Settings). */
+LB_API int lb_get_settings(LbRenderer r, LbSettings* out);
 LB_API int lb_set_depth(LbRenderer r, uint32_t depth);
 LB_API int lb_set_blend_mode(LbRenderer r, int blend);
 LB_API int lb_get_blend_mode(LbRenderer r, int* blend);
@@ -344,6 +350,57 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
 LB_API int lb_set_overlap(LbRenderer r, int mode);
 /* Run all work on an externally owned CUDA stream (e.g. torch's current stream); 0/NULL = the renderer's own. */
 LB_API int lb_set_stream(LbRenderer r, void* cuda_stream);
+LB_API int lb_get_stream(LbRenderer r, void** cuda_stream);
+
+/* ---- multi-GPU inside the library (csrc/lb_multigpu.cpp). The reference is single-GPU: WaveFrontRenderer owns one CUDA context
+ * (PT/Framework/WaveFrontRenderer.cpp:70-322). NCCL (libnccl.so.2) is loaded at run time by the first call below — a single-GPU application
+ * does not need it installed. Two partitionings, both without any exchange DURING a frame:
+ *   samples  every GPU renders its own frames with a disjoint slice of the reference's frameCount sequence (first_frame_count = 2 * rank,
+ *            frame_count_stride = 2 * ranks) into its fp32 accumulation buffer; ONE ncclReduce(sum) of that buffer on the renderers' streams
+ *            produces the image on the root, which divides by the total frame count;
+ *   bands    every GPU renders a row band of ONE frame plus a 60-row ReSTIR halo (lb_band_settings); the owned rows are gathered on the root
+ *            (ncclSend / ncclRecv on the renderers' streams).
+ * Errors: LB_ERR_* codes; text in lb_multigpu_last_error(). */
+#define LB_RESTIR_HALO 60          /* spatial radius 30 px x 2 iterations, ReSTIRData.h:49,56 */
+/* Settings of the renderer that produces rank `rank`'s band (+ halo) of the frame described by `full`: height / band_row0 / band_full_height /
+ * band_own_row0 / band_own_rows are set; own_y0 / own_y1 (optional) receive the owned rows. band_row0 is lowered until band_row0 * width is a
+ * multiple of 256 (the RIS light-bag group). */
+LB_API int lb_band_settings(const LbSettings* full, uint32_t rank, uint32_t ranks, LbSettings* out, uint32_t* own_y0, uint32_t* own_y1);
+/* Settings of sample-sharding rank `rank`: blend mode + the rank's frameCount stream. */
+LB_API int lb_shard_settings(const LbSettings* base, uint32_t rank, uint32_t ranks, LbSettings* out);
+
+/* -- one rank per process (any launcher: the 128-byte id is created on one rank and handed to the others by the host application) */
+#define LB_COMM_ID_BYTES 128
+LB_API int lb_comm_unique_id(uint8_t* id128);
+LB_API int lb_comm_init(LbRenderer r, const uint8_t* id128, int rank, int ranks);
+/* samples: sum-reduce the accumulation buffers onto `root` (in place, on the renderer's stream); the root then resolves its HDR / LDR buffers as
+ * sum / total_frames (total_frames = frames accumulated by ALL ranks). Asynchronous like lb_render_frames. In place: the root's accumulation
+ * buffer then holds the sum of all ranks — lb_set_blend_mode(r, 1) clears it before the next image is accumulated. */
+LB_API int lb_comm_reduce_accum(LbRenderer r, int root, uint32_t total_frames);
+/* bands: every rank sends the rows it owns of its merged frame to `root`; on the root `full_frame_device` receives the band_full_height x width
+ * float4 image (device memory of the root's GPU; ignored on the other ranks). The renderer must have been created from lb_band_settings. */
+LB_API int lb_comm_gather_bands(LbRenderer r, int root, void* full_frame_device);
+LB_API int lb_comm_destroy(LbRenderer r);
+
+/* -- one process driving n GPUs (ncclCommInitAll): what a C++ application on the adapter uses */
+typedef struct LbGroup_t* LbGroup;
+enum { LB_GROUP_SAMPLES = 0, LB_GROUP_BANDS = 1 };
+/* Creates one renderer per device (settings derived from `settings` by lb_shard_settings / lb_band_settings) and one communicator over them.
+ * The scene is loaded into every member through the ordinary entry points (lb_group_member). */
+LB_API int lb_group_create(const int* devices, uint32_t n, const LbSettings* settings, int mode, LbGroup* out);
+LB_API int lb_group_size(LbGroup g, uint32_t* n);
+LB_API int lb_group_member(LbGroup g, uint32_t i, LbRenderer* out);
+/* samples: `frames` frames on every member (n * frames samples); bands: `frames` complete frames, each gathered on member 0. Asynchronous. */
+LB_API int lb_group_render(LbGroup g, uint32_t frames);
+/* samples: the one collective + resolve on member 0 (bands: no-op). Asynchronous; lb_group_read_hdr synchronises. The reduce is in place:
+ * afterwards member 0's accumulation buffer holds the sum of all members, and lb_group_reset starts the next progressive image. */
+LB_API int lb_group_reduce(LbGroup g);
+LB_API int lb_group_reset(LbGroup g);
+/* The image on member 0: width x full height float4. */
+LB_API int lb_group_read_hdr(LbGroup g, float* rgba, size_t capacity_bytes);
+LB_API int lb_group_synchronize(LbGroup g);
+LB_API int lb_group_destroy(LbGroup g);
+LB_API const char* lb_multigpu_last_error(void);
 
 /* ---- debug taps used by the parity tests ---- */
 /* Trace caller-supplied rays with the extend kernel (closest hit) or the any-hit kernel.

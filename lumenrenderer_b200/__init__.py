@@ -52,5 +52,91 @@ class Renderer(api.Renderer):
         super().__init__(bindings(), settings if settings is not None else Settings(**kwargs))
 
 
+# ---- multi-GPU inside the library (csrc/lb_multigpu.cpp, include/lumen_b200.h "multi-GPU inside the library")
+def _mg(code: int):
+    if code != 0:
+        raise LumenError(code, (bindings().multigpu_last_error() or b"").decode())
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id: create on one rank, hand to the others (any launcher), pass to Renderer.comm_init on every rank."""
+    buf = (ctypes.c_uint8 * 128)()
+    _mg(bindings().comm_unique_id(buf))
+    return bytes(buf)
+
+
+def band_settings(settings: Settings, rank: int, ranks: int):
+    """lb_band_settings: settings of the renderer producing band `rank` (+ halo) of the frame `settings` describes, and its owned rows (y0, y1)."""
+    full, out, y0, y1 = settings.to_c(), api.LbSettings(), ctypes.c_uint32(), ctypes.c_uint32()
+    _mg(bindings().band_settings(ctypes.byref(full), rank, ranks, ctypes.byref(out), ctypes.byref(y0), ctypes.byref(y1)))
+    return Settings.from_c(out), (y0.value, y1.value)
+
+
+def shard_settings(settings: Settings, rank: int, ranks: int) -> Settings:
+    base, out = settings.to_c(), api.LbSettings()
+    _mg(bindings().shard_settings(ctypes.byref(base), rank, ranks, ctypes.byref(out)))
+    return Settings.from_c(out)
+
+
+class Group:
+    """One process driving n GPUs (lb_group_*): n member renderers + one NCCL communicator (ncclCommInitAll). mode = "samples" (disjoint
+    frameCount streams, one reduce of the accumulation buffers) or "bands" (row bands of one frame with a ReSTIR halo, one gather per frame)."""
+
+    def __init__(self, devices, settings: Settings, mode: str = "samples"):
+        self.b = bindings()
+        self._g = ctypes.c_void_p()
+        dev = (ctypes.c_int * len(devices))(*devices)
+        cs = settings.to_c()
+        _mg(self.b.group_create(dev, len(devices), ctypes.byref(cs), {"samples": 0, "bands": 1}[mode], ctypes.byref(self._g)))
+        self.width, self.height, self.mode = settings.width, settings.height, mode
+        self.members = []
+        for i in range(len(devices)):
+            h = ctypes.c_void_p()
+            _mg(self.b.group_member(self._g, i, ctypes.byref(h)))
+            m = api.Renderer.__new__(api.Renderer)              # a view of the member: the group owns and destroys it
+            m.b, m._h, m._borrowed = self.b, h, True
+            m.settings = m.get_settings(); m.width, m.height = m.settings.width, m.settings.height
+            self.members.append(m)
+
+    def load_scene(self, scene):
+        for m in self.members:
+            m.load_scene(scene)
+
+    def set_camera(self, position, rotation):
+        for m in self.members:
+            m.set_camera(position, rotation)
+
+    def render(self, frames: int = 1):
+        _mg(self.b.group_render(self._g, frames))
+
+    def reduce(self):
+        _mg(self.b.group_reduce(self._g))
+
+    def reset(self):
+        _mg(self.b.group_reset(self._g))
+
+    def synchronize(self):
+        _mg(self.b.group_synchronize(self._g))
+
+    def read_hdr(self):
+        import numpy as np
+        out = np.empty((self.height, self.width, 4), np.float32)
+        _mg(self.b.group_read_hdr(self._g, out.ctypes.data, out.nbytes))
+        return out
+
+    def close(self):
+        if self._g:
+            for m in self.members:
+                m._h = ctypes.c_void_p()
+            self.b.group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def version() -> str:
     return bindings().version().decode()

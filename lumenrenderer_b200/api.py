@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, fields
 from typing import Optional, Sequence
 
 import numpy as np
@@ -30,7 +30,7 @@ class LbSettings(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("blend_output", C.c_uint32),
                 ("restir", C.c_uint32), ("restir_temporal", C.c_uint32), ("restir_spatial", C.c_uint32),
                 ("device", C.c_int32), ("volume_mode", C.c_uint32), ("first_frame_count", C.c_uint32),
-                ("frame_count_stride", C.c_uint32), ("band_row0", C.c_uint32), ("band_full_height", C.c_uint32), ("restir_unbiased", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("frame_count_stride", C.c_uint32), ("band_row0", C.c_uint32), ("band_full_height", C.c_uint32), ("restir_unbiased", C.c_uint32), ("band_own_row0", C.c_uint32), ("band_own_rows", C.c_uint32)]
 
 
 class LbMaterialDesc(C.Structure):
@@ -122,6 +122,12 @@ class Settings:
     band_row0: int = 0
     band_full_height: int = 0
     restir_unbiased: bool = False
+    band_own_row0: int = 0
+    band_own_rows: int = 0
+
+    @classmethod
+    def from_c(cls, c: "LbSettings") -> "Settings":
+        return cls(**{f.name: type(getattr(cls, f.name))(getattr(c, f.name)) for f in fields(cls)})
 
     def to_c(self) -> LbSettings:
         s = LbSettings()
@@ -158,6 +164,7 @@ _SIGS = {
     "camera_set_fov_y": [C.c_void_p, C.c_float],
     "set_render_resolution": [C.c_void_p, C.c_uint32, C.c_uint32],
     "get_render_resolution": [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+    "get_settings": [C.c_void_p, C.POINTER(LbSettings)],
     "set_depth": [C.c_void_p, C.c_uint32],
     "set_blend_mode": [C.c_void_p, C.c_int],
     "get_blend_mode": [C.c_void_p, C.POINTER(C.c_int)],
@@ -226,8 +233,26 @@ _HOST_SIGS = {
     "nanovdb_dense": [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
     "volume_create_nanovdb": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
     "volume_create_file": [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)],
+    # multi-GPU inside the library (csrc/lb_multigpu.cpp): NCCL over NVLink, no oracle counterpart (the CPU tests use gloo for the same exchange)
+    "get_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "band_settings": [C.POINTER(LbSettings), C.c_uint32, C.c_uint32, C.POINTER(LbSettings), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+    "shard_settings": [C.POINTER(LbSettings), C.c_uint32, C.c_uint32, C.POINTER(LbSettings)],
+    "comm_unique_id": [C.c_void_p],
+    "comm_init": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+    "comm_reduce_accum": [C.c_void_p, C.c_int, C.c_uint32],
+    "comm_gather_bands": [C.c_void_p, C.c_int, C.c_void_p],
+    "comm_destroy": [C.c_void_p],
+    "group_create": [C.POINTER(C.c_int), C.c_uint32, C.POINTER(LbSettings), C.c_int, C.POINTER(C.c_void_p)],
+    "group_size": [C.c_void_p, C.POINTER(C.c_uint32)],
+    "group_member": [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)],
+    "group_render": [C.c_void_p, C.c_uint32],
+    "group_reduce": [C.c_void_p],
+    "group_reset": [C.c_void_p],
+    "group_read_hdr": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "group_synchronize": [C.c_void_p],
+    "group_destroy": [C.c_void_p],
 }
-HOST_ONLY_SYMBOLS = tuple(_HOST_SIGS) + ("gltf_last_error", "nanovdb_last_error")
+HOST_ONLY_SYMBOLS = tuple(_HOST_SIGS) + ("gltf_last_error", "nanovdb_last_error", "multigpu_last_error")
 C_ABI_SYMBOLS = tuple(_SIGS) + ("last_error", "version")
 
 HIT_DTYPE = np.dtype([("instance", np.uint32), ("primitive", np.uint32), ("u", np.float32), ("v", np.float32), ("t", np.float32)])
@@ -255,6 +280,8 @@ class Bindings:
             self.gltf_last_error.restype = C.c_char_p
             self.nanovdb_last_error = lib.lb_nanovdb_last_error
             self.nanovdb_last_error.restype = C.c_char_p
+            self.multigpu_last_error = lib.lb_multigpu_last_error
+            self.multigpu_last_error.restype = C.c_char_p
 
     def check(self, code: int):
         if code != LB_OK:
@@ -290,9 +317,9 @@ class Renderer:
 
     # ---- lifetime
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):          # a member of a lumenrenderer_b200.Group belongs to the group
             self.b.destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -566,6 +593,32 @@ class Renderer:
 
     def set_stream(self, cuda_stream: int):
         self.b.check(self.b.set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def get_settings(self) -> Settings:
+        c = LbSettings()
+        self.b.check(self.b.get_settings(self._h, C.byref(c)))
+        return Settings.from_c(c)
+
+    # ---- multi-GPU, one rank per process (CUDA library only; csrc/lb_multigpu.cpp)
+    def _mg(self, code: int):
+        if code != LB_OK:
+            raise LumenError(code, (self.b.multigpu_last_error() or b"").decode())
+
+    def comm_init(self, unique_id: bytes, rank: int, ranks: int):
+        """Joins the NCCL communicator described by the 128-byte id of `comm_unique_id()` (created on one rank, handed round by the launcher)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._mg(self.b.comm_init(self._h, buf, rank, ranks))
+
+    def comm_reduce_accum(self, root: int, total_frames: int):
+        """Sample sharding: the one collective — sum-reduce of the fp32 accumulation buffers onto `root`, which resolves sum / total_frames."""
+        self._mg(self.b.comm_reduce_accum(self._h, root, total_frames))
+
+    def comm_gather_bands(self, root: int, full_frame_device_ptr: int = 0):
+        """Row bands: every rank's owned rows to `root` (device to device); `full_frame_device_ptr` = H x W float4 on the root."""
+        self._mg(self.b.comm_gather_bands(self._h, root, C.c_void_p(full_frame_device_ptr)))
+
+    def comm_destroy(self):
+        self._mg(self.b.comm_destroy(self._h))
 
     # ---- debug taps
     def trace_closest(self, origins, directions, tmin=0.01, tmax=5000.0) -> np.ndarray:

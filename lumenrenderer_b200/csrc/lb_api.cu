@@ -355,6 +355,7 @@ struct Renderer {
         FrameView fv;
         fv.width = st.width; fv.height = st.height; fv.npix = npix();
         fv.row0 = st.band_row0; fv.full_height = full_height(); fv.pix0 = st.band_row0 * st.width;
+        if (st.band_own_rows && vinstances.empty()) { fv.own_pix0 = (st.band_own_row0 - st.band_row0) * st.width; fv.own_pix1 = fv.own_pix0 + st.band_own_rows * st.width; }
         for (int q = 0; q < 2; ++q) fv.rays[q] = RayQueue{d_rays[q][0].p, d_rays[q][1].p, d_rays[q][2].p};
         fv.hits = d_hits.p; fv.primary_hits = d_primary_hits.p;
         fv.shadow = ShadowQueue{d_shadow[0].p, d_shadow[1].p, d_shadow[2].p};
@@ -522,6 +523,8 @@ LB_API int lb_create(const LbSettings* s, LbRenderer* out) {
     if (s->band_full_height && (s->band_row0 + s->height > s->band_full_height || ((uint64_t)s->band_row0 * s->width) % 256u))
         return fail(LB_ERR_INVALID_ARGUMENT, "row band: band_row0 + height must fit band_full_height and band_row0 * width must be a multiple of 256");
     if (!s->band_full_height && s->band_row0) return fail(LB_ERR_INVALID_ARGUMENT, "band_row0 without band_full_height");
+    if (s->band_own_rows && (s->band_own_row0 < s->band_row0 || s->band_own_row0 + s->band_own_rows > s->band_row0 + s->height))
+        return fail(LB_ERR_INVALID_ARGUMENT, "band_own_row0 / band_own_rows must lie inside the rendered rows");
     std::unique_ptr<lb::Renderer> r(new lb::Renderer());
     r->st = *s;
     try { r->init(); }
@@ -642,6 +645,7 @@ LB_API int lb_camera_set_min_max_distance(LbRenderer r, float mn, float mx) {
 LB_API int lb_set_render_resolution(LbRenderer r, uint32_t w, uint32_t h) {
     return guarded(R_, [&]() { if (!w || !h) return fail(LB_ERR_INVALID_ARGUMENT, "resolution"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->st.width = w; R_->st.height = h; R_->resize(); return (int)LB_OK; });
 }
+LB_API int lb_get_settings(LbRenderer r, LbSettings* out) { return guarded(R_, [&]() { if (!out) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *out = R_->st; return (int)LB_OK; }); }
 LB_API int lb_get_render_resolution(LbRenderer r, uint32_t* w, uint32_t* h) { return guarded(R_, [&]() { *w = R_->st.width; *h = R_->st.height; return (int)LB_OK; }); }
 LB_API int lb_set_depth(LbRenderer r, uint32_t d) { return guarded(R_, [&]() { if (!d || d > 24) return fail(LB_ERR_INVALID_ARGUMENT, "depth"); R_->st.depth = d; return (int)LB_OK; }); }
 LB_API int lb_set_blend_mode(LbRenderer r, int b) {
@@ -794,6 +798,7 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
 LB_API int lb_set_overlap(LbRenderer r, int enabled) {
     return guarded(R_, [&]() { if (enabled < 0 || enabled > 7) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
 }
+LB_API int lb_get_stream(LbRenderer r, void** s) { return guarded(R_, [&]() { if (!s) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *s = (void*)R_->stream; return (int)LB_OK; }); }
 LB_API int lb_set_stream(LbRenderer r, void* s) {
     return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->stream = s ? (cudaStream_t)s : R_->own_stream; return (int)LB_OK; });
 }

@@ -26,6 +26,9 @@ struct FrameView {
     uint32_t width = 0, height = 0, npix = 0;
     // row band of a larger frame (LbSettings::band_*): first row, rows of the full frame, index of the band's first pixel in the full frame
     uint32_t row0 = 0, full_height = 0, pix0 = 0;
+    // pixels [own_pix0, own_pix1) of this renderer are the ones whose radiance is wanted (LbSettings::band_own_*): the rest is ReSTIR halo and
+    // spawns neither NEE shadow rays nor bounce rays
+    uint32_t own_pix0 = 0, own_pix1 = 0xFFFFFFFFu;
     RayQueue rays[2];
     uint4* hits = nullptr;            // per queue slot (depth > 0)
     uint4* primary_hits = nullptr;    // per pixel == per queue slot at depth 0

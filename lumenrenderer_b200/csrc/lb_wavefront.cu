@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv,
             fv.channels[1 * np + pixel] = zero; fv.channels[2 * np + pixel] = zero; fv.channels[3 * np + pixel] = zero;
         }
 
-        if (a.do_nee) {
+        const bool owned = pixel >= fv.own_pix0 && pixel < fv.own_pix1;          // halo rows of a band: surface record only
+        if (a.do_nee && owned) {
             uint32_t seed = wang_hash(a.seed + gpixel);
             if (a.num_volumes && a.volume_mode == 0 /* LB_VOLUME_COMPAT */ && sc.num_lights) {
                 // VolumetricShadeDirect (GPUVolumetricShadeDirect.cu:8-101): 5 fixed steps, constant density per unit length, the grid is
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv,
                 fv.shadow.L[slot] = f4(sr.radiance, __int_as_float(a.nee_channel));
             }
         }
-        if (a.do_bounce) {
+        if (a.do_bounce && owned) {
             BounceOut b;
             const bool ok = bounce_sample(s, gpixel, wang_hash(a.seed), b);
             if (ok) {

@@ -56,11 +56,13 @@ def band_settings(settings, rank: int, world: int, halo: int = RESTIR_HALO):
     """Settings of the renderer that produces rank `rank`'s band (+ halo) of the frame described by `settings`, and the band
     (y0, y1, h0, h1). Camera, jitter, motion vectors and random streams stay keyed on full-frame pixel positions, so the pixels of
     rows y0..y1 are the ones a single renderer would produce (bit for bit while the ReSTIR history they depend on lies inside the halo:
-    the first two frames after a history reset; afterwards the outer `halo` rows of a band reuse a slightly different neighbourhood)."""
+    the first two frames after a history reset; afterwards the outer `halo` rows of a band reuse a slightly different neighbourhood).
+    The halo rows (outside band_own_*) only produce what a ReSTIR neighbour needs of them — primary surface record and reservoirs — and
+    spawn no NEE or bounce rays. Same arithmetic as lb_band_settings of the C ABI (csrc/lb_multigpu.cpp)."""
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
     y0, y1, h0, h1 = band_partition(settings.height, world, halo, settings.width)[rank]
-    return replace(settings, height=h1 - h0, band_row0=h0, band_full_height=settings.height), (y0, y1, h0, h1)
+    return replace(settings, height=h1 - h0, band_row0=h0, band_full_height=settings.height, band_own_row0=y0, band_own_rows=y1 - y0), (y0, y1, h0, h1)
 
 
 def gather_bands(band_rows, full_frame, bands, rank: int, dst: int = 0, group=None):

@@ -106,6 +106,12 @@ struct Renderer {
     // row band of a larger frame (LbSettings::band_*): random streams, camera and motion vectors are keyed on the full-frame position
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     uint32_t pix0() const { return st.band_row0 * st.width; }
+    // LbSettings::band_own_*: pixels outside the owned rows are ReSTIR halo — no NEE shadow rays, no bounce rays (ignored with media)
+    bool owned(uint32_t pixel_index) const {
+        if (!st.band_own_rows || !vinstances.empty()) return true;
+        const uint32_t row = pixel_index / st.width + st.band_row0;
+        return row >= st.band_own_row0 && row < st.band_own_row0 + st.band_own_rows;
+    }
     void resize() {
         const size_t n = npix();
         for (auto& s : surface) s.assign(n, Surface{});
@@ -830,7 +836,7 @@ struct Renderer {
                 #pragma omp parallel for schedule(dynamic, 256)
                 for (int64_t i = 0; i < (int64_t)rays.size(); ++i) {
                     const uint32_t pi = rays[i].py * st.width + rays[i].px;
-                    ok[i] = shade_indirect_pixel(S[pi], pi, s2, cand[i]) ? 1 : 0;
+                    ok[i] = owned(pi) && shade_indirect_pixel(S[pi], pi, s2, cand[i]) ? 1 : 0;
                 }
                 for (size_t i = 0; i < rays.size(); ++i) if (ok[i]) next.push_back(cand[i]);
                 lap("bounce");
@@ -866,7 +872,7 @@ struct Renderer {
         #pragma omp parallel for schedule(dynamic, 256) if (!has_vol)
         for (int64_t i = 0; i < (int64_t)rays.size(); ++i) {
             const uint32_t pi = rays[i].py * st.width + rays[i].px;
-            ok[i] = shade_direct_pixel(S[pi], pi, seed, chan, has_vol ? &volhits[pi] : nullptr, &vrays, cand[i]) ? 1 : 0;
+            ok[i] = owned(pi) && shade_direct_pixel(S[pi], pi, seed, chan, has_vol ? &volhits[pi] : nullptr, &vrays, cand[i]) ? 1 : 0;
         }
         for (size_t i = 0; i < rays.size(); ++i) if (ok[i]) srays.push_back(cand[i]);
     }
@@ -902,6 +908,8 @@ LB_API int lo_create(const LbSettings* s, LbRenderer* out) {
     if (s->band_full_height && (s->band_row0 + s->height > s->band_full_height || ((uint64_t)s->band_row0 * s->width) % 256u))
         return fail(LB_ERR_INVALID_ARGUMENT, "row band: band_row0 + height must fit band_full_height and band_row0 * width must be a multiple of 256");
     if (!s->band_full_height && s->band_row0) return fail(LB_ERR_INVALID_ARGUMENT, "band_row0 without band_full_height");
+    if (s->band_own_rows && (s->band_own_row0 < s->band_row0 || s->band_own_row0 + s->band_own_rows > s->band_row0 + s->height))
+        return fail(LB_ERR_INVALID_ARGUMENT, "band_own_row0 / band_own_rows must lie inside the rendered rows");
     auto* r = new lo::Renderer(); r->st = *s;
     Texture white; white.px = {255, 255, 255, 255}; Texture nrm; nrm.px = {128, 128, 255, 255};   // LM/Renderer/LumenRenderer.cpp:50-58
     r->textures.push_back(white); r->textures.push_back(nrm);
@@ -996,6 +1004,7 @@ LB_API int lo_read_gbuffer(LbRenderer r, float* depth, float* nr, float* albedo,
     return LB_OK;
 }
 LB_API int lo_set_render_resolution(LbRenderer r, uint32_t w, uint32_t h) { CHECK_R; if (!w || !h) return fail(LB_ERR_INVALID_ARGUMENT, "resolution"); R_->st.width = w; R_->st.height = h; R_->resize(); return LB_OK; }
+LB_API int lo_get_settings(LbRenderer r, LbSettings* out) { CHECK_R; if (!out) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *out = R_->st; return LB_OK; }
 LB_API int lo_get_render_resolution(LbRenderer r, uint32_t* w, uint32_t* h) { CHECK_R; *w = R_->st.width; *h = R_->st.height; return LB_OK; }
 LB_API int lo_set_depth(LbRenderer r, uint32_t d) { CHECK_R; if (!d) return fail(LB_ERR_INVALID_ARGUMENT, "depth"); R_->st.depth = d; return LB_OK; }
 LB_API int lo_set_blend_mode(LbRenderer r, int b) { CHECK_R; R_->st.blend_output = b != 0; R_->blend_count = 0; std::fill(R_->accum.begin(), R_->accum.end(), V4{0, 0, 0, 0}); return LB_OK; }
