@@ -53,6 +53,23 @@ class Renderer(api.Renderer):
 
 
 # ---- multi-GPU inside the library (csrc/lb_multigpu.cpp, include/lumen_b200.h "multi-GPU inside the library")
+def _prefer_bundled_nccl():
+    """The library loads NCCL at run time by soname. When this interpreter also has torch (which bundles a newer libnccl.so.2), the first copy
+    mapped serves both — so name the bundled file before the library's first NCCL call (LB_NCCL_LIB, csrc/lb_multigpu.cpp). torch is not imported."""
+    if os.environ.get("LB_NCCL_LIB"):
+        return
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        path = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            os.environ["LB_NCCL_LIB"] = path
+            return
+
+
 def _mg(code: int):
     if code != 0:
         raise LumenError(code, (bindings().multigpu_last_error() or b"").decode())
@@ -60,6 +77,7 @@ def _mg(code: int):
 
 def comm_unique_id() -> bytes:
     """128-byte NCCL id: create on one rank, hand to the others (any launcher), pass to Renderer.comm_init on every rank."""
+    _prefer_bundled_nccl()
     buf = (ctypes.c_uint8 * 128)()
     _mg(bindings().comm_unique_id(buf))
     return bytes(buf)
@@ -83,6 +101,7 @@ class Group:
     frameCount streams, one reduce of the accumulation buffers) or "bands" (row bands of one frame with a ReSTIR halo, one gather per frame)."""
 
     def __init__(self, devices, settings: Settings, mode: str = "samples"):
+        _prefer_bundled_nccl()
         self.b = bindings()
         self._g = ctypes.c_void_p()
         dev = (ctypes.c_int * len(devices))(*devices)

@@ -606,6 +606,8 @@ class Renderer:
 
     def comm_init(self, unique_id: bytes, rank: int, ranks: int):
         """Joins the NCCL communicator described by the 128-byte id of `comm_unique_id()` (created on one rank, handed round by the launcher)."""
+        import lumenrenderer_b200 as _pkg
+        _pkg._prefer_bundled_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._mg(self.b.comm_init(self._h, buf, rank, ranks))
 

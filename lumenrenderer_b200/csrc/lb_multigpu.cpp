@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -38,7 +39,12 @@ struct Nccl {
     std::string error;
     bool load() {
         if (lib) return true;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        // LB_NCCL_LIB names the library file explicitly. It matters when the process will ALSO load a framework that bundles a newer NCCL under
+        // the same soname (torch): whichever libnccl.so.2 is mapped first serves both, so the host should point this at the bundled one
+        // (lumenrenderer_b200/__init__.py does) instead of letting the system copy win.
+        const char* forced = getenv("LB_NCCL_LIB");
+        if (forced && *forced) lib = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { if (lib) break; lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); }
         if (!lib) { error = std::string("NCCL not found (libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return false; }
         auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) error = std::string("NCCL symbol missing: ") + n; return p; };
         GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId"); CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
