@@ -27,6 +27,7 @@
 #include "lb_json.h"
 #include <unistd.h>
 #include "lb_png.h"
+#include "lb_jpeg.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -131,10 +132,12 @@ struct LbGltfOpaque {
 };
 
 namespace {
-// stb_image in the reference (LoadFile :121); here PNG natively, anything else through the caller's decoder, else the 1x1 default
+// stb_image in the reference (LoadFile :121); here PNG and JPEG natively (lb_png.h, lb_jpeg.h: both pinned on the reference's stb_image), anything
+// else (BMP, TGA, ...) through the caller's decoder, else the 1x1 default
 void decode_image(LbGltfOpaque& g, Image& im, LbImageDecodeFn decoder, void* user) {
     const bool have = !im.raw.empty();
     if (have && lb::png::decode_rgba8(im.raw.data(), im.raw.size(), im.px, im.w, im.h)) im.decoded = true;
+    else if (have && lb::jpeg::decode_rgba8(im.raw.data(), im.raw.size(), im.px, im.w, im.h)) im.decoded = true;
     else if (have && decoder) {
         uint8_t* px = nullptr; uint32_t w = 0, h = 0;
         if (decoder(im.raw.data(), im.raw.size(), &px, &w, &h, user) == 0 && px && w && h) { im.px.assign(px, px + (size_t)w * h * 4); im.w = w; im.h = h; im.decoded = true; }
