@@ -48,6 +48,12 @@ __global__ void k_debug_bsdf(const float* __restrict__ mat24, const float* __res
                               __float_as_uint(b2.z + 0.f) == __float_as_uint(b.z + 0.f) && __float_as_uint(p2 + 0.f) == __float_as_uint(pdf + 0.f);
             if (!same) { b = f3(__int_as_float(0x7fc00000)); pdf = __int_as_float(0x7fc00000); }
         }
+        if (c.is_isotropic()) {                      // likewise the evaluation without the anisotropic microfacet terms
+            float p3 = 0.f; const float3 b3 = c.eval<true>(wi, p3);
+            const bool same = __float_as_uint(b3.x + 0.f) == __float_as_uint(b.x + 0.f) && __float_as_uint(b3.y + 0.f) == __float_as_uint(b.y + 0.f) &&
+                              __float_as_uint(b3.z + 0.f) == __float_as_uint(b.z + 0.f) && __float_as_uint(p3 + 0.f) == __float_as_uint(pdf + 0.f);
+            if (!same && pdf == pdf) { b = f3(__int_as_float(0x7fc00000)); pdf = __int_as_float(0x7fc00000); }
+        }
         out[4 * i] = b.x; out[4 * i + 1] = b.y; out[4 * i + 2] = b.z; out[4 * i + 3] = pdf;
     } else {
         float pdf = 0.f; bool spec = false; float3 wi = f3(0.f);

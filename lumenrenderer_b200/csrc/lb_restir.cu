@@ -138,27 +138,45 @@ __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __res
 //    global gathers (bag entry -> 64-byte light record): ncu showed the first version bound by the L1 data pipe
 //    (l1tex__data_pipe_lsu_wavefronts 77 % of peak, ~8.5 wavefronts per request, profiles/r01_m_frame.md), not by instruction issue.
 struct BagSmem {
+    // phase A (conservative accept / reject of a candidate, 2 reads): bounding sphere of the light triangle, its plane
+    float4* sph;    // centre.xyz, radius (+inf: "never reject": entries whose bag pdf is 0 or NaN take the ordered path)
+    float4* pln;    // normal.xyz, min over the vertices of dot(normal, vertex)
+    // phase B (the survivors: exact geometry, radiance)
     float4* g0;     // p0.xyz, p1.x
     float4* g1;     // p1.yz, p2.xy
-    float4* g2;     // p2.z, normal.xyz
-    float4* rad;    // radiance.xyz, -
+    float4* g2;     // p2.z, radiance.xyz
     float2* pa;     // bag pdf, area
 };
-constexpr size_t kRisBagBytes = (size_t)kLightsPerBag * (4 * sizeof(float4) + sizeof(float2));
-constexpr size_t kRisSmemBytes = kRisBagBytes + (size_t)kPrimarySamples * kBlock * sizeof(uint32_t);
+constexpr int kRisBlock = 512;                                  // ONE block per SM: 16 warps share one staged bag
+constexpr size_t kRisBagBytes = (size_t)kLightsPerBag * (5 * sizeof(float4) + sizeof(float2));
+constexpr size_t kRisSmemBytes = kRisBagBytes + (size_t)kPrimarySamples * kRisBlock * sizeof(uint32_t);
+static_assert(kRisSmemBytes <= 227u * 1024u, "bag + candidate states must fit the 227 KB a block can have");
 
 struct BagCandidate { LightSample ls; float bag_pdf; };
-// geometry of the next candidate of stream `s` (position on the light, normal, area, bag pdf) + its bag slot
+// geometry of the next candidate of stream `s` (position on the light, normal, area, bag pdf) + its bag slot and radiance
 LB_D uint32_t draw_candidate_geom(const BagSmem& b, uint32_t& s, BagCandidate& c) {
     const float r = rand_f(s);
     const uint32_t slot = (uint32_t)(int)roundf((float)(kLightsPerBag - 1u) * r);
-    const float4 a = b.g0[slot], bb = b.g1[slot], cc = b.g2[slot]; const float2 pa = b.pa[slot];
+    const float4 a = b.g0[slot], bb = b.g1[slot], cc = b.g2[slot], pl = b.pln[slot]; const float2 pa = b.pa[slot];
     const float u = rand_f(s), v = rand_f(s) * (1.f - u);
     const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(a.w, bb.x, bb.y), p2 = f3(bb.z, bb.w, cc.x);
-    c.ls.normal = f3(cc.y, cc.z, cc.w); c.ls.area = pa.y; c.ls.contribution = f3(0.f); c.ls.pdf = 0.f;
+    c.ls.normal = f3(pl); c.ls.area = pa.y; c.ls.contribution = f3(0.f); c.ls.pdf = 0.f;
+    c.ls.radiance = f3(cc.y, cc.z, cc.w);
     c.ls.position = p0 + ((p1 - p0) * u) + ((p2 - p0) * v);
     c.bag_pdf = pa.x;
     return slot;
+}
+// Phase A's test: can the candidate at `slot` possibly pass Resample's geometric test (light above the pixel's horizon, facing it)? Decided
+// for the WHOLE light triangle from its bounding sphere and plane, with margins 100x the rounding error of the exact test — a superset of
+// what phase B accepts; a false survivor merely takes the ordered path with weight 0. Any point x of the triangle has
+//   (x - p) . N  <=  (c - p) . N + r |N|      and      n . (p - x)  <=  n . p - min_vertices(n . v)   (n: the light's stored normal),
+// the two quantities whose signs Resample tests (cos_in, cos_out, ReSTIRKernels.cu:1270-1281).
+LB_D bool candidate_may_pass(const BagSmem& b, uint32_t slot, const float3& ppos, const float3& pnormal) {
+    const float4 S = b.sph[slot], P = b.pln[slot];
+    const float3 d = f3(S) - ppos;
+    const float s_in = dot(d, pnormal) + S.w * 1.001f, eps_in = 1e-5f * (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + S.w);
+    const float dn = dot(f3(P), ppos), s_out = dn - P.w, eps_out = 1e-5f * (fabsf(dn) + fabsf(P.w) + S.w);
+    return !(s_in < -eps_in || s_out < -eps_out);                // NaN / inf anywhere: not rejected
 }
 
 extern __shared__ __align__(16) unsigned char ris_smem[];
@@ -191,10 +209,11 @@ __global__ void __launch_bounds__(1024) k_ris_order(uint32_t seed, uint32_t npix
 }
 
 // Phase B of k_ris for one 32-pixel row: the survivors of every lane in candidate order, one per lane per round, the lanes aligned on the
-// BSDF evaluation. SIMPLE = every pixel of the row has a material without transmission / sheen / clear coat / anisotropy / subsurface
-// (voted by the warp): the round then runs the lean evaluation — no predicated-off lobes, no transmission branch.
-template <bool SIMPLE>
-LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kBlock], const BsdfCtx& ctx, const Surface& px, uint32_t mask, uint32_t s0, Reservoir& fresh) {
+// BSDF evaluation. MODE is voted by the warp: 2 = every pixel of the row has a material without transmission / sheen / clear coat / anisotropy
+// / subsurface (lean evaluation), 1 = every pixel has isotropic roughness (the general evaluation without the anisotropic microfacet terms, which
+// the compiler otherwise executes predicated-off), 0 = anything.
+template <int MODE>
+LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisBlock], const BsdfCtx& ctx, const Surface& px, uint32_t mask, uint32_t s0, Reservoir& fresh) {
     uint32_t sb = s0;
     while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
         const bool active = mask != 0u;
@@ -204,12 +223,11 @@ LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kBlock], con
         if (active) {
             const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
             sb = s_state[k][threadIdx.x];
-            const uint32_t slot = draw_candidate_geom(bag, sb, c);
-            c.ls.radiance = f3(bag.rad[slot]);
+            draw_candidate_geom(bag, sb, c);
             have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
         }
         __syncwarp();
-        if (have_g) resample_shade<SIMPLE>(ctx, g, c.ls);
+        if (have_g) resample_shade<MODE>(ctx, g, c.ls);
         if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
         __syncwarp();
     }
@@ -221,17 +239,16 @@ LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kBlock], con
 // on to the next bag that still has rows (work stealing; costs one more staging). The first version handed whole 256-pixel groups to
 // blocks in image order and re-staged the bag for every group (14 400 times per frame at 1440p): barrier stalls 0.46 and
 // long-scoreboard 0.64 warps per issue (profiles/r01_u_kernels.md).
-__global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed, int allow_simple) {
+__global__ void __launch_bounds__(kRisBlock, 1) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed, int allow_simple) {
     static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
-    static_assert(kBlock == 256, "8 warps = the 8 rows of a 256-pixel bag group");
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     const size_t np = fv.npix;
     BagSmem bag;
-    bag.g0 = reinterpret_cast<float4*>(ris_smem); bag.g1 = bag.g0 + kLightsPerBag; bag.g2 = bag.g1 + kLightsPerBag; bag.rad = bag.g2 + kLightsPerBag;
-    bag.pa = reinterpret_cast<float2*>(bag.rad + kLightsPerBag);
+    bag.sph = reinterpret_cast<float4*>(ris_smem); bag.pln = bag.sph + kLightsPerBag; bag.g0 = bag.pln + kLightsPerBag; bag.g1 = bag.g0 + kLightsPerBag; bag.g2 = bag.g1 + kLightsPerBag;
+    bag.pa = reinterpret_cast<float2*>(bag.g2 + kLightsPerBag);
     // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
     // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
-    uint32_t (*s_state)[kBlock] = reinterpret_cast<uint32_t (*)[kBlock]>(ris_smem + kRisBagBytes);
+    uint32_t (*s_state)[kRisBlock] = reinterpret_cast<uint32_t (*)[kRisBlock]>(ris_smem + kRisBagBytes);
     __shared__ uint32_t s_next;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ngroups = (fv.npix + 255u) / 256u;
@@ -258,11 +275,20 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
         cur = s_next;
         if (cur == kNone || ++visited > 2u * kNumBags) break;
         const uint2* picked = bags + (size_t)cur * kLightsPerBag;
-        for (uint32_t e = threadIdx.x; e < kLightsPerBag; e += kBlock) {
+        for (uint32_t e = threadIdx.x; e < kLightsPerBag; e += kRisBlock) {
             const uint2 be = __ldg(&picked[e]);
             const float4* lp = reinterpret_cast<const float4*>(sc.lights + be.x);
             const float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d = __ldg(lp + 3);
-            bag.g0[e] = a; bag.g1[e] = b; bag.g2[e] = c; bag.rad[e] = make_float4(d.x, d.y, d.z, 0.f); bag.pa[e] = make_float2(__uint_as_float(be.y), d.w);
+            const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(a.w, b.x, b.y), p2 = f3(b.z, b.w, c.x), nrm = f3(c.y, c.z, c.w);
+            const float3 ctr = (p0 + p1 + p2) * (1.f / 3.f);
+            float rad = fmaxf(length(p0 - ctr), fmaxf(length(p1 - ctr), length(p2 - ctr))) * 1.0001f + 1e-6f;
+            const float bag_pdf = __uint_as_float(be.y);
+            // the light's normal is the transformed mean VERTEX normal (GPUDataBufferKernels.cu:150-156), not the triangle's own: n . x is not constant
+            // over the triangle, so the plane offset is its minimum over the three vertices (n . x is linear in x)
+            float4 plane = f4(nrm, fminf(dot(nrm, p0), fminf(dot(nrm, p1), dot(nrm, p2))));
+            if (!(bag_pdf != 0.f && bag_pdf == bag_pdf)) { rad = __int_as_float(0x7f800000); plane.w = -__int_as_float(0x7f800000); }      // never rejected: ordered path
+            bag.sph[e] = f4(ctr, rad); bag.pln[e] = plane;
+            bag.g0[e] = a; bag.g1[e] = b; bag.g2[e] = make_float4(c.x, d.x, d.y, d.z); bag.pa[e] = make_float2(bag_pdf, d.w);
         }
         __syncthreads();
         const uint2 range = meta[cur];
@@ -290,12 +316,12 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 #pragma unroll 2
             for (uint32_t k = 0; k < kPrimarySamples; ++k) {
                 s_state[k][threadIdx.x] = sa;
-                BagCandidate c; draw_candidate_geom(bag, sa, c);
-                ResampleGeom g;
-                const bool have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
-                // ordered unless the update is provably a pure count increment: weight 0 / bag_pdf exactly 0 (bag_pdf neither 0 nor NaN)
-                // and a non-zero acceptance draw
-                const bool ordered = have_g || !(c.bag_pdf != 0.f && c.bag_pdf == c.bag_pdf) || sa == 0u;
+                const float r = rand_f(sa);
+                const uint32_t slot = (uint32_t)(int)roundf((float)(kLightsPerBag - 1u) * r);
+                rand_u32(sa); rand_u32(sa);                      // the candidate's u and v: only the stream position matters here
+                // ordered unless the update is provably a pure count increment: the light cannot pass the geometric test from anywhere on it
+                // (weight 0 / bag pdf, a bag pdf of 0 or NaN never lands here) and the acceptance draw is not the all-zero xorshift state
+                const bool ordered = candidate_may_pass(bag, slot, px.pos, px.normal) || sa == 0u;
                 mask |= (ordered ? 1u : 0u) << k;
             }
             fresh.count = (int)kPrimarySamples - __popc(mask);
@@ -303,8 +329,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_ris(FrameView fv, SceneView sc, c
 
         // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation
         const BsdfCtx ctx = surface_ctx(px);
-        if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_simple()))) ris_phase_b<true>(bag, s_state, ctx, px, mask, s0, fresh);
-        else ris_phase_b<false>(bag, s_state, ctx, px, mask, s0, fresh);
+        if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_simple()))) ris_phase_b<2>(bag, s_state, ctx, px, mask, s0, fresh);
+        else if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_isotropic()))) ris_phase_b<1>(bag, s_state, ctx, px, mask, s0, fresh);
+        else ris_phase_b<0>(bag, s_state, ctx, px, mask, s0, fresh);
         if (valid) {
             reservoir_update_weight(fresh);
             reservoir_store(fv.res_cur, np, i, fresh);
@@ -577,7 +604,7 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     seed = wang_hash(seed);
     LB_CUDA(cudaFuncSetAttribute(k_ris, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRisSmemBytes));      // per device; a host-side setting, no launch
     k_ris_order<<<1, 1024, 0, st>>>(seed, fv.npix, fv.pix0, rb.ris_order); LB_LAUNCH_CHECK();
-    k_ris<<<cfg.sms * 2, kBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed, a.ris_simple); LB_LAUNCH_CHECK();
+    k_ris<<<cfg.sms, kRisBlock, kRisSmemBytes, st>>>(fv, sc, rb.bags, rb.ris_order, seed, a.ris_simple); LB_LAUNCH_CHECK();
     lap("restir_ris");
     const float shaded = 1.f + (a.temporal ? 1.f : 0.f) + (a.spatial ? 1.f : 0.f);
     int vis_pass = 0;

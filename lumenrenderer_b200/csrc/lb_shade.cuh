@@ -169,10 +169,10 @@ LB_D bool resample_geom(const float3& lpos, const float3& lnormal, float larea, 
     g.dir = dir; g.cos_in = cos_in; g.solid = (cos_out * larea) / (dist * dist);
     return true;
 }
-// SIMPLE: the caller has established ctx.is_simple() (lean evaluation, lb_bsdf.cuh)
-template <bool SIMPLE = false>
+// MODE (what the caller has established about the material, lb_bsdf.cuh): 0 nothing, 1 isotropic roughness, 2 BsdfCtx::is_simple()
+template <int MODE = 0>
 LB_D void resample_shade(const BsdfCtx& ctx, const ResampleGeom& g, LightSample& out) {
-    float pdf = 0.f; const float3 bsdf = SIMPLE ? ctx.eval_simple(g.dir, pdf) : ctx.eval(g.dir, pdf);
+    float pdf = 0.f; const float3 bsdf = MODE == 2 ? ctx.eval_simple(g.dir, pdf) : (MODE == 1 ? ctx.eval<true>(g.dir, pdf) : ctx.eval<false>(g.dir, pdf));
     const float added = pdf + bsdf.x + bsdf.y + bsdf.z;
     if (pdf <= kBsdfEps || isnan(added) || isinf(added)) { out.contribution = f3(0.f); out.pdf = 0; return; }
     const float3 c = (bsdf / pdf) * g.solid * g.cos_in * out.radiance;
