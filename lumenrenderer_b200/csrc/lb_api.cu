@@ -60,6 +60,8 @@ struct Renderer {
     std::vector<HostTexture> textures; std::vector<HostMaterial> materials; std::vector<HostPrimitive> prims; std::vector<HostMesh> meshes;
     std::vector<HostInstance> instances; std::vector<HostVolume> volumes; std::vector<HostVolumeInstance> vinstances;
     bool resources_dirty = true, scene_dirty = true;
+    // only instance transforms changed since the last commit: the hierarchies are refitted instead of rebuilt (refit_scene)
+    bool transforms_dirty = false; std::vector<uint32_t> inst_entry_begin;
 
     // ---- device-side scene
     DevBuf<uchar4> d_texels; DevBuf<DevTexture> d_textures; DevBuf<DevMaterial> d_materials; DevBuf<float> d_srgb_lut;
@@ -90,7 +92,7 @@ struct Renderer {
     DevBuf<float4> d_vis_rays[2];
     bool vis_sort = vis_sort_default();
     static bool vis_sort_default() { const char* e = getenv("LB_VIS_SORT"); return e && atoi(e) != 0; }
-    uint64_t counters[12]{};
+    uint64_t counters[16]{};
 
     // ---- FrameStats (LumenRenderer.h:29-34): CUDA events instead of host wall clock around forced syncs
     // A lap's time is measured from `prev`, the preceding lap of the same stream (overlap mode has two chains; the ReSTIR chain starts at
@@ -263,9 +265,10 @@ struct Renderer {
     void commit_scene() {
         LB_CUDA(cudaStreamSynchronize(stream));        // frames in flight read the buffers replaced below
         if (resources_dirty) upload_resources();
-        h_entries.clear(); total_tris = 0;
+        h_entries.clear(); total_tris = 0; inst_entry_begin.assign(instances.size() + 1, 0u);
         for (size_t i = 0; i < instances.size(); ++i) {
             const HostInstance& in = instances[i];
+            inst_entry_begin[i] = (uint32_t)h_entries.size();
             bool mesh_emissive = false; for (int q : meshes[in.mesh].prims) mesh_emissive |= prims[q].num_lights > 0;
             for (int p : meshes[in.mesh].prims) {
                 DevEntry e{}; memcpy(e.m, in.m, sizeof e.m);
@@ -280,6 +283,7 @@ struct Renderer {
                 total_tris += e.tri_count; h_entries.push_back(e);
             }
         }
+        inst_entry_begin[instances.size()] = (uint32_t)h_entries.size();
         d_entries.upload(h_entries.data(), h_entries.size(), stream);
         LB_CUDA(cudaStreamSynchronize(stream));
         ScenePrepIn in{d_entries.p, (uint32_t)h_entries.size(), total_tris, d_indices.p, d_vtx_pos.p};
@@ -315,7 +319,29 @@ struct Renderer {
         LB_CUDA(cudaStreamSynchronize(stream));
         counters[4] = lights.num_lights; counters[5] = total_tris; counters[6] = bvh.num_nodes + (dual_bvh ? bvh_any.num_nodes : 0u); counters[7] = bvh.bytes() + (dual_bvh ? bvh_any.bytes() : 0u);
         counters[8] = (uint64_t)((bvh.build_ms + (dual_bvh ? bvh_any.build_ms : 0.f)) * 1000.f); counters[9] = bvh.levels; counters[10] = bvh.ploc_rounds;
-        scene_dirty = false;
+        counters[12] = 0; counters[13] = 0;
+        scene_dirty = false; transforms_dirty = false;
+    }
+
+    // ---- instances moved, nothing else changed (lb_instance_set_transform): the scene table gets the new matrices, the world-space triangles
+    // are flattened again, and both hierarchies are REFITTED (bvh_refit: same topology, new boxes) instead of rebuilt — the reference rebuilds
+    // its instance acceleration structures on every transform change (PTScene.cpp:74-156, PTMeshInstance.cpp:51-103). Everything is enqueued
+    // on the renderer's stream behind the frames in flight. LB_REFIT_MAX bounds how many refits may follow a build (boxes only ever loosen).
+    void refit_scene() {
+        static const uint32_t max_refits = []() { const char* e = getenv("LB_REFIT_MAX"); return e ? (uint32_t)atoi(e) : 4096u; }();
+        if (!total_tris || bvh.num_tris != total_tris || bvh.refits >= max_refits) { scene_dirty = true; commit_scene(); return; }
+        for (size_t i = 0; i < instances.size(); ++i)
+            for (uint32_t e = inst_entry_begin[i]; e < inst_entry_begin[i + 1]; ++e) memcpy(h_entries[e].m, instances[i].m, sizeof h_entries[e].m);
+        d_entries.upload(h_entries.data(), h_entries.size(), stream);
+        ScenePrepIn in{d_entries.p, (uint32_t)h_entries.size(), total_tris, d_indices.p, d_vtx_pos.p};
+        launch_flatten(cfg(), in, d_flat.p);
+        bvh_refit(stream, d_flat.p, total_tris, bvh);
+        if (dual_bvh) bvh_refit(stream, d_flat.p, total_tris, bvh_any);
+        lights.num_lights = 0; lights.cdf_sum = 0.f;
+        build_lights(cfg(), scene_view(), in, d_prim_flags.p, lights);
+        counters[4] = lights.num_lights;
+        counters[12] = (uint64_t)((bvh.refit_ms + (dual_bvh ? bvh_any.refit_ms : 0.f)) * 1000.f); counters[13] = bvh.refits;
+        transforms_dirty = false;
     }
 
     // ---- camera (Camera.cpp:79-93,122-140): row-major world matrix, columns right/up/forward/position
@@ -385,6 +411,7 @@ struct Renderer {
     // ---- WaveFrontRenderer::TraceFrame
     void render_frame() {
         if (scene_dirty || resources_dirty) commit_scene();
+        else if (transforms_dirty) refit_scene();
         laps.clear(); events_used = 0; last_lap[0] = last_lap[1] = 0;
         lap("begin");
         const LaunchCfg c = cfg();
@@ -613,7 +640,7 @@ LB_API int lb_scene_add_mesh_instance(LbRenderer r, LbHandle mesh, const float* 
     });
 }
 LB_API int lb_instance_set_transform(LbRenderer r, LbHandle i, const float* m16) {
-    return guarded(R_, [&]() { if (i < 0 || i >= (LbHandle)R_->instances.size() || !m16) return fail(LB_ERR_INVALID_HANDLE, "instance"); memcpy(R_->instances[i].m, m16, 64); R_->scene_dirty = true; return (int)LB_OK; });
+    return guarded(R_, [&]() { if (i < 0 || i >= (LbHandle)R_->instances.size() || !m16) return fail(LB_ERR_INVALID_HANDLE, "instance"); memcpy(R_->instances[i].m, m16, 64); R_->transforms_dirty = true; return (int)LB_OK; });
 }
 LB_API int lb_instance_set_emissiveness(LbRenderer r, LbHandle i, const LbEmissiveness* em) {
     return guarded(R_, [&]() { if (i < 0 || i >= (LbHandle)R_->instances.size() || !em) return fail(LB_ERR_INVALID_HANDLE, "instance"); R_->instances[i].em = *em; R_->scene_dirty = true; return (int)LB_OK; });
@@ -744,7 +771,7 @@ static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uin
     LB_CUDA(cudaStreamSynchronize(R->stream));
     R->counters[11] = overflows;              // traversal-stack overflows since the last frame began (debug traces included): must be 0
     R->counters[0] = s[STAT_EXTEND]; R->counters[1] = s[STAT_SHADOW]; R->counters[2] = s[STAT_VIS]; R->counters[3] = R->launches_last_frame;
-    const uint32_t n = cap < 12 ? cap : 12; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
+    const uint32_t n = cap < 14 ? cap : 14; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
 }
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* count) {
     return guarded(R_, [&]() { return frame_counters_locked(R_, v, cap, count); });
@@ -762,10 +789,10 @@ LB_API int lb_save_png(LbRenderer r, const char* path) {
 }
 LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* needed) {
     return guarded(R_, [&]() {
-        static const char* kCounterNames[12] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
-                                                "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds", "stack_overflows"};
-        uint64_t cnt[12]; uint32_t n = 0;
-        int rc = frame_counters_locked(R_, cnt, 12, &n); if (rc) return rc;
+        static const char* kCounterNames[14] = {"extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes",
+                                                "bvh_bytes", "bvh_build_us", "bvh_levels", "bvh_build_rounds", "stack_overflows", "bvh_refit_us", "bvh_refits"};
+        uint64_t cnt[14]; uint32_t n = 0;
+        int rc = frame_counters_locked(R_, cnt, 14, &n); if (rc) return rc;
         LB_CUDA(cudaStreamSynchronize(R_->stream));
         // stages that run several times per frame (extend, shade, shadow per wave) are summed, as FrameStats::m_Times does with its map
         std::vector<std::pair<std::string, double>> times;
@@ -778,7 +805,7 @@ LB_API int lb_frame_stats_json(LbRenderer r, char* json, size_t cap, size_t* nee
         std::string o = "{\"frame_id\": " + std::to_string(R_->frame_index) + ", \"resolution\": [" + std::to_string(R_->st.width) + ", " + std::to_string(R_->st.height) + "], \"times_us\": {";
         for (size_t i = 0; i < times.size(); ++i) { snprintf(num, sizeof num, "%.3f", times[i].second); o += (i ? ", \"" : "\"") + times[i].first + "\": " + num; }
         o += "}, \"counters\": {";
-        for (uint32_t i = 0; i < n && i < 12; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);
+        for (uint32_t i = 0; i < n && i < 14; ++i) o += std::string(i ? ", \"" : "\"") + kCounterNames[i] + "\": " + std::to_string(cnt[i]);
         o += "}}";
         if (needed) *needed = o.size() + 1;
         if (!json || cap < o.size() + 1) return (json || cap) ? fail(LB_ERR_INVALID_ARGUMENT, "buffer too small") : (needed ? (int)LB_OK : fail(LB_ERR_INVALID_ARGUMENT, "null"));
@@ -806,7 +833,7 @@ LB_API int lb_set_stream(LbRenderer r, void* s) {
 // ---- debug taps
 LB_API int lb_debug_trace_closest(LbRenderer r, const float* rays6, uint32_t n, float tmin, float tmax, void* hits20) {
     return guarded(R_, [&]() {
-        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene();
+        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene(); else if (R_->transforms_dirty) R_->refit_scene();
         if (!n) return (int)LB_OK;
         DevBuf<float> d_rays; DevBuf<unsigned char> d_hits;
         d_rays.upload(rays6, (size_t)n * 6, R_->stream); d_hits.reserve((size_t)n * 20);
@@ -816,7 +843,7 @@ LB_API int lb_debug_trace_closest(LbRenderer r, const float* rays6, uint32_t n, 
 }
 LB_API int lb_debug_trace_any(LbRenderer r, const float* rays6, const float* tmaxs, uint32_t n, float tmin, uint8_t* occ) {
     return guarded(R_, [&]() {
-        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene();
+        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene(); else if (R_->transforms_dirty) R_->refit_scene();
         if (!n) return (int)LB_OK;
         DevBuf<float> d_rays, d_tmax; DevBuf<uint8_t> d_occ;
         d_rays.upload(rays6, (size_t)n * 6, R_->stream); d_tmax.upload(tmaxs, n, R_->stream); d_occ.reserve(n);
@@ -826,7 +853,7 @@ LB_API int lb_debug_trace_any(LbRenderer r, const float* rays6, const float* tma
 }
 LB_API int lb_debug_read_lights(LbRenderer r, float* l16, float* cdf, uint32_t cap, uint32_t* count) {
     return guarded(R_, [&]() {
-        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene();
+        if (R_->scene_dirty || R_->resources_dirty) R_->commit_scene(); else if (R_->transforms_dirty) R_->refit_scene();
         const uint32_t n = R_->lights.num_lights; if (count) *count = n;
         if (cap < n) return fail(LB_ERR_INVALID_ARGUMENT, "capacity");
         if (n && l16) { const int rc = read_back(R_, R_->lights.lights.p, (size_t)n * 64, l16, (size_t)cap * 64); if (rc) return rc; }

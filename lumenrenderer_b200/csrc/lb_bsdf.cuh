@@ -448,7 +448,10 @@ struct BsdfCtx {
 
 LB_D float3 bsdf_eval(const Material& mat, const float3& iN, const float3& iT, const float3& wow, const float3& wiw, float& pdf) {
     const BsdfCtx c(mat, iN, iT, wow);
-    return c.eval(wiw, pdf);
+#if !defined(LB_ISO_PER_LANE) || LB_ISO_PER_LANE
+    if (c.is_isotropic()) return c.eval<true>(wiw, pdf);
+#endif
+    return c.eval<false>(wiw, pdf);
 }
 
 // ---------------------------------------------------------------- SampleBSDF (disney.cuh:173-304)

@@ -231,9 +231,67 @@ __device__ __forceinline__ uint32_t quant_exponent(float extent) {
     return (uint32_t)max(1, min(254, e));
 }
 
+__device__ __forceinline__ uint32_t quant_down(float v, float p, float inv, float scale) { float q = floorf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q > 0.f && p + q * scale > v) q -= 1.f; return (uint32_t)q; }
+__device__ __forceinline__ uint32_t quant_up(float v, float p, float inv, float scale) { float q = ceilf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q < 255.f && p + q * scale < v) q += 1.f; return (uint32_t)q; }
+
+// ---- refit (bvh_refit): gather the moved triangles into leaf order, then recompute the boxes level by level from the deepest level up
+__global__ void k_regather(const DevTri* __restrict__ tris_in, const uint32_t* __restrict__ perm, uint32_t n, DevTri* __restrict__ tris_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tris_out[i] = tris_in[perm[i]];
+}
+__global__ void k_refit_level(Bvh8Node* __restrict__ nodes, uint32_t first, uint32_t count, const DevTri* __restrict__ tris, float4* __restrict__ box_lo, float4* __restrict__ box_hi) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= count) return;
+    const uint32_t id = first + w;
+    Bvh8Node nd = nodes[id];
+    const uint32_t imask = nd.q0.w >> 24, child_base = nd.q1.x, tri_base = nd.q1.y;
+    float3 clo[8], chi[8]; bool used[8];
+    float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
+    for (int s = 0; s < 8; ++s) {
+        const uint32_t m = ((s < 4 ? nd.q1.z : nd.q1.w) >> (8 * (s & 3))) & 0xFFu;
+        used[s] = m != 0u;
+        if (!used[s]) continue;
+        float3 l, h;
+        if (imask & (1u << s)) { const uint32_t c = child_base + __popc(imask & ((1u << s) - 1u)); l = f3(box_lo[c]); h = f3(box_hi[c]); }
+        else {
+            const uint32_t k = __popc(m >> 5), off = m & 31u;
+            l = f3(FLT_MAX); h = f3(-FLT_MAX);
+            for (uint32_t t = 0; t < k; ++t) {
+                const DevTri tr = tris[tri_base + off + t];
+                const float3 a = f3(tr.v0), b = f3(tr.v1), c = f3(tr.v2);
+                float3 tl = f3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+                float3 th = f3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+                const float3 p = f3(pad_of(tl.x, th.x), pad_of(tl.y, th.y), pad_of(tl.z, th.z));          // the padding of k_tri_bounds
+                tl = tl - p; th = th + p;
+                l = f3(fminf(l.x, tl.x), fminf(l.y, tl.y), fminf(l.z, tl.z)); h = f3(fmaxf(h.x, th.x), fmaxf(h.y, th.y), fmaxf(h.z, th.z));
+            }
+        }
+        clo[s] = l; chi[s] = h;
+        lo = f3(fminf(lo.x, l.x), fminf(lo.y, l.y), fminf(lo.z, l.z)); hi = f3(fmaxf(hi.x, h.x), fmaxf(hi.y, h.y), fmaxf(hi.z, h.z));
+    }
+    box_lo[id] = f4(lo, 0.f); box_hi[id] = f4(hi, 0.f);
+    const uint32_t ex = quant_exponent(hi.x - lo.x), ey = quant_exponent(hi.y - lo.y), ez = quant_exponent(hi.z - lo.z);
+    const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+    const float ix = 1.0f / sx, iy = 1.0f / sy, iz = 1.0f / sz;
+    uint32_t qlo[3][8], qhi[3][8];
+    for (int s = 0; s < 8; ++s) {
+        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; }
+        if (!used[s]) continue;
+        qlo[0][s] = quant_down(clo[s].x, lo.x, ix, sx); qlo[1][s] = quant_down(clo[s].y, lo.y, iy, sy); qlo[2][s] = quant_down(clo[s].z, lo.z, iz, sz);
+        qhi[0][s] = quant_up(chi[s].x, lo.x, ix, sx); qhi[1][s] = quant_up(chi[s].y, lo.y, iy, sy); qhi[2][s] = quant_up(chi[s].z, lo.z, iz, sz);
+    }
+    auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+    nd.q0 = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+    nd.q2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    nd.q3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    nd.q4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    nodes[id] = nd;
+}
+
 __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items, WorkItem* __restrict__ next, uint32_t* __restrict__ counters /* 0: nodes, 1: tris, 2: next items */,
                            int n, const uint2* __restrict__ children, const uint32_t* __restrict__ count, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                           const uint32_t* __restrict__ sorted, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out) {
+                           const uint32_t* __restrict__ sorted, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out,
+                           uint32_t* __restrict__ perm_out) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_items) return;
     const WorkItem item = items[w];
@@ -298,10 +356,8 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
         if (c < 0) continue;
         const uint32_t node = cand[c];
         const float4 l = nlo[node], h = nhi[node];
-        auto qdown = [](float v, float p, float inv, float scale) { float q = floorf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q > 0.f && p + q * scale > v) q -= 1.f; return (uint32_t)q; };
-        auto qup = [](float v, float p, float inv, float scale) { float q = ceilf((v - p) * inv); q = fminf(fmaxf(q, 0.f), 255.f); while (q < 255.f && p + q * scale < v) q += 1.f; return (uint32_t)q; };
-        qlo[0][s] = qdown(l.x, plo.x, ix, sx); qlo[1][s] = qdown(l.y, plo.y, iy, sy); qlo[2][s] = qdown(l.z, plo.z, iz, sz);
-        qhi[0][s] = qup(h.x, plo.x, ix, sx); qhi[1][s] = qup(h.y, plo.y, iy, sy); qhi[2][s] = qup(h.z, plo.z, iz, sz);
+        qlo[0][s] = quant_down(l.x, plo.x, ix, sx); qlo[1][s] = quant_down(l.y, plo.y, iy, sy); qlo[2][s] = quant_down(l.z, plo.z, iz, sz);
+        qhi[0][s] = quant_up(h.x, plo.x, ix, sx); qhi[1][s] = quant_up(h.y, plo.y, iy, sy); qhi[2][s] = quant_up(h.z, plo.z, iz, sz);
         const uint32_t k = tri_count(node);
         if (k <= kLeafMax) {
             meta[s] = (((1u << k) - 1u) << 5) | tri_off;
@@ -309,7 +365,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
             uint32_t walk[kLeafMax + 1]; int wp = 0; walk[wp++] = node;
             while (wp > 0) {
                 const uint32_t b = walk[--wp];
-                if (b >= first_leaf) tris_out[tri_base + tri_off++] = tris_in[sorted[b - first_leaf]];
+                if (b >= first_leaf) { const uint32_t src = sorted[b - first_leaf]; perm_out[tri_base + tri_off] = src; tris_out[tri_base + tri_off++] = tris_in[src]; }
                 else { const uint2 ch = children[b]; walk[wp++] = ch.y; walk[wp++] = ch.x; }
             }
         } else {
@@ -344,6 +400,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     keys.reserve(n, s); keys_sorted.reserve(n, s); vals.reserve(n, s); sorted.reserve(n, s); counters.reserve(4, s);
     children.reserve(n, s); items_a.reserve(n, s); items_b.reserve(n, s);
     out.nodes.reserve(n); out.tris.reserve(3 * (size_t)n);          // three axis-rotated copies of the leaf-ordered triangles (k_rotate_tris)
+    out.perm.reserve(n); out.box_lo.reserve(n); out.box_hi.reserve(n); out.level_start.clear(); out.refits = 0;
 
     const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
@@ -399,20 +456,42 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     LB_CUDA(cudaMemcpyAsync(items_a.p, &root_item, sizeof root_item, cudaMemcpyHostToDevice, s));
     uint32_t n_items = 1; WorkItem* cur = items_a.p; WorkItem* nxt = items_b.p;
     uint32_t h_c[4];
+    uint32_t level_first = 0;                               // the nodes of a level are a contiguous range: [level_first, level_first + n_items)
     while (n_items) {
+        out.level_start.push_back(level_first); level_first += n_items;
         LB_CUDA(cudaMemsetAsync(counters.p + 2, 0, sizeof(uint32_t), s));
-        k_collapse<<<grid_for(n_items, 128), 128, 0, s>>>(cur, n_items, nxt, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, tris_in, out.nodes.p, out.tris.p);
+        k_collapse<<<grid_for(n_items, 128), 128, 0, s>>>(cur, n_items, nxt, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, tris_in, out.nodes.p, out.tris.p, out.perm.p);
         LB_LAUNCH_CHECK();
         LB_CUDA(cudaMemcpyAsync(h_c, counters.p, sizeof h_c, cudaMemcpyDeviceToHost, s));
         LB_CUDA(cudaStreamSynchronize(s));
         n_items = h_c[2]; std::swap(cur, nxt); ++out.levels;
     }
+    out.level_start.push_back(level_first);
     out.num_nodes = h_c[0]; out.num_tris = h_c[1];
     if (out.num_tris == n) { k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(out.tris.p, n); LB_LAUNCH_CHECK(); }
     LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
     LB_CUDA(cudaEventElapsedTime(&out.build_ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (out.num_tris != n) throw CudaError("bvh_build: triangle count mismatch after collapse");
+    if (level_first != out.num_nodes) throw CudaError("bvh_build: level ranges do not cover the nodes");
+}
+
+void bvh_refit(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& bvh) {
+    if (n == 0 || bvh.num_tris != n || bvh.level_start.size() != (size_t)bvh.levels + 1u) throw CudaError("bvh_refit: the hierarchy was not built from this many triangles");
+    cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
+    LB_CUDA(cudaEventRecord(e0, s));
+    const int B = 256;
+    k_regather<<<grid_for(n, B), B, 0, s>>>(tris_in, bvh.perm.p, n, bvh.tris.p); LB_LAUNCH_CHECK();
+    k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(bvh.tris.p, n); LB_LAUNCH_CHECK();
+    for (int level = (int)bvh.levels - 1; level >= 0; --level) {
+        const uint32_t first = bvh.level_start[level], count = bvh.level_start[level + 1] - first;
+        if (!count) continue;
+        k_refit_level<<<grid_for(count, 128), 128, 0, s>>>(bvh.nodes.p, first, count, bvh.tris.p, bvh.box_lo.p, bvh.box_hi.p); LB_LAUNCH_CHECK();
+    }
+    LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
+    LB_CUDA(cudaEventElapsedTime(&bvh.refit_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ++bvh.refits;
 }
 
 } // namespace lb

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include <cstdint>
 #include <cstdio>
 #include "lb_device.cuh"
@@ -64,8 +65,11 @@ struct StreamBuf {
 
 struct DeviceBvh {
     DevBuf<Bvh8Node> nodes; DevBuf<DevTri> tris;
-    uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0;
-    float build_ms = 0.f;
+    // what a refit needs (bvh_refit): leaf slot -> index of the source triangle, the first node of every level (nodes are created level by
+    // level, so a level is a contiguous range), and a full-precision box per node to hand up to its parent
+    DevBuf<uint32_t> perm; DevBuf<float4> box_lo, box_hi; std::vector<uint32_t> level_start;
+    uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0, refits = 0;
+    float build_ms = 0.f, refit_ms = 0.f;
     BvhView view(uint32_t* overflow = nullptr) const { return BvhView{nodes.p, tris.p, num_tris, overflow}; }
     size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + 3 * (size_t)num_tris * sizeof(DevTri); }      // three rotated triangle copies
 };
@@ -76,6 +80,13 @@ struct DeviceBvh {
 enum class BvhBuilder { PLOC, LBVH };
 // ploc_radius: neighbour search window of PLOC in Morton order (16, 64 or 128)
 void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC, int ploc_radius = 16);
+
+// Same topology, new triangle positions (instances moved): the leaf-ordered triangle copies are re-gathered from `tris_in` (the same source
+// order the hierarchy was built from) and every node's child boxes are recomputed bottom-up, level by level — no sort, no clustering, no
+// collapse. Hits stay exactly what a rebuild would give (they are a pure function of ray and triangle set); only the boxes' tightness,
+// i.e. speed, can degrade when instances move far from where the hierarchy was built. Replaces the reference's IAS rebuild on a transform
+// change (PTScene.cpp:74-156, PTMeshInstance.cpp:51-103).
+void bvh_refit(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& bvh);
 
 inline int grid_for(size_t n, int block) { return (int)((n + block - 1) / block); }
 

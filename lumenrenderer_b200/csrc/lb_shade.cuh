@@ -10,6 +10,9 @@
 //                        arithmetic on raw RGBA8 texels so results do not depend on the 9-bit texture-unit filter
 #pragma once
 #include "lb_bsdf.cuh"
+#ifndef LB_ISO_PER_LANE
+#define LB_ISO_PER_LANE 1
+#endif
 
 namespace lb {
 
@@ -182,7 +185,13 @@ LB_D void resample(const LightSample& in, const float3& ppos, const float3& pnor
     out = in;
     ResampleGeom g;
     if (!resample_geom(in.position, in.normal, in.area, ppos, pnormal, g)) { out.pdf = 0; return; }
+#if LB_ISO_PER_LANE
+    // per lane (temporal / spatial reuse, buffer merge): isotropic materials — nearly all — take the evaluation that has no anisotropic terms
+    // instead of executing them predicated-off
+    if (ctx.is_isotropic()) resample_shade<1>(ctx, g, out); else resample_shade<0>(ctx, g, out);
+#else
     resample_shade(ctx, g, out);
+#endif
 }
 LB_D BsdfCtx surface_ctx(const Surface& px) { return BsdfCtx(px.mat, px.normal, px.tangent, -px.incoming); }
 

@@ -251,4 +251,37 @@ def test_dynamic_scene_moving_camera_and_instance(oracle):
     assert nonzero_mv >= 3
     rg, rc = g.read_reservoirs(), c.read_reservoirs()
     assert (rg[..., 2] != rc[..., 2]).mean() < 1e-3
+    assert g.frame_counters()["bvh_refits"] == 3          # the three instance moves refitted the hierarchies (no rebuild), and stayed bit-exact
     g.close(); c.close()
+
+
+def test_refitted_hierarchy_returns_the_hits_of_a_rebuilt_one(gpu):
+    """bvh_refit (instances moved -> same topology, new boxes) against a full rebuild of the same final scene: hit records of 200 K random
+    rays bit-identical, closest-hit and any-hit; instances are moved far (boxes that were disjoint at build time now overlap) and back."""
+    scene = scenes.material_gallery()
+    rng = np.random.default_rng(9)
+    o = rng.uniform(-3, 3, (200_000, 3)).astype(np.float32); o[:, 1] = np.abs(o[:, 1])
+    d = rng.normal(size=(200_000, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tmax = (rng.random(200_000) * 8).astype(np.float32)
+    st = lr.Settings(width=64, height=48, depth=2, restir=True)
+    moves = [(k, scenes.translate(*(rng.uniform(-1.5, 1.5, 3) * [1, 0.2, 1]), 1.0, float(rng.uniform(0, 360)))) for k in range(1, min(6, len(scene.instances)))]
+    with api.Renderer(gpu, st) as a:
+        a.load_scene(scene); a.render_frames(1)
+        for step in range(3):
+            for k, m in moves:
+                mm = np.asarray(m, np.float32).reshape(4, 4).copy(); mm[:3, 3] *= np.float32(step + 1)
+                a.set_instance_transform(k, mm)
+            a.render_frames(1)
+        ca = a.frame_counters()
+        assert ca["bvh_refits"] == 3 and ca["stack_overflows"] == 0
+        ha, oa, la = a.trace_closest(o, d), a.trace_any(o, d, tmax), a.read_lights()
+    moved_scene = scenes.material_gallery()
+    for k, m in moves:
+        mm = np.asarray(m, np.float32).reshape(4, 4).copy(); mm[:3, 3] *= np.float32(3)
+        moved_scene.instances[k]["transform"] = mm
+    with api.Renderer(gpu, st) as b:
+        b.load_scene(moved_scene); b.render_frames(1)
+        assert b.frame_counters()["bvh_refits"] == 0
+        hb, ob, lb_ = b.trace_closest(o, d), b.trace_any(o, d, tmax), b.read_lights()
+    assert np.array_equal(ha, hb) and np.array_equal(oa, ob) and (ha["t"] > 0).mean() > 0.3
+    assert np.array_equal(la[0], lb_[0]) and np.array_equal(la[1], lb_[1])
