@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include "lb_bsdf.cuh"
 #include "lb_png.h"
+#include <cuda.h>                     // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time: no link against libcuda)
 #include <vector>
 #include <string>
 #include <memory>
@@ -89,6 +90,28 @@ struct Renderer {
     DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags, d_ris_order;
     // direction-binned queue of the ReSTIR visibility rays (lb_restir.cu k_vis_bin), LB_VIS_SORT=1. Off by default: measured on C2 the binned
     // trace is 5.5 % faster (1.586 -> 1.499 ms for both passes) but the binning pre-pass costs 0.230 ms (profiles/r02_a_ab.md)
+    // TMA descriptors of surface plane 1 (normal + signed depth) of both surface buffers: the spatial-reuse pass stages a 92 x 76 box of it per
+    // 32 x 16-pixel tile in shared memory (lb_restir.cu k_spatial_tma). LB_SPATIAL_TMA=0: gather from global memory instead.
+    CUtensorMap tmap_geom[2]; bool have_tmap = false;
+    bool spatial_tma = []() { const char* e = getenv("LB_SPATIAL_TMA"); return !e || atoi(e) != 0; }();
+    void make_tensor_maps() {
+        have_tmap = false;
+        if (!spatial_tma) return;
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = []() -> EncodeFn {
+            void* p = nullptr; cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+            return (EncodeFn)p;
+        }();
+        if (!encode) return;
+        const cuuint64_t dims[3] = {4, st.width, st.height}, strides[2] = {16, (cuuint64_t)st.width * 16};
+        const cuuint32_t box[3] = {4, 32 + 2 * 30, 16 + 2 * 30}, estr[3] = {1, 1, 1};
+        for (int k = 0; k < 2; ++k)
+            if (encode(&tmap_geom[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d_surf[k].p + npix(), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+        have_tmap = true;
+    }
     DevBuf<float4> d_vis_rays[2];
     bool vis_sort = vis_sort_default();
     static bool vis_sort_default() { const char* e = getenv("LB_VIS_SORT"); return e && atoi(e) != 0; }
@@ -185,6 +208,7 @@ struct Renderer {
         d_vol_hits.reserve(n); for (auto& p : d_vol_shadow) p.reserve(n * 5);
         d_hits.reserve(n); d_primary_hits.reserve(n); d_primary_hits.zero(stream); d_motion.reserve(n); d_motion.zero(stream); d_ldr.reserve(n); d_ldr.zero(stream);
         blend_count = 0; frame_index = 0; surf_cur = 0; res_cur = 0; have_prev_cam = false;
+        make_tensor_maps();
     }
 
     // ---- materials: WaveFrontRenderer::CreateMaterial (WaveFrontRenderer.cpp:1260-1311) + PTMaterial setters (PTMaterial.cpp:160-266)
@@ -444,7 +468,7 @@ struct Renderer {
             RestirArgs ra{seed0, (int)st.restir_temporal, (int)st.restir_spatial};
             static const int ris_simple = []() { const char* e = getenv("LB_RIS_SIMPLE"); return (!e || atoi(e) != 0) ? 1 : 0; }();
             ra.ris_simple = ris_simple; ra.unbiased = st.restir_unbiased ? 1 : 0;
-            RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr};
+            RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr, have_tmap ? &tmap_geom[surf_cur] : nullptr};
             LaunchCfg cr = c;
             if (on_side) {
                 need_side_stream();

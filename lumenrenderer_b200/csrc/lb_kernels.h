@@ -84,7 +84,8 @@ void launch_debug_reservoirs(const LaunchCfg&, const float4* planes, uint32_t np
 void launch_debug_hits(const LaunchCfg&, const uint4* hits, uint32_t n, void* hits20);
 
 // ---- ReSTIR (lb_restir.cu)
-struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; float4* vis_ray_o = nullptr; float4* vis_ray_d = nullptr; };      // vis_ray_*: binned visibility-ray queue (o.xyz, tmax | d.xyz, pixel), nullptr = trace straight from the reservoirs      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
+struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; float4* vis_ray_o = nullptr; float4* vis_ray_d = nullptr;
+                       const void* tmap_geom = nullptr; };      // CUtensorMap of the current frame's surface plane 1 (k_spatial_tma), nullptr = gather from global memory      // vis_ray_*: binned visibility-ray queue (o.xyz, tmax | d.xyz, pixel), nullptr = trace straight from the reservoirs      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
 void launch_restir(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView&, const RestirBuffers&, const RestirArgs&, uint32_t& ticket);
 
 // ---- scene preparation (lb_scene.cu)

@@ -16,6 +16,7 @@
 #include "lb_trace.cuh"
 #include "lb_shade.cuh"
 #include <cfloat>
+#include <cuda.h>                     // CUtensorMap (type only: the driver entry point is resolved at run time, lb_api.cu)
 
 namespace lb {
 
@@ -507,76 +508,138 @@ LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i)
     return p;
 }
 
-template <bool UNBIASED>
-__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+// One pixel of SpatialNeighbourSamplingInternal (ReSTIRKernels.cu:787-980). `geom_at(nx, ny, index)` returns the similarity record (surface
+// plane 1: normal, signed depth) of a pixel inside the image — from global memory (k_spatial) or from the tile staged in shared memory
+// (k_spatial_tma).
+template <bool UNBIASED, class GeomAt>
+LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed, int x, int y, const GeomAt& geom_at) {
     const size_t np = fv.npix;
     const int W = (int)fv.width, H = (int)fv.height;
-    const TileWalk tw(fv);
-    const float4* __restrict__ geom = fv.surf_cur + np;          // plane 1: normal, signed depth
     const bool degenerate = seed == 0u;
+    const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
+    const SurfGeom gc = surf_geom_unpack(geom_at(x, y, i));
+    if (gc.flagged) return;
+    uint32_t s = wang_hash(seed + i + fv.pix0);
+    // all five neighbour probes are issued before any is tested (5 independent 16-byte reads in flight)
+    uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
+#pragma unroll
+    for (uint32_t k = 0; k < kSpatialSamples; ++k) {
+        const int ny = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + y;
+        const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
+        inside[k] = !(nx < 0 || nx >= W || ny < 0 || ny >= H);
+        ni[k] = inside[k] ? (uint32_t)ny * fv.width + (uint32_t)nx : i;
+        ng[k] = inside[k] ? geom_at(nx, ny, ni[k]) : geom_at(x, y, i);
+    }
+    uint32_t nb[kSpatialSamples]; int count = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kSpatialSamples; ++k) {
+        const SurfGeom gn = surf_geom_unpack(ng[k]);
+        if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) nb[count++] = ni[k];
+    }
+    if (count > 1) {
+        ResProbe cur = res_probe(in, np, nb[0]);
+        Surface p0; surface_load_shading(fv.surf_cur, np, nb[0], p0);      // resampled at the FIRST accepted neighbour
+        const BsdfCtx ctx = surface_ctx(p0);
+        Reservoir acc = reservoir_zero(); int total = 0;
+#pragma unroll 1
+        for (int k = 0; k < count; ++k) {
+            ResProbe nxt = cur;
+            if (k + 1 < count) nxt = res_probe(in, np, nb[k + 1]);          // next neighbour's reservoir is in flight during this evaluation
+            LightSample q; q.position = f3(cur.b); q.area = cur.b.w; q.normal = f3(cur.c); q.radiance = f3(cur.d); q.pdf = cur.a.w;
+            // a geometrically rejected sample keeps its stored contribution, but it can only be selected when the acceptance draw is
+            // exactly 0, i.e. for the all-zero xorshift state: only then is plane 4 fetched
+            q.contribution = degenerate ? f3(in[4 * np + nb[k]]) : f3(0.f);
+            const int qcount = __float_as_int(cur.a.z); const float qweight = cur.a.y;
+            LightSample rs; resample(q, p0.pos, p0.normal, ctx, rs);
+            reservoir_update(acc, rs, (float)qcount * qweight * rs.pdf, seed);   // kernel-wide seed by value (hazard 14)
+            total += qcount;
+            cur = nxt;
+        }
+        acc.count = total;
+        if (!UNBIASED) reservoir_update_weight(acc);
+        else {
+            // the unbiased branch, ReSTIRKernels.cu:905-970: the selected sample re-evaluated at every accepted neighbour; the reference adds
+            // the sample count of the OUTPUT buffer's stale reservoir of this pixel (a_ReservoirsOut[index].sampleCount, :951) — as written
+            const int stale = __float_as_int(out[i].z);
+            int correction = 0;
+#pragma unroll 1
+            for (int k = 0; k < count; ++k) {
+                Surface pk; surface_load_shading(fv.surf_cur, np, nb[k], pk);
+                const BsdfCtx ck = surface_ctx(pk);
+                LightSample rs; resample(acc.s, pk.pos, pk.normal, ck, rs);
+                if (rs.pdf > 0) correction += stale;
+            }
+            const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);
+            acc.weight = (1.f / fmaxf(acc.s.pdf, FLT_EPSILON)) * (m * acc.weight_sum);
+        }
+        reservoir_store(out, np, i, acc);
+    } else {
+        const float4 r0 = out[i];                                   // Reservoir::Reset keeps the stored sample
+        out[i] = make_float4(0.f, 0.f, __int_as_float(0), r0.w);
+    }
+}
+
+template <bool UNBIASED>
+__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+    const TileWalk tw(fv);
+    const float4* __restrict__ geom = fv.surf_cur + fv.npix;          // plane 1: normal, signed depth
+    auto geom_at = [geom](int, int, uint32_t index) { return geom[index]; };
     for (uint32_t item = tw.next(ticket); item < tw.nitems; item = tw.next(ticket)) {
         int x, y;
         if (!tw.pixel(fv, item, x, y)) continue;
-        const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
-        const SurfGeom gc = surf_geom_unpack(geom[i]);
-        if (gc.flagged) continue;
-        uint32_t s = wang_hash(seed + i + fv.pix0);
-        // all five neighbour probes are issued before any is tested (5 independent 16-byte gathers in flight)
-        uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
-#pragma unroll
-        for (uint32_t k = 0; k < kSpatialSamples; ++k) {
-            const int ny = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + y;
-            const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
-            inside[k] = !(nx < 0 || nx >= W || ny < 0 || ny >= H);
-            ni[k] = inside[k] ? (uint32_t)ny * fv.width + (uint32_t)nx : i;
-            ng[k] = geom[ni[k]];
-        }
-        uint32_t nb[kSpatialSamples]; int count = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < kSpatialSamples; ++k) {
-            const SurfGeom gn = surf_geom_unpack(ng[k]);
-            if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) nb[count++] = ni[k];
-        }
-        if (count > 1) {
-            ResProbe cur = res_probe(in, np, nb[0]);
-            Surface p0; surface_load_shading(fv.surf_cur, np, nb[0], p0);      // resampled at the FIRST accepted neighbour
-            const BsdfCtx ctx = surface_ctx(p0);
-            Reservoir acc = reservoir_zero(); int total = 0;
+        spatial_pixel<UNBIASED>(fv, in, out, seed, x, y, geom_at);
+    }
+}
+
+// ---- the same pass with the neighbourhood's similarity records staged in shared memory by the TMA unit (north_star item 3).
+// A block owns a 32x16-pixel tile; every neighbour a pixel of the tile can draw lies within +-30 pixels, so ONE tensor copy
+// (cp.async.bulk.tensor.3d, box 4 floats x 92 x 76 = 111 872 bytes of surface plane 1, zero-filled outside the image) brings in everything
+// the five similarity probes of all 512 pixels can touch; the probes — the first dependent step of every pixel — are then shared-memory
+// reads (29 cycles) instead of L2 / DRAM gathers. Two blocks per SM: while one waits for its tile the other evaluates. The reservoirs of the
+// ACCEPTED neighbours (4 planes) and the surface of the first one (8 planes) do not fit beside the tile and stay global gathers.
+constexpr int kSpTileW = 32, kSpTileH = 16, kSpHalo = (int)kSpatialRadius, kSpBoxW = kSpTileW + 2 * kSpHalo, kSpBoxH = kSpTileH + 2 * kSpHalo;
+constexpr uint32_t kSpTileBytes = (uint32_t)(kSpBoxW * kSpBoxH * sizeof(float4));
+static_assert(2u * (kSpTileBytes + 2048u) <= 228u * 1024u, "two blocks of the TMA-staged spatial pass per SM");
+static_assert(kBlock / 32 * 2 == kSpTileH, "8 warps x 2 rows = the 16 rows of a tile");
+extern __shared__ __align__(128) unsigned char sp_smem[];
+
+LB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LB_D void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+LB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+LB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+LB_D void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(kBlock, 2) k_spatial_tma(FrameView fv, const __grid_constant__ CUtensorMap tmap, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+    float4* tile = reinterpret_cast<float4*>(sp_smem);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tile;
+    const uint32_t tiles_x = (fv.width + kSpTileW - 1u) / kSpTileW, tiles_y = (fv.height + kSpTileH - 1u) / kSpTileH, ntiles = tiles_x * tiles_y;
+    constexpr uint32_t kStrip = 16u;                               // tiles are walked in vertical strips 16 tiles (512 px) wide, like TileWalk: the
+    const uint32_t full = kStrip * tiles_y;                        // gathers of neighbouring blocks then share L2 lines
+    if (threadIdx.x == 0) { mbar_init(&bar, 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    uint32_t parity = 0u;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();                                           // the ticket is visible — and nobody reads the previous tile any more
+        const uint32_t t = s_tile;
+        __syncthreads();
+        if (t >= ntiles) break;
+        const uint32_t strip = t / full, r = t - strip * full, sw = min(kStrip, tiles_x - strip * kStrip);
+        const uint32_t ty = r / sw, tx = strip * kStrip + (r - ty * sw);
+        const int x0 = (int)(tx * kSpTileW), y0 = (int)(ty * kSpTileH), bx = x0 - kSpHalo, by = y0 - kSpHalo;
+        if (threadIdx.x == 0) { mbar_expect_tx(&bar, kSpTileBytes); tma_load_3d(tile, &tmap, &bar, 0, bx, by); }
+        mbar_wait(&bar, parity); parity ^= 1u;
+        auto geom_at = [tile, bx, by](int nx, int ny, uint32_t) { return tile[(ny - by) * kSpBoxW + (nx - bx)]; };
 #pragma unroll 1
-            for (int k = 0; k < count; ++k) {
-                ResProbe nxt = cur;
-                if (k + 1 < count) nxt = res_probe(in, np, nb[k + 1]);          // next neighbour's reservoir is in flight during this evaluation
-                LightSample q; q.position = f3(cur.b); q.area = cur.b.w; q.normal = f3(cur.c); q.radiance = f3(cur.d); q.pdf = cur.a.w;
-                // a geometrically rejected sample keeps its stored contribution, but it can only be selected when the acceptance draw is
-                // exactly 0, i.e. for the all-zero xorshift state: only then is plane 4 fetched
-                q.contribution = degenerate ? f3(in[4 * np + nb[k]]) : f3(0.f);
-                const int qcount = __float_as_int(cur.a.z); const float qweight = cur.a.y;
-                LightSample rs; resample(q, p0.pos, p0.normal, ctx, rs);
-                reservoir_update(acc, rs, (float)qcount * qweight * rs.pdf, seed);   // kernel-wide seed by value (hazard 14)
-                total += qcount;
-                cur = nxt;
-            }
-            acc.count = total;
-            if (!UNBIASED) reservoir_update_weight(acc);
-            else {
-                // the unbiased branch, ReSTIRKernels.cu:905-970: the selected sample re-evaluated at every accepted neighbour; the reference adds
-                // the sample count of the OUTPUT buffer's stale reservoir of this pixel (a_ReservoirsOut[index].sampleCount, :951) — as written
-                const int stale = __float_as_int(out[i].z);
-                int correction = 0;
-#pragma unroll 1
-                for (int k = 0; k < count; ++k) {
-                    Surface pk; surface_load_shading(fv.surf_cur, np, nb[k], pk);
-                    const BsdfCtx ck = surface_ctx(pk);
-                    LightSample rs; resample(acc.s, pk.pos, pk.normal, ck, rs);
-                    if (rs.pdf > 0) correction += stale;
-                }
-                const float m = 1.f / fmaxf((float)correction, FLT_EPSILON);
-                acc.weight = (1.f / fmaxf(acc.s.pdf, FLT_EPSILON)) * (m * acc.weight_sum);
-            }
-            reservoir_store(out, np, i, acc);
-        } else {
-            const float4 r0 = out[i];                                   // Reservoir::Reset keeps the stored sample
-            out[i] = make_float4(0.f, 0.f, __int_as_float(0), r0.w);
+        for (int row = 0; row < 2; ++row) {
+            const int x = x0 + (int)(threadIdx.x & 31u), y = y0 + (int)(threadIdx.x >> 5) * 2 + row;
+            if ((uint32_t)x < fv.width && (uint32_t)y < fv.height) spatial_pixel<false>(fv, in, out, seed, x, y, geom_at);
         }
     }
 }
@@ -631,7 +694,10 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
             if (a.unbiased) k_spatial<true><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
-            else k_spatial<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            else if (rb.tmap_geom) {
+                LB_CUDA(cudaFuncSetAttribute(k_spatial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpTileBytes));
+                k_spatial_tma<<<cfg.sms * 2, kBlock, kSpTileBytes, st>>>(fv, *static_cast<const CUtensorMap*>(rb.tmap_geom), &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            } else k_spatial<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
             LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }

@@ -137,12 +137,14 @@ void build_lights(const LaunchCfg& cfg, const SceneView& sc, const ScenePrepIn& 
     const uint32_t n = in.total_tris;
     if (!n) return;
     cudaStream_t s = cfg.stream;
-    DevBuf<uint32_t> flags, offsets; DevBuf<unsigned char> tmp;
-    flags.reserve(n); offsets.reserve(n);
+    // scratch from the stream-ordered pool (StreamBuf): a dynamic scene rebuilds the light list after every instance move, and ten cudaMalloc /
+    // cudaFree pairs (each a device-wide synchronisation) cost more than the kernels — up to 100 ms of host time on the 10 M-triangle C4
+    StreamBuf<uint32_t> flags, offsets; StreamBuf<unsigned char> tmp;
+    flags.reserve(n, s); offsets.reserve(n, s);
     k_light_flags<<<cfg.sms * 8, 256, 0, s>>>(sc, in, prim_flags, flags.p); LB_LAUNCH_CHECK();
     size_t tb = 0;
     LB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags.p, offsets.p, (int)n, s));
-    tmp.reserve(tb);
+    tmp.reserve(tb, s);
     LB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, offsets.p, (int)n, s));
     uint32_t last_flag = 0, last_off = 0;
     LB_CUDA(cudaMemcpyAsync(&last_flag, flags.p + (n - 1), 4, cudaMemcpyDeviceToHost, s));
@@ -150,17 +152,17 @@ void build_lights(const LaunchCfg& cfg, const SceneView& sc, const ScenePrepIn& 
     LB_CUDA(cudaStreamSynchronize(s));
     const uint32_t nl = last_flag + last_off;
     if (!nl) return;
-    DevBuf<DevLight> unsorted; DevBuf<uint32_t> keys, keys2, vals, order; DevBuf<float> totals;
-    unsorted.reserve(nl); keys.reserve(nl); keys2.reserve(nl); vals.reserve(nl); order.reserve(nl);
+    StreamBuf<DevLight> unsorted; StreamBuf<uint32_t> keys, keys2, vals, order; StreamBuf<float> totals;
+    unsorted.reserve(nl, s); keys.reserve(nl, s); keys2.reserve(nl, s); vals.reserve(nl, s); order.reserve(nl, s);
     out.lights.reserve(nl); out.cdf.reserve(nl);
     k_light_emit<<<cfg.sms * 8, 256, 0, s>>>(sc, in, prim_flags, flags.p, offsets.p, unsorted.p, keys.p, vals.p); LB_LAUNCH_CHECK();
     size_t sb = 0;
     LB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sb, keys.p, keys2.p, vals.p, order.p, (int)nl, 0, 32, s));
-    DevBuf<unsigned char> tmp2; tmp2.reserve(sb);
+    StreamBuf<unsigned char> tmp2; tmp2.reserve(sb, s);
     LB_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, sb, keys.p, keys2.p, vals.p, order.p, (int)nl, 0, 32, s));
     k_light_gather<<<grid_for(nl, 256), 256, 0, s>>>(unsorted.p, order.p, nl, out.lights.p); LB_LAUNCH_CHECK();
     const uint32_t nb = (nl + 255u) / 256u;
-    totals.reserve(nb);
+    totals.reserve(nb, s);
     k_cdf_blocks<<<grid_for(nb, 64), 64, 0, s>>>(out.lights.p, nl, out.cdf.p, totals.p); LB_LAUNCH_CHECK();
     k_cdf_offsets<<<1, 1, 0, s>>>(totals.p, nb); LB_LAUNCH_CHECK();
     k_cdf_apply<<<grid_for(nl, 256), 256, 0, s>>>(out.cdf.p, nl, totals.p); LB_LAUNCH_CHECK();

@@ -6,7 +6,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 k=0
 for envs in "$@"; do
-  env $envs python bench.py --no-cpu-baseline --steps 20 --warmup 8 > gpurun_out/${TAG}_$k.json 2> gpurun_out/${TAG}_$k.err
+  env $envs python bench.py --no-cpu-baseline --no-extras --steps 20 --warmup 8 > gpurun_out/${TAG}_$k.json 2> gpurun_out/${TAG}_$k.err
   python - "$envs" gpurun_out/${TAG}_$k.json <<'PY'
 import json, sys
 try:
