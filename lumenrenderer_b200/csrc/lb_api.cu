@@ -127,6 +127,7 @@ struct Renderer {
     // the bounce waves (extend / shade / shadow at depth > 0) write only the other channels. They run as two chains that fork after the
     // primary shade and join before the merge, so that the latency-bound tail waves can execute under the ReSTIR kernels. Off by default:
     // on B200 the two chains of persistent grids interfere (8.45 -> 8.87..9.45 ms/frame, profiles/r01_p_experiments.md).
+    // bit 3 (default on) = from the third wave on the bounce chain is one launch, a lane per path (k_tail).
     // `overlap` is a mask: bit 0 (default on) = the shadow rays of bounce wave d run on the side stream under the extend of wave d + 1 — two
     // small latency-bound launches that share nothing but read-only data; bit 1 (default off) = the ReSTIR chain on the side stream beside ALL
     // bounce waves; bit 2 (default on) = the ReSTIR chain is launched after the first bounce wave and the later waves run beside it.
@@ -139,7 +140,7 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
-    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 7) : 5; }      // whole-chain overlap (bit 1) off: measured slower
+    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 15) : 13; }      // whole-chain overlap (bit 1) off: measured slower
     static TraceTuning trace_tuning(bool any) {
         TraceTuning t;
         if (const char* e = getenv(any ? "LB_TRACE_ANY_REFILL_MIN" : "LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);
@@ -486,6 +487,14 @@ struct Renderer {
             const int queue = (int)(depth & 1u);
             LaunchCfg cb = c; if (tail_forked) cb.stream = restir_stream;         // stream of the bounce chain
             const int chain = tail_forked ? 1 : 0;
+            // overlap bit 3: from the third wave on, the rest of the bounce chain is ONE launch, a lane per path (lb_wavefront.cu k_tail)
+            if (depth >= 2u && (overlap & 8) && a.num_volumes == 0u) {
+                // wave (depth - 1)'s shadow rays on the side stream add into the same INDIRECT channel: they come first
+                if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(cb.stream, ev_shadow, 0)); shadow_in_flight = false; }
+                launch_tail(cb, fv, sc, bv, bva, queue, depth, st.depth, seed, 0.01f, 5000.f); ++launches;
+                lap("tail", chain);
+                break;
+            }
             launch_extend(cb, fv, bv, queue, take_ticket(), depth == 0, 0.01f, 5000.f); ++launches;
             lap("extend", chain);
             // the previous wave's shadow rays (side stream) read the shadow queue this wave's shade kernel is about to refill
@@ -847,7 +856,7 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
     return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
 }
 LB_API int lb_set_overlap(LbRenderer r, int enabled) {
-    return guarded(R_, [&]() { if (enabled < 0 || enabled > 7) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
+    return guarded(R_, [&]() { if (enabled < 0 || enabled > 15) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });
 }
 LB_API int lb_get_stream(LbRenderer r, void** s) { return guarded(R_, [&]() { if (!s) return fail(LB_ERR_INVALID_ARGUMENT, "null"); *s = (void*)R_->stream; return (int)LB_OK; }); }
 LB_API int lb_set_stream(LbRenderer r, void* s) {

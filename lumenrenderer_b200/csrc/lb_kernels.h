@@ -73,6 +73,9 @@ void launch_volume_extend(const LaunchCfg&, const FrameView&, int queue, bool pr
 void launch_volume_delta(const LaunchCfg&, const FrameView&, const SceneView&, int queue, bool primary, const ShadeArgs&);
 void launch_shade(const LaunchCfg&, const FrameView&, const SceneView&, int queue, const ShadeArgs&);
 void launch_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
+// waves first_depth .. max_depth - 1 of the bounce chain in one launch, a lane per path (no media): rays[queue] holds the input of wave first_depth
+void launch_tail(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView& closest, const BvhView& any_hit, int queue, uint32_t first_depth, uint32_t max_depth,
+                 uint32_t seed, float tmin, float tmax);
 void launch_volume_shadow(const LaunchCfg&, const FrameView&, const BvhView&, uint32_t ticket, float tmin);
 void launch_merge(const LaunchCfg&, const FrameView&, int blend, uint32_t blend_count);
 void launch_resolve(const LaunchCfg&, const FrameView&, float inv_frames);

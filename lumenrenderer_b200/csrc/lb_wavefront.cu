@@ -188,6 +188,53 @@ __global__ void __launch_bounds__(kBlock, 4) k_shadow(BvhView bvh, ShadowQueue q
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stat, (unsigned long long)n);
 }
 
+// ------------------------------------------------------------------ the late bounce waves as ONE launch (K2 + K6 + K10 + K3 + K11 per path)
+// From the third wave on a frame holds few rays (C2: 1e5, then 2e4 of 3.7 M pixels): a wave's extend, shade and shadow launches each last as
+// long as their slowest ray's chain of dependent node visits (~0.03 .. 0.1 ms), whatever their size, and every launch ends in a tail of idle
+// SMs. Here a LANE follows one path from its queue entry to its end — closest hit, surface extraction, NEE sample + its shadow ray, bounce,
+// next closest hit, ... — so the rest of the frame's bounce chain is one launch with no grid-wide step between the waves. Every stage is the
+// device function the per-wave kernels call, seeded per wave exactly as the host seeds the launches (seed_d+1 = WangHash(seed_d)), and the
+// fp32 adds into the pixel's INDIRECT channel happen in wave order: the image is bit-identical to the per-wave schedule.
+struct TailArgs { uint32_t first_depth, max_depth, seed; float tmin, tmax; };
+__global__ void __launch_bounds__(128, 4) k_tail(FrameView fv, SceneView sc, BvhView bvh, BvhView bvh_any, int queue, TailArgs a) {
+    const uint32_t n = fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A];
+    const RayQueue in = fv.rays[queue];
+    const size_t np = fv.npix;
+    uint32_t n_extend = 0u, n_shadow = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = in.o[i], d4 = in.d[i], T4 = in.T[i];
+        float3 o = f3(o4), d = f3(d4), T = f3(T4);
+        const uint32_t pixel = __float_as_uint(d4.w), gpixel = pixel + fv.pix0;
+        uint32_t seed = a.seed;
+        for (uint32_t depth = a.first_depth; depth < a.max_depth; ++depth, seed = wang_hash(seed)) {
+            HitInfo h; h.inst = 0u; h.prim = 0u; h.u = 0.f; h.v = 0.f; h.t = -1.f;
+            const bool hit = bvh8_trace<false>(bvh, o, d, a.tmin, a.tmax, h);
+            ++n_extend;
+            // the hit record of the wavefront path carries fp16 barycentrics (WaveFrontShaders.cu:318-321)
+            const Surface s = extract_surface(sc, o, d, T, h.inst, h.prim, half_round(h.u), half_round(h.v), hit ? h.t : -1.f);
+            uint32_t nee_seed = wang_hash(seed + gpixel);
+            ShadowRayOut sr;
+            if (nee_sample(sc, s, nee_seed, sr)) {
+                ++n_shadow;
+                HitInfo unused;
+                if (!bvh8_trace<true>(bvh_any, sr.o, sr.d, a.tmin, sr.tmax, unused)) {
+                    float4* dst = &fv.channels[(size_t)1 /* LB_CHANNEL_INDIRECT */ * np + pixel];
+                    float4 c = *dst; c.x += sr.radiance.x; c.y += sr.radiance.y; c.z += sr.radiance.z; *dst = c;
+                }
+            }
+            if (depth + 1u >= a.max_depth) break;
+            BounceOut b;
+            if (!bounce_sample(s, gpixel, wang_hash(seed), b)) break;
+            o = b.o; d = b.d; T = b.throughput;
+        }
+    }
+    n_extend = __reduce_add_sync(0xFFFFFFFFu, n_extend); n_shadow = __reduce_add_sync(0xFFFFFFFFu, n_shadow);
+    if ((threadIdx.x & 31u) == 0u) {
+        if (n_extend) atomicAdd(&fv.stats[STAT_EXTEND], (unsigned long long)n_extend);
+        if (n_shadow) atomicAdd(&fv.stats[STAT_SHADOW], (unsigned long long)n_shadow);
+    }
+}
+
 // ------------------------------------------------------------------ K12 merge + progressive accumulate + K13 8-bit output
 __device__ __forceinline__ unsigned char to_srgb8(float c) {
     c = clampf(c, 0.f, 1.f);
@@ -264,6 +311,10 @@ void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc
 void launch_shadow(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh, uint32_t ticket, float tmin) {
     k_shadow<<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(bvh, fv.shadow, &fv.counters[CNT_SHADOW], &fv.counters[CNT_TICKET0 + ticket],
         fv.channels, fv.npix, tmin, &fv.stats[STAT_SHADOW], cfg.trace_any); LB_LAUNCH_CHECK();
+}
+void launch_tail(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, const BvhView& bvh, const BvhView& bvh_any, int queue, uint32_t first_depth, uint32_t max_depth,
+                 uint32_t seed, float tmin, float tmax) {
+    k_tail<<<cfg.sms * 8, 128, 0, cfg.stream>>>(fv, sc, bvh, bvh_any, queue, TailArgs{first_depth, max_depth, seed, tmin, tmax}); LB_LAUNCH_CHECK();
 }
 void launch_merge(const LaunchCfg& cfg, const FrameView& fv, int blend, uint32_t blend_count) {
     k_merge<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, blend, blend_count); LB_LAUNCH_CHECK();

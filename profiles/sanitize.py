@@ -14,7 +14,7 @@ cases = [("cornell_nee", scenes.cornell_box(), dict(depth=3, restir=False)), ("c
          ("gallery", scenes.material_gallery(), dict(depth=4, restir=True)), ("fog_compat", scenes.fog_room(16), dict(depth=3, restir=True)),
          ("fog_delta", scenes.fog_room(16), dict(depth=3, restir=True, volume_mode=lr.api.VOLUME_DELTA))]
 for name, scene, kw in cases:
-    for overlap in (0, 5):
+    for overlap in (0, 5, 13):
         r = lr.Renderer(lr.Settings(width=W, height=H, **kw)); r.load_scene(scene); r.set_overlap(overlap)
         r.render_frames(2)
         hdr = r.read_hdr(); fc = r.frame_counters()
