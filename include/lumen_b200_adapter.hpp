@@ -292,11 +292,17 @@ class Renderer final : public LumenRenderer
 public:
     Renderer() = default;
     explicit Renderer(const Settings& a_Settings) { Init(a_Settings); }
+    // a member of a RendererGroup: the handle belongs to the group (lb_group_member), this object only speaks LumenRenderer for it
+    Renderer(LbRenderer a_Borrowed, glm::uvec2 a_OutputResolution) : m_Renderer(a_Borrowed), m_Owned(false), m_OutputResolution(a_OutputResolution)
+    {
+        CreateDefaultResources();
+        m_Scene = CreateScene(SceneData());
+    }
     ~Renderer() override
     {
         StopRendering();
         m_Scene.reset();
-        if (m_Renderer) lb_destroy(m_Renderer);
+        if (m_Renderer && m_Owned) lb_destroy(m_Renderer);
     }
 
     // WaveFrontRenderer::Init, WaveFrontRenderer.cpp:70-322 (also creates the default textures and the first scene, :318-321)
@@ -483,11 +489,63 @@ public:
 
 private:
     LbRenderer m_Renderer = nullptr;
+    bool m_Owned = true;
     glm::uvec2 m_OutputResolution = {0, 0};
     std::thread m_Thread;
     std::atomic<bool> m_Stop{false};
     std::mutex m_FrameMutex;
     uint64_t m_FrameId = 0;
+};
+
+// One process driving n GPUs (lb_group_*, csrc/lb_multigpu.cpp): n member renderers behind the LumenRenderer interface + one NCCL
+// communicator. The application loads the same assets into every Member(i) with the calls it already makes on a single renderer
+// (SceneManager::LoadGLTF etc.), then Render / Reduce / ReadHdr replace the single renderer's frame loop:
+//     B200::RendererGroup group({0, 1, 2, 3}, settings, LB_GROUP_SAMPLES);
+//     for (uint32_t i = 0; i < group.Size(); ++i) LoadScene(group.Member(i));
+//     group.Render(16); group.Reduce(); auto hdr = group.ReadHdr();          // 64 samples per pixel, one ncclReduce
+class RendererGroup
+{
+public:
+    RendererGroup(const std::vector<int>& a_Devices, const Settings& a_Settings, int a_Mode)
+    {
+        LbSettings s;
+        std::memset(&s, 0, sizeof s);
+        s.width = a_Settings.renderResolution.x; s.height = a_Settings.renderResolution.y; s.depth = a_Settings.depth;
+        s.restir = a_Settings.restir; s.restir_temporal = a_Settings.restirTemporal; s.restir_spatial = a_Settings.restirSpatial; s.volume_mode = a_Settings.volumeMode;
+        if (lb_group_create(a_Devices.data(), static_cast<uint32_t>(a_Devices.size()), &s, a_Mode, &m_Group) != LB_OK) throw std::runtime_error(lb_multigpu_last_error());
+        m_Width = s.width; m_Height = s.height;
+        for (uint32_t i = 0; i < a_Devices.size(); ++i)
+        {
+            LbRenderer member = nullptr;
+            if (lb_group_member(m_Group, i, &member) != LB_OK) throw std::runtime_error(lb_multigpu_last_error());
+            m_Members.emplace_back(new Renderer(member, a_Settings.outputResolution));
+        }
+    }
+    ~RendererGroup() { m_Members.clear(); if (m_Group) lb_group_destroy(m_Group); }
+    RendererGroup(const RendererGroup&) = delete;
+    RendererGroup& operator=(const RendererGroup&) = delete;
+
+    uint32_t Size() const { return static_cast<uint32_t>(m_Members.size()); }
+    Renderer& Member(uint32_t a_Index) { return *m_Members.at(a_Index); }
+    // the scene graph of every member is flushed to its renderer (MeshInstance / camera changes), then the frames are enqueued on all GPUs
+    void Render(uint32_t a_Frames)
+    {
+        for (auto& m : m_Members) if (m->m_Scene) static_cast<B200::Scene&>(*m->m_Scene).Synchronise();
+        if (lb_group_render(m_Group, a_Frames) != LB_OK) throw std::runtime_error(lb_multigpu_last_error());
+    }
+    void Reduce() { if (lb_group_reduce(m_Group) != LB_OK) throw std::runtime_error(lb_multigpu_last_error()); }
+    void Reset() { if (lb_group_reset(m_Group) != LB_OK) throw std::runtime_error(lb_multigpu_last_error()); }
+    std::vector<float> ReadHdr()
+    {
+        std::vector<float> pixels(static_cast<size_t>(m_Width) * m_Height * 4);
+        if (lb_group_read_hdr(m_Group, pixels.data(), pixels.size() * sizeof(float)) != LB_OK) throw std::runtime_error(lb_multigpu_last_error());
+        return pixels;
+    }
+
+private:
+    LbGroup m_Group = nullptr;
+    uint32_t m_Width = 0, m_Height = 0;
+    std::vector<std::unique_ptr<Renderer>> m_Members;
 };
 
 } // namespace B200
