@@ -249,7 +249,8 @@ def run_gpu(args):
     for _ in range(args.steps):
         r.render_frames(1)
     if world > 1:
-        r.comm_reduce_accum(0, args.steps * world)                              # the one collective of the path: ncclReduce on the renderer's stream + resolve on rank 0
+        r.comm_reduce_accum(0, args.steps * world)                              # the one collective of the path: ncclReduce inside the library + resolve on rank 0
+        r.reduce_wait()                                                         # it runs on a side stream: the timed stream waits for it
     e1.record(stream)
     barrier()
     t_wall1 = time.time()
@@ -262,7 +263,7 @@ def run_gpu(args):
         # the collective alone (59 MB of fp32 per rank at 1440p), timed on the stream after a barrier
         r.set_blend_mode(True); r.render_frames(1); barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream); r.comm_reduce_accum(0, world); c1.record(stream); barrier()
+        c0.record(stream); r.comm_reduce_accum(0, world); r.reduce_wait(); c1.record(stream); barrier()
         reduce_ms = c0.elapsed_time(c1)
         t = torch.tensor([ms, float(rays)], device="cuda", dtype=torch.float64)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -273,7 +274,8 @@ def run_gpu(args):
     # with the library's asynchronous read-back into two alternating pinned buffers (the copy of frame k overlaps frame k+1; every frame has
     # arrived in host memory before the clock stops). N GPUs: a step is one image of N samples — every rank uploads the camera and renders one
     # frame into a cleared accumulation buffer, the library reduces the N buffers onto rank 0 (NVLink), and ONLY rank 0 reads the image back
-    # (round 1 read every rank's own frame back: 8 x 59 MB per step into one host).
+    # (round 1 read every rank's own frame back: 8 x 59 MB per step into one host). The reduce runs on the library's side stream and the read-back on
+    # its copy stream: both overlap the next step's frame, and every image has arrived in host memory before the clock stops.
     hosts = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else []
     host = hosts[0] if rank == 0 else None
 
@@ -460,7 +462,7 @@ def run_extras(args, lr, torch, dist, rank, world, local, scene, stream, join_co
     def c5(_):
         r5.render_frames(frames)
         if world > 1:
-            r5.comm_reduce_accum(0, total_spp)
+            r5.comm_reduce_accum(0, total_spp); r5.reduce_wait()
         else:
             r5.resolve_accum(total_spp)
     ms5 = timed(c5, 1)

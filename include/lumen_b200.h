@@ -371,13 +371,23 @@ LB_API int lb_band_settings(const LbSettings* full, uint32_t rank, uint32_t rank
 /* Settings of sample-sharding rank `rank`: blend mode + the rank's frameCount stream. */
 LB_API int lb_shard_settings(const LbSettings* base, uint32_t rank, uint32_t ranks, LbSettings* out);
 
+/* Hooks the two layers below are built on (a host with its own collective library can use them the same way): lb_reduce_begin hands out a
+ * side stream that has waited for the frames rendered so far, the accumulation buffer to send and — for the root — a separate buffer to
+ * receive the sum in; lb_reduce_end(is_root, total_frames) resolves the image from that sum on the side stream (root) and arms a fence: the
+ * renderer's next frame waits for the collective only before its merge kernel, read-backs wait on their copy stream — so the exchange runs
+ * under the next frame. lb_reduce_wait makes the renderer's own stream wait for it (e.g. before timing with events on that stream). */
+LB_API int lb_reduce_begin(LbRenderer r, void** side_stream, void** send_device, void** recv_device_root, size_t* bytes);
+LB_API int lb_reduce_end(LbRenderer r, int is_root, uint32_t total_frames);
+LB_API int lb_reduce_wait(LbRenderer r);
+
 /* -- one rank per process (any launcher: the 128-byte id is created on one rank and handed to the others by the host application) */
 #define LB_COMM_ID_BYTES 128
 LB_API int lb_comm_unique_id(uint8_t* id128);
 LB_API int lb_comm_init(LbRenderer r, const uint8_t* id128, int rank, int ranks);
 /* samples: sum-reduce the accumulation buffers onto `root` (in place, on the renderer's stream); the root then resolves its HDR / LDR buffers as
- * sum / total_frames (total_frames = frames accumulated by ALL ranks). Asynchronous like lb_render_frames. In place: the root's accumulation
- * buffer then holds the sum of all ranks — lb_set_blend_mode(r, 1) clears it before the next image is accumulated. */
+ * sum / total_frames (total_frames = frames accumulated by ALL ranks). Asynchronous, and off the renderer's stream (lb_reduce_begin / _end): the
+ * next frames overlap the collective. Every rank's accumulation buffer is left untouched (the root receives into a separate buffer);
+ * lb_set_blend_mode(r, 1) starts the next image. */
 LB_API int lb_comm_reduce_accum(LbRenderer r, int root, uint32_t total_frames);
 /* bands: every rank sends the rows it owns of its merged frame to `root`; on the root `full_frame_device` receives the band_full_height x width
  * float4 image (device memory of the root's GPU; ignored on the other ranks). The renderer must have been created from lb_band_settings. */
@@ -394,8 +404,8 @@ LB_API int lb_group_size(LbGroup g, uint32_t* n);
 LB_API int lb_group_member(LbGroup g, uint32_t i, LbRenderer* out);
 /* samples: `frames` frames on every member (n * frames samples); bands: `frames` complete frames, each gathered on member 0. Asynchronous. */
 LB_API int lb_group_render(LbGroup g, uint32_t frames);
-/* samples: the one collective + resolve on member 0 (bands: no-op). Asynchronous; lb_group_read_hdr synchronises. The reduce is in place:
- * afterwards member 0's accumulation buffer holds the sum of all members, and lb_group_reset starts the next progressive image. */
+/* samples: the one collective + resolve on member 0 (bands: no-op). Asynchronous; lb_group_read_hdr synchronises. The accumulation buffers keep
+ * accumulating afterwards (more frames + another reduce refine the same image); lb_group_reset starts the next progressive image. */
 LB_API int lb_group_reduce(LbGroup g);
 LB_API int lb_group_reset(LbGroup g);
 /* The image on member 0: width x full height float4. */

@@ -235,6 +235,9 @@ _HOST_SIGS = {
     "volume_create_file": [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)],
     # multi-GPU inside the library (csrc/lb_multigpu.cpp): NCCL over NVLink, no oracle counterpart (the CPU tests use gloo for the same exchange)
     "get_stream": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "reduce_begin": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+    "reduce_end": [C.c_void_p, C.c_int, C.c_uint32],
+    "reduce_wait": [C.c_void_p],
     "band_settings": [C.POINTER(LbSettings), C.c_uint32, C.c_uint32, C.POINTER(LbSettings), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
     "shard_settings": [C.POINTER(LbSettings), C.c_uint32, C.c_uint32, C.POINTER(LbSettings)],
     "comm_unique_id": [C.c_void_p],
@@ -614,6 +617,10 @@ class Renderer:
     def comm_reduce_accum(self, root: int, total_frames: int):
         """Sample sharding: the one collective — sum-reduce of the fp32 accumulation buffers onto `root`, which resolves sum / total_frames."""
         self._mg(self.b.comm_reduce_accum(self._h, root, total_frames))
+
+    def reduce_wait(self):
+        """Makes the renderer's stream wait for the reduce started by comm_reduce_accum (which otherwise overlaps the following frames)."""
+        self.b.check(self.b.reduce_wait(self._h))
 
     def comm_gather_bands(self, root: int, full_frame_device_ptr: int = 0):
         """Row bands: every rank's owned rows to `root` (device to device); `full_frame_device_ptr` = H x W float4 on the root."""

@@ -55,6 +55,10 @@ struct Renderer {
     DevBuf<float> d_gbuffer;
     // asynchronous read-back (lb_read_hdr_async): a copy stream + two events; the next frame's merge waits for a pending copy
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered = nullptr, ev_copied = nullptr; bool copy_pending = false;
+    // asynchronous multi-GPU reduce (lb_reduce_begin / lb_reduce_end, used by csrc/lb_multigpu.cpp): the collective runs on a side stream behind
+    // the frames rendered so far and — on the root — lands in `d_reduced`, from which the image is resolved; the next frame only waits for it
+    // before its merge kernel (the one kernel that writes the accumulation buffer), so the reduce hides under the next frame
+    cudaStream_t reduce_stream = nullptr; cudaEvent_t ev_frames = nullptr, ev_reduced = nullptr; bool reduce_pending = false; DevBuf<float4> d_reduced;
     std::mutex mu;
 
     // ---- host-side scene (the reference keeps the same tables in PTScene / SceneDataTable)
@@ -155,6 +159,9 @@ struct Renderer {
         if (stream) cudaStreamSynchronize(stream);
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (reduce_stream) { cudaStreamSynchronize(reduce_stream); cudaStreamDestroy(reduce_stream); }
+        if (ev_frames) cudaEventDestroy(ev_frames);
+        if (ev_reduced) cudaEventDestroy(ev_reduced);
         if (ev_rendered) cudaEventDestroy(ev_rendered);
         if (ev_copied) cudaEventDestroy(ev_copied);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -545,6 +552,7 @@ struct Renderer {
         if (shadow_in_flight) { LB_CUDA(cudaStreamWaitEvent(stream, ev_shadow, 0)); shadow_in_flight = false; }
         if (forked) { LB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); lap("restir_join"); }    // the time the bounce chain waited for the ReSTIR chain
         if (copy_pending) LB_CUDA(cudaStreamWaitEvent(stream, ev_copied, 0));      // an asynchronous read-back still owns the combined buffer
+        if (reduce_pending) { LB_CUDA(cudaStreamWaitEvent(stream, ev_reduced, 0)); reduce_pending = false; }      // a reduce still reads the accumulation buffer
         launch_merge(c, fv, (int)st.blend_output, blend_count); ++launches;
         lap("merge");
         if (st.blend_output) ++blend_count; else blend_count = 1;
@@ -709,14 +717,18 @@ LB_API int lb_get_settings(LbRenderer r, LbSettings* out) { return guarded(R_, [
 LB_API int lb_get_render_resolution(LbRenderer r, uint32_t* w, uint32_t* h) { return guarded(R_, [&]() { *w = R_->st.width; *h = R_->st.height; return (int)LB_OK; }); }
 LB_API int lb_set_depth(LbRenderer r, uint32_t d) { return guarded(R_, [&]() { if (!d || d > 24) return fail(LB_ERR_INVALID_ARGUMENT, "depth"); R_->st.depth = d; return (int)LB_OK; }); }
 LB_API int lb_set_blend_mode(LbRenderer r, int b) {
-    return guarded(R_, [&]() { R_->st.blend_output = b != 0; R_->blend_count = 0; R_->d_accum.zero(R_->stream); return (int)LB_OK; });
+    // the first frame after this call overwrites the accumulation buffer (k_merge with blend_count == 0): no memset here, which would have to
+    // wait for a reduce that may still be reading the buffer (lb_reduce_begin)
+    return guarded(R_, [&]() { R_->st.blend_output = b != 0; R_->blend_count = 0; return (int)LB_OK; });
 }
 LB_API int lb_get_blend_mode(LbRenderer r, int* b) { return guarded(R_, [&]() { *b = (int)R_->st.blend_output; return (int)LB_OK; }); }
 LB_API int lb_reset_history(LbRenderer r) { return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->resize(); return (int)LB_OK; }); }
 LB_API int lb_render_frames(LbRenderer r, uint32_t frames) {
     return guarded(R_, [&]() { for (uint32_t i = 0; i < frames; ++i) R_->render_frame(); return (int)LB_OK; });
 }
-LB_API int lb_synchronize(LbRenderer r) { return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); return (int)LB_OK; }); }
+LB_API int lb_synchronize(LbRenderer r) {
+    return guarded(R_, [&]() { LB_CUDA(cudaStreamSynchronize(R_->stream)); if (R_->reduce_stream) LB_CUDA(cudaStreamSynchronize(R_->reduce_stream)); return (int)LB_OK; });
+}
 LB_API int lb_start_rendering(LbRenderer r) {
     if (!r) return fail(LB_ERR_INVALID_ARGUMENT, "null renderer");
     lb::Renderer* R = R_;
@@ -744,6 +756,7 @@ LB_API int lb_stop_rendering(LbRenderer r) {
 
 static int read_back(lb::Renderer* R, const void* src, size_t bytes, void* dst, size_t cap) {
     if (!dst || cap < bytes) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small");
+    if (R->reduce_pending) LB_CUDA(cudaStreamWaitEvent(R->stream, R->ev_reduced, 0));          // the image may be the one a reduce is resolving
     LB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, R->stream));
     LB_CUDA(cudaStreamSynchronize(R->stream));
     return LB_OK;
@@ -755,6 +768,7 @@ LB_API int lb_read_hdr_async(LbRenderer r, float* out, size_t cap) {
         if (!out || cap < bytes) return fail(LB_ERR_INVALID_ARGUMENT, "buffer too small");
         LB_CUDA(cudaEventRecord(R_->ev_rendered, R_->stream));
         LB_CUDA(cudaStreamWaitEvent(R_->copy_stream, R_->ev_rendered, 0));
+        if (R_->reduce_pending) LB_CUDA(cudaStreamWaitEvent(R_->copy_stream, R_->ev_reduced, 0));      // the copy engine, not the render stream, waits for the resolve
         LB_CUDA(cudaMemcpyAsync(out, R_->d_combined.p, bytes, cudaMemcpyDeviceToHost, R_->copy_stream));
         LB_CUDA(cudaEventRecord(R_->ev_copied, R_->copy_stream));
         R_->copy_pending = true;
@@ -854,6 +868,38 @@ LB_API int lb_accum_buffer(LbRenderer r, void** p, size_t* bytes, uint32_t* fram
 }
 LB_API int lb_resolve_accum(LbRenderer r, uint32_t total) {
     return guarded(R_, [&]() { if (!total) return fail(LB_ERR_INVALID_ARGUMENT, "frames"); FrameView fv = R_->frame_view(); if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_copied, 0)); launch_resolve(R_->cfg(), fv, 1.0f / (float)total); return (int)LB_OK; });
+}
+// ---- hooks of the multi-GPU layer (csrc/lb_multigpu.cpp): a collective over the accumulation buffers that overlaps the next frame
+LB_API int lb_reduce_begin(LbRenderer r, void** side_stream, void** send, void** recv_root, size_t* bytes) {
+    return guarded(R_, [&]() {
+        if (!side_stream || !send || !recv_root || !bytes) return fail(LB_ERR_INVALID_ARGUMENT, "null");
+        if (!R_->reduce_stream) {
+            LB_CUDA(cudaStreamCreateWithFlags(&R_->reduce_stream, cudaStreamNonBlocking));
+            LB_CUDA(cudaEventCreateWithFlags(&R_->ev_frames, cudaEventDisableTiming)); LB_CUDA(cudaEventCreateWithFlags(&R_->ev_reduced, cudaEventDisableTiming));
+        }
+        R_->d_reduced.reserve(R_->npix());
+        LB_CUDA(cudaEventRecord(R_->ev_frames, R_->stream)); LB_CUDA(cudaStreamWaitEvent(R_->reduce_stream, R_->ev_frames, 0));
+        if (R_->copy_pending) LB_CUDA(cudaStreamWaitEvent(R_->reduce_stream, R_->ev_copied, 0));      // the resolve will overwrite the image a read-back may still be copying
+        *side_stream = (void*)R_->reduce_stream; *send = R_->d_accum.p; *recv_root = R_->d_reduced.p; *bytes = (size_t)R_->npix() * 16;
+        return (int)LB_OK;
+    });
+}
+LB_API int lb_reduce_end(LbRenderer r, int is_root, uint32_t total_frames) {
+    return guarded(R_, [&]() {
+        if (!R_->reduce_stream) return fail(LB_ERR_STATE, "lb_reduce_begin first");
+        if (is_root) {
+            if (!total_frames) return fail(LB_ERR_INVALID_ARGUMENT, "frames");
+            FrameView fv = R_->frame_view(); fv.accum = R_->d_reduced.p;
+            LaunchCfg c = R_->cfg(); c.stream = R_->reduce_stream;
+            launch_resolve(c, fv, 1.0f / (float)total_frames);
+        }
+        LB_CUDA(cudaEventRecord(R_->ev_reduced, R_->reduce_stream));
+        R_->reduce_pending = true;
+        return (int)LB_OK;
+    });
+}
+LB_API int lb_reduce_wait(LbRenderer r) {
+    return guarded(R_, [&]() { if (R_->reduce_pending) { LB_CUDA(cudaStreamWaitEvent(R_->stream, R_->ev_reduced, 0)); R_->reduce_pending = false; } return (int)LB_OK; });
 }
 LB_API int lb_set_overlap(LbRenderer r, int enabled) {
     return guarded(R_, [&]() { if (enabled < 0 || enabled > 15) return fail(LB_ERR_INVALID_ARGUMENT, "overlap mode"); LB_CUDA(cudaStreamSynchronize(R_->stream)); R_->overlap = enabled; return (int)LB_OK; });

@@ -166,11 +166,12 @@ LB_API int lb_comm_reduce_accum(LbRenderer r, int root, uint32_t total_frames) {
     if (it == comms().end()) return mfail(LB_ERR_INVALID_HANDLE, "no communicator on this renderer (lb_comm_init)");
     const Comm& c = it->second;
     if (root < 0 || root >= c.ranks || !total_frames) return mfail(LB_ERR_INVALID_ARGUMENT, "root / total_frames");
-    void* acc = nullptr; size_t bytes = 0; uint32_t frames = 0; void* stream = nullptr; LbSettings st;
-    MG_LB(lb_accum_buffer(r, &acc, &bytes, &frames)); MG_LB(lb_get_stream(r, &stream)); MG_LB(lb_get_settings(r, &st));
-    MG_CUDA(cudaSetDevice(st.device));
-    MG_NCCL(nccl().Reduce(acc, acc, bytes / 4, ncclFloat, ncclSum, root, c.comm, (cudaStream_t)stream));      // the one collective of the path, in place
-    if (c.rank == root) MG_LB(lb_resolve_accum(r, total_frames));
+    void* side = nullptr; void* send = nullptr; void* recv = nullptr; size_t bytes = 0; LbSettings st;
+    MG_LB(lb_get_settings(r, &st)); MG_CUDA(cudaSetDevice(st.device));
+    MG_LB(lb_reduce_begin(r, &side, &send, &recv, &bytes));
+    // the one collective of the path, on the renderer's side stream: the frames that follow overlap it
+    MG_NCCL(nccl().Reduce(send, c.rank == root ? recv : send, bytes / 4, ncclFloat, ncclSum, root, c.comm, (cudaStream_t)side));
+    MG_LB(lb_reduce_end(r, c.rank == root ? 1 : 0, total_frames));
     return LB_OK;
 }
 LB_API int lb_comm_gather_bands(LbRenderer r, int root, void* full_frame_device) {
@@ -226,7 +227,6 @@ LB_API int lb_group_member(LbGroup g, uint32_t i, LbRenderer* out) {
 LB_API int lb_group_render(LbGroup g, uint32_t frames) {
     if (!g) return mfail(LB_ERR_INVALID_ARGUMENT, "null group");
     std::lock_guard<std::mutex> lock(g_mu);
-    if (g->mode == LB_GROUP_SAMPLES && g->reduced) return mfail(LB_ERR_STATE, "member 0 holds the reduced sum: lb_group_reset starts the next image");
     // launches are asynchronous: one host thread keeps every GPU's stream fed, frame by frame (a frame is ~25 launches, the GPUs need
     // milliseconds for it)
     for (uint32_t f = 0; f < frames; ++f) {
@@ -261,17 +261,17 @@ LB_API int lb_group_reduce(LbGroup g) {
     if (g->mode != LB_GROUP_SAMPLES) return LB_OK;
     std::lock_guard<std::mutex> lock(g_mu);
     if (!g->frames_per_member) return mfail(LB_ERR_STATE, "nothing rendered yet");
-    if (g->reduced) return mfail(LB_ERR_STATE, "the accumulation buffers were already reduced (member 0 holds the sum)");
+    struct Leg { void* side; void* send; void* recv; size_t bytes; };
+    std::vector<Leg> legs(g->members.size());
+    for (size_t i = 0; i < g->members.size(); ++i) MG_LB(lb_reduce_begin(g->members[i].r, &legs[i].side, &legs[i].send, &legs[i].recv, &legs[i].bytes));
     MG_NCCL(nccl().GroupStart());
-    for (Member& m : g->members) {
-        void* acc = nullptr; size_t bytes = 0; uint32_t frames = 0;
-        MG_LB(lb_accum_buffer(m.r, &acc, &bytes, &frames));
+    for (size_t i = 0; i < g->members.size(); ++i) {
+        Member& m = g->members[i];
         MG_CUDA(cudaSetDevice(m.device));
-        MG_NCCL(nccl().Reduce(acc, acc, bytes / 4, ncclFloat, ncclSum, 0, m.comm, m.stream));
+        MG_NCCL(nccl().Reduce(legs[i].send, i == 0 ? legs[i].recv : legs[i].send, legs[i].bytes / 4, ncclFloat, ncclSum, 0, m.comm, (cudaStream_t)legs[i].side));
     }
     MG_NCCL(nccl().GroupEnd());
-    MG_LB(lb_resolve_accum(g->members[0].r, g->frames_per_member * (uint32_t)g->members.size()));
-    g->reduced = true;
+    for (size_t i = 0; i < g->members.size(); ++i) MG_LB(lb_reduce_end(g->members[i].r, i == 0 ? 1 : 0, g->frames_per_member * (uint32_t)g->members.size()));
     return LB_OK;
 }
 LB_API int lb_group_synchronize(LbGroup g) {

@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(kBlock) k_merge(FrameView fv, int blend, uint3
         m = make_float4(m.x * (1.0f - al) + vo.x * al, m.y * (1.0f - al) + vo.y * al, m.z * (1.0f - al) + vo.z * al, m.w * (1.0f - al) + vo.w * al);
         float4 c;
         if (blend) {
-            float4 acc = fv.accum[i]; acc = acc + m; fv.accum[i] = acc;
+            float4 acc = blend_count ? fv.accum[i] + m : m;          // the first blended frame starts the sum (no cleared buffer needed)
+            fv.accum[i] = acc;
             const float inv = xdiv(1.0f, (float)(blend_count + 1u));
             c = acc * inv;
         } else { c = m; fv.accum[i] = m; }

@@ -94,14 +94,17 @@ def test_group_samples_on_two_gpus_equal_one_renderer_on_the_union_of_streams(gp
     with lr.Group([0, 1], st, "samples") as g:
         g.load_scene(scene); g.render(3); g.reduce()
         img = g.read_hdr()
-        with pytest.raises(lr.LumenError):
-            g.render(1)                                        # member 0 holds the sum: reset first
-        g.reset(); g.render(1); g.reduce()
+        g.render(1); g.reduce()                                # the members keep accumulating: a second reduce refines the same image (8 samples)
+        img8 = g.read_hdr()
+        g.reset(); g.render(1); g.reduce()                     # a new progressive image: the next two samples of the streams
         assert np.isfinite(g.read_hdr()).all()
     with api.Renderer(gpu, api.Settings(**{**st.__dict__, "blend_output": True})) as r:      # frameCount 1, 3, ..., 11: both streams interleaved
         r.load_scene(scene); r.render_frames(6)
         want = r.read_hdr()
+        r.render_frames(2)
+        want8 = r.read_hdr()
     assert np.allclose(img, want, rtol=1e-5, atol=1e-7) and np.abs(want).sum() > 0
+    assert np.allclose(img8, want8, rtol=1e-5, atol=1e-7) and not np.array_equal(img8, img)
 
 
 @pytest.mark.gpu
