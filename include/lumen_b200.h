@@ -345,8 +345,8 @@ LB_API int lb_resolve_accum(LbRenderer r, uint32_t total_frames);
  *   bit 1 (default OFF — measured slower on B200) the ReSTIR passes run on the side stream beside ALL bounce waves;
  *   bit 2 (default ON)  the ReSTIR passes are launched after the first bounce wave; the later, latency-bound waves (1e5 .. 1e4 rays) run
  *                       on the side stream beside them (takes precedence over bit 0 where it applies: ReSTIR on, depth >= 3, no media).
- *   bit 3 (default ON)  from the third wave on (1e5 .. 1e4 rays on C2) the rest of the bounce chain — extend, shade, shadow of every remaining wave —
- *                       is ONE launch in which a lane follows a path to its end (no media).
+ *   bit 3 (default OFF — measured 0.07 ms slower on C2) from the third wave on (1e5 .. 1e4 rays on C2) the rest of the bounce chain — extend,
+ *                       shade, shadow of every remaining wave — is ONE launch in which a lane follows a path to its end (no media).
  * Results are identical in every mode; with mode 0 every stage time of lb_frame_stats is an exclusive device time (what bench.py uses for
  * its per-kernel roofline table). */
 LB_API int lb_set_overlap(LbRenderer r, int mode);

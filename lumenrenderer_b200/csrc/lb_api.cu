@@ -95,9 +95,11 @@ struct Renderer {
     // direction-binned queue of the ReSTIR visibility rays (lb_restir.cu k_vis_bin), LB_VIS_SORT=1. Off by default: measured on C2 the binned
     // trace is 5.5 % faster (1.586 -> 1.499 ms for both passes) but the binning pre-pass costs 0.230 ms (profiles/r02_a_ab.md)
     // TMA descriptors of surface plane 1 (normal + signed depth) of both surface buffers: the spatial-reuse pass stages a 92 x 76 box of it per
-    // 32 x 16-pixel tile in shared memory (lb_restir.cu k_spatial_tma). LB_SPATIAL_TMA=0: gather from global memory instead.
+    // 32 x 16-pixel tile in shared memory (lb_restir.cu k_spatial_tma), LB_SPATIAL_TMA=1. Off by default: measured on C2 the staged pass takes
+    // 1.22 ms against 0.53 ms per pass — the probes are 15 % of the pass's gathers, and the 224 KB of tiles leave the reservoir / surface
+    // gathers 1/8 of the L1 (profiles/r02_k_spatial_tma.md)
     CUtensorMap tmap_geom[2]; bool have_tmap = false;
-    bool spatial_tma = []() { const char* e = getenv("LB_SPATIAL_TMA"); return !e || atoi(e) != 0; }();
+    bool spatial_tma = []() { const char* e = getenv("LB_SPATIAL_TMA"); return e && atoi(e) != 0; }();
     void make_tensor_maps() {
         have_tmap = false;
         if (!spatial_tma) return;
@@ -108,12 +110,15 @@ struct Renderer {
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
             return (EncodeFn)p;
         }();
-        if (!encode) return;
-        const cuuint64_t dims[3] = {4, st.width, st.height}, strides[2] = {16, (cuuint64_t)st.width * 16};
-        const cuuint32_t box[3] = {4, 32 + 2 * 30, 16 + 2 * 30}, estr[3] = {1, 1, 1};
+        if (!encode) throw CudaError("LB_SPATIAL_TMA=1: the driver does not export cuTensorMapEncodeTiled");
+        // the plane as a 2-D tensor of 8-byte elements (two per 16-byte record): a box row is then ONE contiguous run (92 records = 184 elements
+        // = 1 472 bytes; the innermost box extent is limited to 256 ELEMENTS, and 16-byte elements do not exist)
+        const cuuint64_t dims[2] = {(cuuint64_t)st.width * 2, st.height}, strides[1] = {(cuuint64_t)st.width * 16};
+        const cuuint32_t box[2] = {(32 + 2 * 30) * 2, 16 + 2 * 30}, estr[2] = {1, 1};
         for (int k = 0; k < 2; ++k)
-            if (encode(&tmap_geom[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d_surf[k].p + npix(), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+            if (encode(&tmap_geom[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_surf[k].p + npix(), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                throw CudaError("LB_SPATIAL_TMA=1: cuTensorMapEncodeTiled rejected the descriptor of surface plane 1");
         have_tmap = true;
     }
     DevBuf<float4> d_vis_rays[2];
@@ -144,7 +149,7 @@ struct Renderer {
     uint32_t npix() const { return st.width * st.height; }
     uint32_t full_height() const { return st.band_full_height ? st.band_full_height : st.height; }
     // LB_TRACE_REFILL_MIN / LB_TRACE_TRI_QUARTER: warp-scheduling knobs of trace_queue (profiling experiments; defaults in TraceTuning)
-    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 15) : 13; }      // whole-chain overlap (bit 1) off: measured slower
+    static int overlap_default() { const char* e = getenv("LB_OVERLAP"); return e ? (atoi(e) & 15) : 5; }       // whole-chain overlap (bit 1) and the fused tail (bit 3) off: measured slower
     static TraceTuning trace_tuning(bool any) {
         TraceTuning t;
         if (const char* e = getenv(any ? "LB_TRACE_ANY_REFILL_MIN" : "LB_TRACE_REFILL_MIN")) t.refill_min = atoi(e);

@@ -592,15 +592,19 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView 
 }
 
 // ---- the same pass with the neighbourhood's similarity records staged in shared memory by the TMA unit (north_star item 3).
-// A block owns a 32x16-pixel tile; every neighbour a pixel of the tile can draw lies within +-30 pixels, so ONE tensor copy
-// (cp.async.bulk.tensor.3d, box 4 floats x 92 x 76 = 111 872 bytes of surface plane 1, zero-filled outside the image) brings in everything
-// the five similarity probes of all 512 pixels can touch; the probes — the first dependent step of every pixel — are then shared-memory
-// reads (29 cycles) instead of L2 / DRAM gathers. Two blocks per SM: while one waits for its tile the other evaluates. The reservoirs of the
-// ACCEPTED neighbours (4 planes) and the surface of the first one (8 planes) do not fit beside the tile and stay global gathers.
+// A block owns a 32x16-pixel tile at a time; every neighbour a pixel of the tile can draw lies within +-30 pixels, so ONE tensor copy
+// (cp.async.bulk.tensor.2d over surface plane 1 seen as rows of 8-byte elements: a box of 184 x 76 = 92 x 76 records = 111 872 bytes, each box
+// row one contiguous 1 472-byte run, zero-filled outside the image) brings in everything the five similarity probes of all 512 pixels can
+// touch; the probes — the first dependent step of every pixel — are then shared-memory reads (29 cycles) instead of L2 / DRAM gathers.
+// One block of 16 warps per SM with TWO tile buffers: while the warps work on one tile (a row each), the TMA unit fills the other with the
+// next tile the block drew from the ticket. The reservoirs of the ACCEPTED neighbours (4 planes) and the surface of the first one (8 planes)
+// do not fit beside the tiles and stay global gathers. (The first version — a 3-D box with a 16-byte innermost extent, one buffer, two
+// blocks per SM — moved the box as 6 992 16-byte requests and exposed every load: 2.36 ms against 1.05 ms, profiles/r02_j_spatial_tma.md.)
 constexpr int kSpTileW = 32, kSpTileH = 16, kSpHalo = (int)kSpatialRadius, kSpBoxW = kSpTileW + 2 * kSpHalo, kSpBoxH = kSpTileH + 2 * kSpHalo;
+constexpr int kSpBlock = 512;
 constexpr uint32_t kSpTileBytes = (uint32_t)(kSpBoxW * kSpBoxH * sizeof(float4));
-static_assert(2u * (kSpTileBytes + 2048u) <= 228u * 1024u, "two blocks of the TMA-staged spatial pass per SM");
-static_assert(kBlock / 32 * 2 == kSpTileH, "8 warps x 2 rows = the 16 rows of a tile");
+static_assert(2u * kSpTileBytes + 1024u <= 227u * 1024u, "two tile buffers of the TMA-staged spatial pass in one block");
+static_assert(kSpBlock / 32 == kSpTileH, "16 warps = the 16 rows of a tile");
 extern __shared__ __align__(128) unsigned char sp_smem[];
 
 LB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -609,38 +613,43 @@ LB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier
 LB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-LB_D void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+LB_D void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_spatial_tma(FrameView fv, const __grid_constant__ CUtensorMap tmap, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
-    float4* tile = reinterpret_cast<float4*>(sp_smem);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_tile;
+__global__ void __launch_bounds__(kSpBlock, 1) k_spatial_tma(FrameView fv, const __grid_constant__ CUtensorMap tmap, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+    float4* const tiles[2] = {reinterpret_cast<float4*>(sp_smem), reinterpret_cast<float4*>(sp_smem + kSpTileBytes)};
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t s_tile[2];
     const uint32_t tiles_x = (fv.width + kSpTileW - 1u) / kSpTileW, tiles_y = (fv.height + kSpTileH - 1u) / kSpTileH, ntiles = tiles_x * tiles_y;
     constexpr uint32_t kStrip = 16u;                               // tiles are walked in vertical strips 16 tiles (512 px) wide, like TileWalk: the
     const uint32_t full = kStrip * tiles_y;                        // gathers of neighbouring blocks then share L2 lines
-    if (threadIdx.x == 0) { mbar_init(&bar, 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
-    uint32_t parity = 0u;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();                                           // the ticket is visible — and nobody reads the previous tile any more
-        const uint32_t t = s_tile;
-        __syncthreads();
-        if (t >= ntiles) break;
+    auto origin = [&](uint32_t t, int& x0, int& y0) {
         const uint32_t strip = t / full, r = t - strip * full, sw = min(kStrip, tiles_x - strip * kStrip);
         const uint32_t ty = r / sw, tx = strip * kStrip + (r - ty * sw);
-        const int x0 = (int)(tx * kSpTileW), y0 = (int)(ty * kSpTileH), bx = x0 - kSpHalo, by = y0 - kSpHalo;
-        if (threadIdx.x == 0) { mbar_expect_tx(&bar, kSpTileBytes); tma_load_3d(tile, &tmap, &bar, 0, bx, by); }
-        mbar_wait(&bar, parity); parity ^= 1u;
+        x0 = (int)(tx * kSpTileW); y0 = (int)(ty * kSpTileH);
+    };
+    // thread 0 draws the next tile and starts its copy into buffer b (the buffer's previous tile is no longer read: callers synchronise first)
+    auto fetch = [&](int b) {
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_tile[b] = t;
+        if (t < ntiles) { int x0, y0; origin(t, x0, y0); mbar_expect_tx(&bar[b], kSpTileBytes); tma_load_2d(tiles[b], &tmap, &bar[b], (x0 - kSpHalo) * 2, y0 - kSpHalo); }
+    };
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1u); mbar_init(&bar[1], 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); fetch(0); }
+    __syncthreads();
+    uint32_t parity[2] = {0u, 0u};
+    for (int b = 0;; b ^= 1) {
+        const uint32_t t = s_tile[b];
+        if (t >= ntiles) break;
+        if (threadIdx.x == 0) fetch(b ^ 1);                        // the other buffer was released by the barrier that ended the previous iteration
+        int x0, y0; origin(t, x0, y0);
+        mbar_wait(&bar[b], parity[b]); parity[b] ^= 1u;
+        const float4* tile = tiles[b]; const int bx = x0 - kSpHalo, by = y0 - kSpHalo;
         auto geom_at = [tile, bx, by](int nx, int ny, uint32_t) { return tile[(ny - by) * kSpBoxW + (nx - bx)]; };
-#pragma unroll 1
-        for (int row = 0; row < 2; ++row) {
-            const int x = x0 + (int)(threadIdx.x & 31u), y = y0 + (int)(threadIdx.x >> 5) * 2 + row;
-            if ((uint32_t)x < fv.width && (uint32_t)y < fv.height) spatial_pixel<false>(fv, in, out, seed, x, y, geom_at);
-        }
+        const int x = x0 + (int)(threadIdx.x & 31u), y = y0 + (int)(threadIdx.x >> 5);
+        if ((uint32_t)x < fv.width && (uint32_t)y < fv.height) spatial_pixel<false>(fv, in, out, seed, x, y, geom_at);
+        __syncthreads();                                           // everybody is done with buffer b, and s_tile[b ^ 1] is visible
     }
 }
 
@@ -695,8 +704,8 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
             if (a.unbiased) k_spatial<true><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
             else if (rb.tmap_geom) {
-                LB_CUDA(cudaFuncSetAttribute(k_spatial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpTileBytes));
-                k_spatial_tma<<<cfg.sms * 2, kBlock, kSpTileBytes, st>>>(fv, *static_cast<const CUtensorMap*>(rb.tmap_geom), &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+                LB_CUDA(cudaFuncSetAttribute(k_spatial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kSpTileBytes)));
+                k_spatial_tma<<<cfg.sms, kSpBlock, 2 * kSpTileBytes, st>>>(fv, *static_cast<const CUtensorMap*>(rb.tmap_geom), &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
             } else k_spatial<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
             LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }

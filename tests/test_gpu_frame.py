@@ -171,7 +171,7 @@ def test_overlap_mode_is_bit_identical_to_the_serialised_frame():
     bounce waves run as one path-per-lane launch."""
     scene = scenes.material_gallery()
     outs = []
-    for overlap in (13, 9, 8, 5, 4, 3, 1, 0):          # bit 3: the waves from the third on as one launch, a lane per path (k_tail)
+    for overlap in (13, 5, 9, 8, 4, 3, 1, 0):          # 5 is the default; bit 3: the waves from the third on as one launch, a lane per path (k_tail)
         g = lr.Renderer(lr.Settings(width=256, height=160, depth=4, restir=True))
         g.load_scene(scene); g.set_overlap(overlap)
         g.render_frames(3)
@@ -187,6 +187,24 @@ def test_overlap_mode_is_bit_identical_to_the_serialised_frame():
         for k in ("extend_rays", "shadow_rays", "visibility_rays"):
             assert a[3][k] == b[3][k]
     assert outs[0][3]["kernel_launches"] < b[3]["kernel_launches"]          # the fused tail replaces the per-wave launches of waves 2 and 3
+
+
+@pytest.mark.parametrize("width,height", [(333, 141), (33, 9)])
+def test_tma_staged_spatial_pass_is_bit_identical(monkeypatch, width, height):
+    """LB_SPATIAL_TMA=1: the spatial-reuse pass with the similarity records of a tile's neighbourhood staged in shared memory by the TMA unit
+    (k_spatial_tma; off by default, it measured slower) returns the reservoirs and the image of the gathering kernel bit for bit — on a size
+    that is no multiple of the 32 x 16 tile and on one smaller than the 92 x 76 box, so the zero-filled border of the box is exercised too."""
+    scene = scenes.material_gallery()
+    outs = []
+    for tma in ("0", "1"):
+        monkeypatch.setenv("LB_SPATIAL_TMA", tma)
+        g = lr.Renderer(lr.Settings(width=width, height=height, depth=3, restir=True))
+        g.load_scene(scene)
+        g.render_frames(3)
+        outs.append((g.read_hdr(), g.read_reservoirs()))
+        g.close()
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
+    assert np.isfinite(outs[1][0]).all() and outs[1][0].max() > 0
 
 
 def test_async_readback_equals_blocking_readback():
