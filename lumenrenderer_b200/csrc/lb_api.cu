@@ -817,6 +817,9 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
     });
 }
 static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uint32_t* count) {     // caller holds R->mu
+#ifdef LB_RIS_STATS
+    cudaStreamSynchronize(R->stream); lb::dump_ris_stats();
+#endif
     unsigned long long s[kNumStats]; uint32_t overflows = 0;
     LB_CUDA(cudaMemcpyAsync(s, R->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R->stream));
     LB_CUDA(cudaMemcpyAsync(&overflows, R->d_counters.p + CNT_STACK_OVERFLOW, sizeof overflows, cudaMemcpyDeviceToHost, R->stream));

@@ -107,4 +107,7 @@ struct LightBuild {
 };
 void build_lights(const LaunchCfg&, const SceneView&, const ScenePrepIn&, const uint8_t* prim_flags, LightBuild& out);
 
+#ifdef LB_RIS_STATS
+void dump_ris_stats();      // debug build: prints and clears the survivor statistics of k_ris
+#endif
 } // namespace lb

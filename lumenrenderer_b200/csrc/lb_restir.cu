@@ -149,9 +149,20 @@ struct BagSmem {
     float2* pa;     // bag pdf, area
 };
 constexpr int kRisBlock = 512;                                  // ONE block per SM: 16 warps share one staged bag
+constexpr int kRisRows = 2;                                     // 32-pixel rows per warp and iteration
+constexpr int kRisSlots = kRisBlock * kRisRows;                 // pixels a block holds between phase A and phase B
+#ifndef LB_RIS_GROUP_WARPS
+#define LB_RIS_GROUP_WARPS 4
+#endif
+constexpr int kRisGroupWarps = LB_RIS_GROUP_WARPS;              // warps that sort their pixels together (a named barrier each: the groups of a block drift apart,
+constexpr int kRisGroups = kRisBlock / 32 / kRisGroupWarps;     // so that one is in the shared-memory-bound phase A while another is in the MUFU-bound phase B)
+constexpr int kRisGroupThreads = kRisGroupWarps * 32, kRisGroupSlots = kRisGroupThreads * kRisRows, kRisGroupRows = kRisGroupWarps * kRisRows;
+static_assert(kRisGroups * kRisGroupWarps * 32 == kRisBlock && (kRisGroups <= 15 || kRisGroupWarps == 1), "groups tile the block; one hardware barrier each");
 constexpr size_t kRisBagBytes = (size_t)kLightsPerBag * (5 * sizeof(float4) + sizeof(float2));
-constexpr size_t kRisSmemBytes = kRisBagBytes + (size_t)kPrimarySamples * kRisBlock * sizeof(uint32_t);
-static_assert(kRisSmemBytes <= 227u * 1024u, "bag + candidate states must fit the 227 KB a block can have");
+constexpr size_t kRisStateBytes = (size_t)kPrimarySamples * kRisSlots * sizeof(uint32_t);
+// bag | candidate states [32][slots] | survivor mask [slots] | pixel [slots] | slots in ascending order of survivors (u16)
+constexpr size_t kRisSmemBytes = kRisBagBytes + kRisStateBytes + (size_t)kRisSlots * (2 * sizeof(uint32_t) + sizeof(uint16_t));
+static_assert(kRisSmemBytes + 1024u <= 227u * 1024u, "bag + candidate states + sort arrays must fit the 227 KB a block can have");
 
 struct BagCandidate { LightSample ls; float bag_pdf; };
 // geometry of the next candidate of stream `s` (position on the light, normal, area, bag pdf) + its bag slot and radiance
@@ -181,6 +192,9 @@ LB_D bool candidate_may_pass(const BagSmem& b, uint32_t slot, const float3& ppos
 }
 
 extern __shared__ __align__(16) unsigned char ris_smem[];
+#ifdef LB_RIS_STATS
+__device__ unsigned long long g_ris_stats[8];
+#endif
 
 // canonical bag of a 256-pixel group (hazard 1): WangHash(seed + full-frame group index) -> one of the 50 bags
 LB_D uint32_t bag_of_group(uint32_t seed, uint32_t group_base_pixel) {
@@ -214,8 +228,13 @@ __global__ void __launch_bounds__(1024) k_ris_order(uint32_t seed, uint32_t npix
 // / subsurface (lean evaluation), 1 = every pixel has isotropic roughness (the general evaluation without the anisotropic microfacet terms, which
 // the compiler otherwise executes predicated-off), 0 = anything.
 template <int MODE>
-LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisBlock], const BsdfCtx& ctx, const Surface& px, uint32_t mask, uint32_t s0, Reservoir& fresh) {
+LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisSlots], uint32_t slot, const BsdfCtx& ctx, const Surface& px, uint32_t mask, uint32_t s0, Reservoir& fresh) {
     uint32_t sb = s0;
+#ifdef LB_RIS_STATS
+    if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[5], 1ull);
+    atomicAdd(&g_ris_stats[0], (unsigned long long)__popc(mask));
+    { uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)__popc(mask)); if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[1], (unsigned long long)mx); }
+#endif
     while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
         const bool active = mask != 0u;
         BagCandidate c; ResampleGeom g; bool have_g = false;
@@ -223,35 +242,50 @@ LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisBlock], 
         g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
         if (active) {
             const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
-            sb = s_state[k][threadIdx.x];
+            sb = s_state[k][slot];
             draw_candidate_geom(bag, sb, c);
             have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
         }
         __syncwarp();
+#ifdef LB_RIS_STATS
+        if (have_g) atomicAdd(&g_ris_stats[2], 1ull);
+        if (__any_sync(0xFFFFFFFFu, have_g) && (threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[3], 1ull);
+        if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[4], 1ull);
+#endif
         if (have_g) resample_shade<MODE>(ctx, g, c.ls);
         if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
         __syncwarp();
     }
 }
 
-// Work item = one 32-pixel row of a 256-pixel group, taken by WARPS from the work ticket of ONE bag: a block stages a bag (1000 entries
-// with the full light record, 72 KB of shared memory) and its 8 warps then work through that bag's rows without ever waiting for one
-// another. Blocks start on bag (blockIdx mod 50) — about six blocks per bag at 2 blocks per SM — and, when their bag is exhausted, move
-// on to the next bag that still has rows (work stealing; costs one more staging). The first version handed whole 256-pixel groups to
-// blocks in image order and re-staged the bag for every group (14 400 times per frame at 1440p): barrier stalls 0.46 and
-// long-scoreboard 0.64 warps per issue (profiles/r01_u_kernels.md).
+// Work item = one 32-pixel row of a 256-pixel group, handed out by the work ticket of ONE bag: a block stages a bag (1000 entries with the
+// full light record, 88 KB of shared memory) and works through that bag's rows 32 at a time — two per warp. Blocks start on bag
+// (blockIdx mod 50) and, when their bag is exhausted, move on to the next bag that still has rows (work stealing; costs one more staging).
+//
+// Phase B costs one BSDF evaluation per lane and round, and a warp runs max-over-lanes(survivors) rounds. The survivor count of a pixel is
+// close to Binomial(32, 1/2): measured on C2 15.8 survivors per pixel but 21.95 rounds per row — 28 % of the lanes of phase B idle
+// (profiles/r02_n_ris_sorted.md). So the block does phase A for all its 1024 pixels first, counting-sorts them by survivor count in
+// shared memory (33 bins), and hands phase B warps of 32 pixels with (nearly) EQUAL counts: warp w takes group w of the ascending order
+// and then group 31 - w, so that every warp has about the same number of rounds in total and the barrier of the next iteration does not
+// wait for the warp that drew the long groups. A pixel's result depends on its own candidates only, so the regrouping changes nothing.
 __global__ void __launch_bounds__(kRisBlock, 1) k_ris(FrameView fv, SceneView sc, const uint2* __restrict__ bags, uint2* __restrict__ order, uint32_t seed, int allow_simple) {
-    static_assert(kPrimarySamples == 32u, "the survivor mask is one 32-bit word");
+    static_assert(kPrimarySamples == 32u && kRisRows % 2 == 0, "the survivor mask is one 32-bit word; a warp takes pairs of sets (a short one, a long one)");
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     const size_t np = fv.npix;
     BagSmem bag;
     bag.sph = reinterpret_cast<float4*>(ris_smem); bag.pln = bag.sph + kLightsPerBag; bag.g0 = bag.pln + kLightsPerBag; bag.g1 = bag.g0 + kLightsPerBag; bag.g2 = bag.g1 + kLightsPerBag;
     bag.pa = reinterpret_cast<float2*>(bag.g2 + kLightsPerBag);
-    // xorshift state in front of every candidate, [candidate][thread]: phase B picks a survivor's stream up here instead of replaying
+    // xorshift state in front of every candidate, [candidate][slot]: phase B picks a survivor's stream up here instead of replaying
     // the draws of the candidates it skips (that replay loop, divergent by nature, was 12 % of the kernel's instructions)
-    uint32_t (*s_state)[kRisBlock] = reinterpret_cast<uint32_t (*)[kRisBlock]>(ris_smem + kRisBagBytes);
-    __shared__ uint32_t s_next;
-    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t (*s_state)[kRisSlots] = reinterpret_cast<uint32_t (*)[kRisSlots]>(ris_smem + kRisBagBytes);
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(ris_smem + kRisBagBytes + kRisStateBytes);
+    uint32_t* s_pix = s_mask + kRisSlots;
+    uint16_t* s_sorted = reinterpret_cast<uint16_t*>(s_pix + kRisSlots);
+    __shared__ uint32_t s_next, s_row0[kRisGroups], s_bin[kRisGroups][kPrimarySamples + 2u];   // bin 0: slots without a pixel; bin 1 + c: pixels with c survivors
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t grp = warp / (uint32_t)kRisGroupWarps, gwarp = warp % (uint32_t)kRisGroupWarps, gtid = threadIdx.x % (uint32_t)kRisGroupThreads;
+    const uint32_t slot_base = grp * (uint32_t)kRisGroupSlots;
+    auto group_sync = [grp]() { if (kRisGroupWarps == 1) __syncwarp(); else asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "n"(kRisGroupThreads) : "memory"); };
     const uint32_t ngroups = (fv.npix + 255u) / 256u;
     const uint2* meta = order + ngroups;
     uint32_t* tickets = reinterpret_cast<uint32_t*>(order + ngroups + 64u);        // .x of entry b (stride 2 words)
@@ -291,52 +325,98 @@ __global__ void __launch_bounds__(kRisBlock, 1) k_ris(FrameView fv, SceneView sc
             bag.sph[e] = f4(ctr, rad); bag.pln[e] = plane;
             bag.g0[e] = a; bag.g1[e] = b; bag.g2[e] = make_float4(c.x, d.x, d.y, d.z); bag.pa[e] = make_float2(bag_pdf, d.w);
         }
-        __syncthreads();
+        __syncthreads();                                        // the bag is staged
         const uint2 range = meta[cur];
-        // ---- this warp's rows of the bag
+        // ---- the bag's rows: every group of warps takes kRisGroupRows at a time, on its own
         for (;;) {
-        uint32_t it = 0u;
-        if (lane == 0u) it = atomicAdd(&tickets[2u * cur], 1u);
-        it = __shfl_sync(0xFFFFFFFFu, it, 0);
-        if (it >= range.y * 8u) break;
-        const uint32_t my_base = __ldg(&order[range.x + (it >> 3)]).x * 256u + (it & 7u) * 32u;
-
-        const uint32_t i = my_base + lane;
-        bool valid = i < fv.npix;
-        Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
-        px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
-        if (valid && surface_flags(fv.surf_cur, np, i)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); valid = false; }
-        if (valid) surface_load_shading(fv.surf_cur, np, i, px);
-        const uint32_t s0 = wang_hash(seed + wang_hash(i + fv.pix0));
-        Reservoir fresh = reservoir_zero();
-
-        // ---- phase A: which candidates need the ordered path
-        uint32_t mask = 0u;
-        if (valid) {
-            uint32_t sa = s0;
+            group_sync();                                       // phase B of the group's previous iteration is over
+            if (gtid == 0u) s_row0[grp] = atomicAdd(&tickets[2u * cur], (uint32_t)kRisGroupRows);
+            if (gtid < kPrimarySamples + 2u) s_bin[grp][gtid] = 0u;
+            group_sync();
+            const uint32_t row0 = s_row0[grp];
+            if (row0 >= range.y * 8u) break;                    // group-uniform
+            // ---- phase A: which candidates of which pixel need the ordered path
+            uint32_t key[kRisRows];
+#pragma unroll
+            for (uint32_t r = 0; r < (uint32_t)kRisRows; ++r) {
+                const uint32_t it = row0 + gwarp * (uint32_t)kRisRows + r, slot = slot_base + r * (uint32_t)kRisGroupThreads + gtid;
+                uint32_t i = kNone;
+                if (it < range.y * 8u) {
+                    i = __ldg(&order[range.x + (it >> 3)]).x * 256u + (it & 7u) * 32u + lane;
+                    if (i >= fv.npix) i = kNone;
+                }
+                float3 ppos = f3(0.f), pnormal = f3(0.f);
+                if (i != kNone) {
+                    const float4 a = fv.surf_cur[i];
+                    if (__float_as_uint(a.w)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); i = kNone; }
+                    else { ppos = f3(a); pnormal = f3(fv.surf_cur[np + i]); }
+                }
+                uint32_t mask = 0u;
+                if (i != kNone) {
+                    uint32_t sa = wang_hash(seed + wang_hash(i + fv.pix0));
 #pragma unroll 2
-            for (uint32_t k = 0; k < kPrimarySamples; ++k) {
-                s_state[k][threadIdx.x] = sa;
-                const float r = rand_f(sa);
-                const uint32_t slot = (uint32_t)(int)roundf((float)(kLightsPerBag - 1u) * r);
-                rand_u32(sa); rand_u32(sa);                      // the candidate's u and v: only the stream position matters here
-                // ordered unless the update is provably a pure count increment: the light cannot pass the geometric test from anywhere on it
-                // (weight 0 / bag pdf, a bag pdf of 0 or NaN never lands here) and the acceptance draw is not the all-zero xorshift state
-                const bool ordered = candidate_may_pass(bag, slot, px.pos, px.normal) || sa == 0u;
-                mask |= (ordered ? 1u : 0u) << k;
+                    for (uint32_t k = 0; k < kPrimarySamples; ++k) {
+                        s_state[k][slot] = sa;
+                        const float rr = rand_f(sa);
+                        const uint32_t cslot = (uint32_t)(int)roundf((float)(kLightsPerBag - 1u) * rr);
+                        rand_u32(sa); rand_u32(sa);                  // the candidate's u and v: only the stream position matters here
+                        // ordered unless the update is provably a pure count increment: the light cannot pass the geometric test from anywhere on it
+                        // (weight 0 / bag pdf, a bag pdf of 0 or NaN never lands here) and the acceptance draw is not the all-zero xorshift state
+                        const bool ordered = candidate_may_pass(bag, cslot, ppos, pnormal) || sa == 0u;
+                        mask |= (ordered ? 1u : 0u) << k;
+                    }
+                }
+                s_mask[slot] = mask; s_pix[slot] = i;
+                key[r] = i == kNone ? 0u : 1u + (uint32_t)__popc(mask);
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key[r]);
+                if (lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(&s_bin[grp][key[r]], (uint32_t)__popc(peers));
             }
-            fresh.count = (int)kPrimarySamples - __popc(mask);
-        }
-
-        // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation
-        const BsdfCtx ctx = surface_ctx(px);
-        if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_simple()))) ris_phase_b<2>(bag, s_state, ctx, px, mask, s0, fresh);
-        else if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_isotropic()))) ris_phase_b<1>(bag, s_state, ctx, px, mask, s0, fresh);
-        else ris_phase_b<0>(bag, s_state, ctx, px, mask, s0, fresh);
-        if (valid) {
-            reservoir_update_weight(fresh);
-            reservoir_store(fv.res_cur, np, i, fresh);
-        }
+            group_sync();
+            // ---- counting sort of the group's slots by survivor count: exclusive scan of the 34 bins by its first warp, then a ranked scatter
+            if (gwarp == 0u) {
+                const uint32_t c0 = s_bin[grp][lane], c1 = lane < 2u ? s_bin[grp][32u + lane] : 0u;
+                uint32_t inc = c0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)lane >= d) inc += t; }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31), c32 = __shfl_sync(0xFFFFFFFFu, c1, 0);
+                s_bin[grp][lane] = inc - c0;
+                if (lane == 0u) s_bin[grp][32] = total; else if (lane == 1u) s_bin[grp][33] = total + c32;
+            }
+            group_sync();
+#pragma unroll
+            for (uint32_t r = 0; r < (uint32_t)kRisRows; ++r) {
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key[r]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0u;
+                if ((int)lane == leader) base = atomicAdd(&s_bin[grp][key[r]], (uint32_t)__popc(peers));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                s_sorted[slot_base + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint16_t)(slot_base + r * (uint32_t)kRisGroupThreads + gtid);
+            }
+            group_sync();
+            // ---- phase B: survivors in candidate order, lanes aligned on the BSDF evaluation; 32 pixels of (nearly) equal survivor count per
+            //      warp: warp w of the group takes set w of the ascending order, then set (last - w)
+#pragma unroll 1
+            for (uint32_t r = 0; r < (uint32_t)kRisRows; ++r) {
+                const uint32_t set = (r & 1u) == 0u ? gwarp * (uint32_t)(kRisRows / 2) + r / 2u : (uint32_t)kRisGroupRows - 1u - (gwarp * (uint32_t)(kRisRows / 2) + r / 2u);
+                const uint32_t slot = s_sorted[slot_base + set * 32u + lane];
+                const uint32_t i = s_pix[slot], mask = s_mask[slot];
+                const bool valid = i != kNone;
+                if (!__any_sync(0xFFFFFFFFu, valid)) continue;
+                Surface px; px.pos = f3(0.f); px.normal = f3(0.f); px.tangent = f3(0.f); px.incoming = f3(0.f); px.transport = f3(0.f); px.t = 0.f; px.flags = 0u;
+                px.mat.color = make_float4(0.f, 0.f, 0.f, 0.f); px.mat.emissive = px.mat.color; px.mat.transmittance = px.mat.color; px.mat.tint = px.mat.color; px.mat.params = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) surface_load_shading(fv.surf_cur, np, i, px);
+                const uint32_t s0 = wang_hash(seed + wang_hash(i + fv.pix0));
+                Reservoir fresh = reservoir_zero();
+                if (valid) fresh.count = (int)kPrimarySamples - __popc(mask);
+                const BsdfCtx ctx = surface_ctx(px);
+                if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_simple()))) ris_phase_b<2>(bag, s_state, slot, ctx, px, mask, s0, fresh);
+                else if (__all_sync(0xFFFFFFFFu, allow_simple && (!valid || ctx.is_isotropic()))) ris_phase_b<1>(bag, s_state, slot, ctx, px, mask, s0, fresh);
+                else ris_phase_b<0>(bag, s_state, slot, ctx, px, mask, s0, fresh);
+                if (valid) {
+                    reservoir_update_weight(fresh);
+                    reservoir_store(fv.res_cur, np, i, fresh);
+                }
+            }
         }
     }
 }
@@ -665,6 +745,14 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_combine(FrameView 
 }
 
 } // namespace
+#ifdef LB_RIS_STATS
+void dump_ris_stats() {
+    unsigned long long h[8]; cudaMemcpyFromSymbol(h, g_ris_stats, sizeof h);
+    fprintf(stderr, "RIS stats: rows %llu, survivors/row %.2f (per lane %.2f), max-per-row %.2f, rounds/row %.2f, rounds with an exact pass %.2f, exact passes/row %.2f\n",
+            h[5], (double)h[0] / h[5], (double)h[0] / h[5] / 32., (double)h[1] / h[5], (double)h[4] / h[5], (double)h[3] / h[5], (double)h[2] / h[5]);
+    memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_ris_stats, h, sizeof h);
+}
+#endif
 
 void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, const BvhView& bvh, const RestirBuffers& rb, const RestirArgs& a, uint32_t& ticket) {
     if (sc.num_lights == 0u) return;
