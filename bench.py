@@ -372,7 +372,7 @@ def run_gpu(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_of(args, W, H), "parallelism": f"sample-sharded x{world}", "history_fill_frames": HISTORY_FRAMES,
                 "fps": args.steps / (ms * 1e-3), "samples_per_s": W * H * args.steps * world / (ms * 1e-3), "rays_per_frame": rays_per_frame,
-                "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
+                "scene": {"triangles": tris, "lights": lights, "bvh_bytes": bvh_bytes, "bvh_build_ms": bvh_build_ms, "bvh_first_alloc_ms": counters.get("bvh_alloc_us", 0) / 1e3, "bvh_builder": os.environ.get("LB_BVH_BUILDER", "ploc")},
                 "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e2e_s / args.steps * 1e3,
                         "what": "one GPU: camera upload + frame + HDR read-back per step" if world == 1 else
                                 f"per step: camera upload and one frame on each of the {world} ranks, ncclReduce of the accumulation buffers onto rank 0 inside the library, HDR read-back on rank 0 only"},

@@ -237,7 +237,9 @@ LB_API int lb_read_gbuffer(LbRenderer r, float* depth, float* normal_roughness4,
  * names are returned as a single ';'-separated string valid until the next call. */
 LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint32_t capacity, uint32_t* count);
 /* counters of the last frame: [0]=extend rays, [1]=shadow rays, [2]=ReSTIR visibility rays, [3]=kernel launches,
- * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes, [8]=bvh build time (us), [9]=bvh levels, [10]=PLOC rounds */
+ * [4]=lights, [5]=triangles, [6]=bvh nodes, [7]=bvh bytes, [8]=bvh build time (us, device time of the build proper: what a re-commit costs),
+ * [9]=bvh levels, [10]=PLOC rounds, [11]=traversal-stack overflows (must be 0), [12]=last refit (us), [13]=refits since the last build,
+ * [14]=host time of the build's allocations (us; paid by the first commit of a renderer only) */
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* values, uint32_t capacity, uint32_t* count);
 
 /* ---- output stage behind the path ---- */

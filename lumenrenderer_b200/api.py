@@ -559,7 +559,7 @@ class Renderer:
         vals, n = np.zeros(16, np.uint64), C.c_uint32()
         self.b.check(self.b.frame_counters(self._h, vals.ctypes.data, 16, C.byref(n)))
         keys = ["extend_rays", "shadow_rays", "visibility_rays", "kernel_launches", "lights", "triangles", "bvh_nodes", "bvh_bytes",
-                "bvh_build_us", "bvh_levels", "bvh_build_rounds", "stack_overflows", "bvh_refit_us", "bvh_refits"]
+                "bvh_build_us", "bvh_levels", "bvh_build_rounds", "stack_overflows", "bvh_refit_us", "bvh_refits", "bvh_alloc_us"]
         return {k: int(v) for k, v in zip(keys, vals[: n.value])}
 
     def save_png(self, path: str):

@@ -356,6 +356,7 @@ struct Renderer {
         LB_CUDA(cudaStreamSynchronize(stream));
         counters[4] = lights.num_lights; counters[5] = total_tris; counters[6] = bvh.num_nodes + (dual_bvh ? bvh_any.num_nodes : 0u); counters[7] = bvh.bytes() + (dual_bvh ? bvh_any.bytes() : 0u);
         counters[8] = (uint64_t)((bvh.build_ms + (dual_bvh ? bvh_any.build_ms : 0.f)) * 1000.f); counters[9] = bvh.levels; counters[10] = bvh.ploc_rounds;
+        counters[14] = (uint64_t)((bvh.alloc_ms + (dual_bvh ? bvh_any.alloc_ms : 0.f)) * 1000.f);   // host time of the builds' allocations (first commit only)
         counters[12] = 0; counters[13] = 0;
         scene_dirty = false; transforms_dirty = false;
     }
@@ -826,7 +827,7 @@ static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uin
     LB_CUDA(cudaStreamSynchronize(R->stream));
     R->counters[11] = overflows;              // traversal-stack overflows since the last frame began (debug traces included): must be 0
     R->counters[0] = s[STAT_EXTEND]; R->counters[1] = s[STAT_SHADOW]; R->counters[2] = s[STAT_VIS]; R->counters[3] = R->launches_last_frame;
-    const uint32_t n = cap < 14 ? cap : 14; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
+    const uint32_t n = cap < 15 ? cap : 15; memcpy(v, R->counters, n * 8); if (count) *count = n; return (int)LB_OK;
 }
 LB_API int lb_frame_counters(LbRenderer r, uint64_t* v, uint32_t cap, uint32_t* count) {
     return guarded(R_, [&]() { return frame_counters_locked(R_, v, cap, count); });

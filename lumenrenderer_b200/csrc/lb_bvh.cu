@@ -155,7 +155,8 @@ __global__ void k_ploc_init(const uint32_t* __restrict__ sorted, const float4* _
 
 // nearest neighbour of every cluster within +-kPlocRadius positions: smallest surface area of the merged box, ties to the smaller index
 template <int kPlocRadius>
-__global__ void __launch_bounds__(kPlocBlock) k_ploc_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, uint32_t m, uint32_t* __restrict__ nearest) {
+__global__ void __launch_bounds__(kPlocBlock) k_ploc_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, const uint32_t* __restrict__ m_in, uint32_t* __restrict__ nearest) {
+    const uint32_t m = *m_in;                                   // the round's cluster count lives on the device: no host round trip per round
     __shared__ float4 slo[kPlocBlock + 2 * kPlocRadius], shi[kPlocBlock + 2 * kPlocRadius];
     const int first = (int)(blockIdx.x * kPlocBlock) - kPlocRadius;
     for (int t = threadIdx.x; t < kPlocBlock + 2 * kPlocRadius; t += kPlocBlock) {
@@ -179,9 +180,9 @@ __global__ void __launch_bounds__(kPlocBlock) k_ploc_nearest(const float4* __res
 }
 
 // mutual nearest neighbours merge into a new binary node, which takes the place of the left partner
-__global__ void k_ploc_merge(uint32_t* __restrict__ cl, float4* __restrict__ clo, float4* __restrict__ chi, const uint32_t* __restrict__ nearest, uint32_t m,
+__global__ void k_ploc_merge(uint32_t* __restrict__ cl, float4* __restrict__ clo, float4* __restrict__ chi, const uint32_t* __restrict__ nearest, const uint32_t* __restrict__ m_in,
                              uint2* __restrict__ children, float4* __restrict__ nlo, float4* __restrict__ nhi, uint32_t* __restrict__ count, uint32_t* __restrict__ next_node, uint32_t* __restrict__ keep) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, m = *m_in;
     if (i >= m) return;
     const uint32_t j = nearest[i];
     if (j >= m || nearest[j] != i) { keep[i] = 1u; return; }
@@ -194,10 +195,11 @@ __global__ void k_ploc_merge(uint32_t* __restrict__ cl, float4* __restrict__ clo
     cl[i] = id; clo[i] = l; chi[i] = h; keep[i] = 1u;
 }
 
-__global__ void k_ploc_compact(const uint32_t* __restrict__ cl, const float4* __restrict__ clo, const float4* __restrict__ chi, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offset, uint32_t m,
-                               uint32_t* __restrict__ cl_out, float4* __restrict__ clo_out, float4* __restrict__ chi_out, uint32_t* __restrict__ m_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_ploc_compact(const uint32_t* __restrict__ cl, const float4* __restrict__ clo, const float4* __restrict__ chi, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offset, const uint32_t* __restrict__ m_in,
+                               uint32_t* __restrict__ cl_out, float4* __restrict__ clo_out, float4* __restrict__ chi_out, uint32_t* __restrict__ m_out, uint32_t* __restrict__ rounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, m = *m_in;
     if (i >= m) return;
+    if (i == 0u && m > 1u) *rounds += 1u;                       // a round launched after the last merge only carries the root across
     if (keep[i]) { const uint32_t o = offset[i]; cl_out[o] = cl[i]; clo_out[o] = clo[i]; chi_out[o] = chi[i]; }
     if (i == m - 1u) *m_out = offset[i] + keep[i];
 }
@@ -288,12 +290,13 @@ __global__ void k_refit_level(Bvh8Node* __restrict__ nodes, uint32_t first, uint
     nodes[id] = nd;
 }
 
-__global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items, WorkItem* __restrict__ next, uint32_t* __restrict__ counters /* 0: nodes, 1: tris, 2: next items */,
+__global__ void k_collapse(const WorkItem* __restrict__ items, const uint32_t* __restrict__ n_items_in, WorkItem* __restrict__ next, uint32_t* __restrict__ next_count, uint32_t* __restrict__ counters /* 0: nodes, 1: tris */,
                            int n, const uint2* __restrict__ children, const uint32_t* __restrict__ count, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
                            const uint32_t* __restrict__ sorted, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out,
                            uint32_t* __restrict__ perm_out) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_items) return;
+    // the level's item count lives on the device (written by the previous level's launch): a fixed grid strides over it
+    const uint32_t n_items = *n_items_in;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_items; w += gridDim.x * blockDim.x) {
     const WorkItem item = items[w];
     const uint32_t first_leaf = (uint32_t)(n - 1);
     auto tri_count = [&](uint32_t node) -> uint32_t { return count[node]; };
@@ -342,7 +345,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
     for (int c = 0; c < nc; ++c) { const uint32_t k = tri_count(cand[c]); if (k <= kLeafMax) n_leaf_tris += k; else ++n_inner; }
     const uint32_t child_base = n_inner ? atomicAdd(&counters[0], n_inner) : 0u;
     const uint32_t tri_base = n_leaf_tris ? atomicAdd(&counters[1], n_leaf_tris) : 0u;
-    const uint32_t next_base = n_inner ? atomicAdd(&counters[2], n_inner) : 0u;
+    const uint32_t next_base = n_inner ? atomicAdd(next_count, n_inner) : 0u;
 
     const uint32_t ex = quant_exponent(phi.x - plo.x), ey = quant_exponent(phi.y - plo.y), ez = quant_exponent(phi.z - plo.z);
     const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
@@ -383,6 +386,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
     out.q3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     out.q4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
     nodes[item.wnode] = out;
+    }
 }
 
 } // namespace
@@ -390,8 +394,11 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, uint32_t n_items,
 void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder, int ploc_radius) {
     out.num_nodes = 0; out.num_tris = 0; out.levels = 0; out.build_ms = 0.f; out.ploc_rounds = 0;
     if (n == 0) return;
+    static const bool timing = getenv("LB_BVH_TIMING") != nullptr;
+    auto tick = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(s); static double last = 0; timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; fprintf(stderr, "[bvh %u] %-10s +%.3f ms\n", n, what, last ? now - last : 0.0); last = now; };
+    tick("enter");
     cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
-    LB_CUDA(cudaEventRecord(e0, s));
+    timespec a0, a1; clock_gettime(CLOCK_MONOTONIC, &a0);
 
     const uint32_t n_binary = 2u * n - 1u;
     StreamBuf<float4> tlo, thi, nlo, nhi; StreamBuf<int> cbounds; StreamBuf<uint64_t> keys, keys_sorted; StreamBuf<uint32_t> vals, sorted, count, counters;
@@ -399,9 +406,16 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     tlo.reserve(n, s); thi.reserve(n, s); nlo.reserve(n_binary, s); nhi.reserve(n_binary, s); count.reserve(n_binary, s); cbounds.reserve(6, s);
     keys.reserve(n, s); keys_sorted.reserve(n, s); vals.reserve(n, s); sorted.reserve(n, s); counters.reserve(4, s);
     children.reserve(n, s); items_a.reserve(n, s); items_b.reserve(n, s);
+    tick("scratch");
     out.nodes.reserve(n); out.tris.reserve(3 * (size_t)n);          // three axis-rotated copies of the leaf-ordered triangles (k_rotate_tris)
     out.perm.reserve(n); out.box_lo.reserve(n); out.box_hi.reserve(n); out.level_start.clear(); out.refits = 0;
 
+    tick("alloc");
+    // build_ms is the device time of the build proper — what a re-commit of the scene costs. The allocations above are paid by the first
+    // build of a renderer only (afterwards the buffers and the stream-ordered pool hold the memory); they are reported apart: on a fresh
+    // process they take 3 - 10 ms of cudaMalloc / pool growth for C2, more than the build itself.
+    clock_gettime(CLOCK_MONOTONIC, &a1); out.alloc_ms = (float)((a1.tv_sec - a0.tv_sec) * 1e3 + (a1.tv_nsec - a0.tv_nsec) * 1e-6);
+    LB_CUDA(cudaEventRecord(e0, s));
     const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
     const int B = 256;
@@ -412,6 +426,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     cub_tmp.reserve(tmp_bytes, s);
     LB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
 
+    tick("sort");
     uint32_t root = 0u;                                     // binary node ids: internal [0, n-2], leaf j = (n-1) + j
     if (builder == BvhBuilder::LBVH || n == 1) {
         StreamBuf<uint32_t> parent, flags; StreamBuf<uint2> range;
@@ -424,54 +439,83 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         // PLOC: the cluster arrays ping-pong through a flag / exclusive-scan / scatter compaction every round
         StreamBuf<uint32_t> cl[2], nearest, keep, offset, m_dev; StreamBuf<float4> clo[2], chi[2];
         for (int k = 0; k < 2; ++k) { cl[k].reserve(n, s); clo[k].reserve(n, s); chi[k].reserve(n, s); }
-        nearest.reserve(n, s); keep.reserve(n, s); offset.reserve(n, s); m_dev.reserve(2, s);
+        nearest.reserve(n, s); keep.reserve(n, s); offset.reserve(n, s); m_dev.reserve(4, s);
         size_t scan_bytes = 0;
         LB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep.p, offset.p, (int)n, s));
         cub_tmp.reserve(scan_bytes, s);
-        LB_CUDA(cudaMemsetAsync(m_dev.p, 0, 2 * sizeof(uint32_t), s));          // [0]: cluster count after the round, [1]: next internal node id
+        // m_dev: [0] / [2] cluster count before / after the round (the two slots alternate), [1] next internal node id, [3] rounds that merged.
+        // The rounds are launched in batches with grids sized for the count at the start of the batch; the kernels read the actual count
+        // from the device, and a round launched after the last merge just carries the root across. One host round trip per BATCH: the
+        // first version read the count back after every round (~55 rounds x 2 hierarchies x ~100 us: 12 of the 16 ms of a C2 build).
+        const uint32_t h_m[4] = {n, 0u, 0u, 0u};
+        LB_CUDA(cudaMemcpyAsync(m_dev.p, h_m, sizeof h_m, cudaMemcpyHostToDevice, s));
         k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
-        uint32_t m = n; int cur = 0;
+        uint32_t m = n; int cur = 0; uint32_t slot = 0u;
+        constexpr int kRoundsPerBatch = 16;
         while (m > 1u) {
-            if (ploc_radius >= 128) k_ploc_nearest<128><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
-            else if (ploc_radius >= 64) k_ploc_nearest<64><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
-            else k_ploc_nearest<16><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m, nearest.p);
-            LB_LAUNCH_CHECK();
-            k_ploc_merge<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, nearest.p, m, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, keep.p); LB_LAUNCH_CHECK();
-            LB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, scan_bytes, keep.p, offset.p, (int)m, s));
-            k_ploc_compact<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, keep.p, offset.p, m, cl[cur ^ 1].p, clo[cur ^ 1].p, chi[cur ^ 1].p, m_dev.p); LB_LAUNCH_CHECK();
-            uint32_t m_new = 0;
-            LB_CUDA(cudaMemcpyAsync(&m_new, m_dev.p, sizeof m_new, cudaMemcpyDeviceToHost, s));
+            for (int b = 0; b < kRoundsPerBatch; ++b) {
+                const uint32_t* m_in = m_dev.p + slot; uint32_t* m_out = m_dev.p + (slot ^ 2u);
+                if (ploc_radius >= 128) k_ploc_nearest<128><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m_in, nearest.p);
+                else if (ploc_radius >= 64) k_ploc_nearest<64><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m_in, nearest.p);
+                else k_ploc_nearest<16><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m_in, nearest.p);
+                LB_LAUNCH_CHECK();
+                k_ploc_merge<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, nearest.p, m_in, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, keep.p); LB_LAUNCH_CHECK();
+                // scanned over the batch's starting count: entries past the round's own count are stale flags of an earlier round and do not
+                // reach the exclusive prefixes in front of them
+                LB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, scan_bytes, keep.p, offset.p, (int)m, s));
+                k_ploc_compact<<<grid_for(m, B), B, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, keep.p, offset.p, m_in, cl[cur ^ 1].p, clo[cur ^ 1].p, chi[cur ^ 1].p, m_out, m_dev.p + 3); LB_LAUNCH_CHECK();
+                cur ^= 1; slot ^= 2u;
+            }
+            uint32_t h_back[4];
+            LB_CUDA(cudaMemcpyAsync(h_back, m_dev.p, sizeof h_back, cudaMemcpyDeviceToHost, s));
+            LB_CUDA(cudaMemcpyAsync(&root, cl[cur].p, sizeof root, cudaMemcpyDeviceToHost, s));
             LB_CUDA(cudaStreamSynchronize(s));
+            const uint32_t m_new = h_back[slot];
             if (m_new >= m || m_new == 0u) throw CudaError("bvh_build: PLOC made no progress");
-            m = m_new; cur ^= 1; ++out.ploc_rounds;
+            m = m_new; out.ploc_rounds = h_back[3];
         }
-        LB_CUDA(cudaMemcpyAsync(&root, cl[cur].p, sizeof root, cudaMemcpyDeviceToHost, s));
-        LB_CUDA(cudaStreamSynchronize(s));
     }
 
-    // level-synchronous collapse of the binary hierarchy into 8-wide nodes
+    tick("binary");
+    // level-synchronous collapse of the binary hierarchy into 8-wide nodes. level_items[L] = work items of level L, appended by the launch of
+    // level L - 1; the launches go out in batches over a fixed grid and the counts are read back once per batch (a launch for a level
+    // past the last one finds 0 items)
     const uint32_t h_counters[4] = {1u, 0u, 0u, 0u};
     LB_CUDA(cudaMemcpyAsync(counters.p, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, s));
     const WorkItem root_item{n == 1 ? 0u : root, 0u};
     LB_CUDA(cudaMemcpyAsync(items_a.p, &root_item, sizeof root_item, cudaMemcpyHostToDevice, s));
-    uint32_t n_items = 1; WorkItem* cur = items_a.p; WorkItem* nxt = items_b.p;
-    uint32_t h_c[4];
-    uint32_t level_first = 0;                               // the nodes of a level are a contiguous range: [level_first, level_first + n_items)
-    while (n_items) {
-        out.level_start.push_back(level_first); level_first += n_items;
-        LB_CUDA(cudaMemsetAsync(counters.p + 2, 0, sizeof(uint32_t), s));
-        k_collapse<<<grid_for(n_items, 128), 128, 0, s>>>(cur, n_items, nxt, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, tris_in, out.nodes.p, out.tris.p, out.perm.p);
-        LB_LAUNCH_CHECK();
+    constexpr uint32_t kMaxLevels = 64, kLevelsPerBatch = 12;
+    StreamBuf<uint32_t> level_items; level_items.reserve(kMaxLevels + 1u, s);
+    uint32_t h_items[kMaxLevels + 1u] = {1u};
+    LB_CUDA(cudaMemcpyAsync(level_items.p, h_items, sizeof h_items, cudaMemcpyHostToDevice, s));
+    WorkItem* cur = items_a.p; WorkItem* nxt = items_b.p;
+    uint32_t h_c[4] = {0u, 0u, 0u, 0u};
+    int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const uint32_t collapse_grid = (uint32_t)std::min<uint64_t>(grid_for(n, 128), (uint64_t)sms * 16u);
+    uint32_t launched = 0;
+    for (;;) {
+        for (uint32_t b = 0; b < kLevelsPerBatch && launched < kMaxLevels; ++b, ++launched) {
+            k_collapse<<<collapse_grid, 128, 0, s>>>(cur, level_items.p + launched, nxt, level_items.p + launched + 1u, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, tris_in,
+                                                     out.nodes.p, out.tris.p, out.perm.p);
+            LB_LAUNCH_CHECK();
+            std::swap(cur, nxt);
+        }
+        LB_CUDA(cudaMemcpyAsync(h_items, level_items.p, sizeof h_items, cudaMemcpyDeviceToHost, s));
         LB_CUDA(cudaMemcpyAsync(h_c, counters.p, sizeof h_c, cudaMemcpyDeviceToHost, s));
         LB_CUDA(cudaStreamSynchronize(s));
-        n_items = h_c[2]; std::swap(cur, nxt); ++out.levels;
+        if (h_items[launched] == 0u) break;
+        if (launched >= kMaxLevels) throw CudaError("bvh_build: hierarchy deeper than 64 levels");
     }
+    uint32_t level_first = 0;                               // the nodes of a level are a contiguous range: [level_first, level_first + items)
+    for (uint32_t L = 0; L < kMaxLevels && h_items[L] != 0u; ++L) { out.level_start.push_back(level_first); level_first += h_items[L]; ++out.levels; }
     out.level_start.push_back(level_first);
     out.num_nodes = h_c[0]; out.num_tris = h_c[1];
+    tick("collapse");
     if (out.num_tris == n) { k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(out.tris.p, n); LB_LAUNCH_CHECK(); }
     LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
     LB_CUDA(cudaEventElapsedTime(&out.build_ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tick("finish");
     if (out.num_tris != n) throw CudaError("bvh_build: triangle count mismatch after collapse");
     if (level_first != out.num_nodes) throw CudaError("bvh_build: level ranges do not cover the nodes");
 }

@@ -69,7 +69,7 @@ struct DeviceBvh {
     // level, so a level is a contiguous range), and a full-precision box per node to hand up to its parent
     DevBuf<uint32_t> perm; DevBuf<float4> box_lo, box_hi; std::vector<uint32_t> level_start;
     uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0, refits = 0;
-    float build_ms = 0.f, refit_ms = 0.f;
+    float build_ms = 0.f, alloc_ms = 0.f, refit_ms = 0.f;
     BvhView view(uint32_t* overflow = nullptr) const { return BvhView{nodes.p, tris.p, num_tris, overflow}; }
     size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + 3 * (size_t)num_tris * sizeof(DevTri); }      // three rotated triangle copies
 };
