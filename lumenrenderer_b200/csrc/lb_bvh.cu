@@ -195,6 +195,62 @@ __global__ void k_ploc_merge(uint32_t* __restrict__ cl, float4* __restrict__ clo
     cl[i] = id; clo[i] = l; chi[i] = h; keep[i] = 1u;
 }
 
+// The last rounds — at most kPlocTail clusters left — in ONE block: clusters in shared memory, the same nearest / merge / compact steps with
+// block barriers instead of launches (the ~20 rounds from 1024 clusters down to the root were ~100 launches of a few microseconds of work).
+// Same search window, same tie rules as k_ploc_nearest / k_ploc_merge: the tree is the one the launch-per-round loop builds.
+constexpr int kPlocTail = 1024;
+template <int kPlocRadius>
+__global__ void __launch_bounds__(kPlocTail) k_ploc_tail(uint32_t* __restrict__ cl, const float4* __restrict__ clo, const float4* __restrict__ chi, uint32_t* __restrict__ m_io,
+                                                         uint2* __restrict__ children, float4* __restrict__ nlo, float4* __restrict__ nhi, uint32_t* __restrict__ count,
+                                                         uint32_t* __restrict__ next_node, uint32_t* __restrict__ rounds) {
+    __shared__ uint32_t s_cl[kPlocTail], s_near[kPlocTail], s_warp[kPlocTail / 32];
+    __shared__ float4 s_lo[kPlocTail], s_hi[kPlocTail];
+    const int i = (int)threadIdx.x, lane = i & 31, warp = i >> 5;
+    int m = (int)*m_io;
+    if (i < m) { s_cl[i] = cl[i]; s_lo[i] = clo[i]; s_hi[i] = chi[i]; }
+    __syncthreads();
+    uint32_t done = 0u;
+    while (m > 1) {
+        float4 l = make_float4(0.f, 0.f, 0.f, 0.f), h = l; uint32_t id = 0u;
+        if (i < m) {
+            l = s_lo[i]; h = s_hi[i]; id = s_cl[i];
+            float best = FLT_MAX; int bj = -1;
+            const int d0 = max(-kPlocRadius, -i), d1 = min(kPlocRadius, m - 1 - i);
+            for (int d = d0; d <= d1; ++d) {
+                if (d == 0) continue;
+                const float4 ol = s_lo[i + d], oh = s_hi[i + d];
+                const float ex = fmaxf(h.x, oh.x) - fminf(l.x, ol.x), ey = fmaxf(h.y, oh.y) - fminf(l.y, ol.y), ez = fmaxf(h.z, oh.z) - fminf(l.z, ol.z);
+                const float a = ex * ey + ey * ez + ez * ex;
+                if (a < best) { best = a; bj = i + d; }
+            }
+            s_near[i] = (uint32_t)bj;
+        }
+        __syncthreads();
+        bool keep = false;
+        if (i < m) {
+            const uint32_t j = s_near[i];
+            if (j >= (uint32_t)m || s_near[j] != (uint32_t)i) keep = true;
+            else if ((uint32_t)i < j) {
+                const uint32_t b = s_cl[j]; const float4 bl = s_lo[j], bh = s_hi[j];
+                const uint32_t node = atomicAdd(next_node, 1u);
+                l = make_float4(fminf(l.x, bl.x), fminf(l.y, bl.y), fminf(l.z, bl.z), 0.f); h = make_float4(fmaxf(h.x, bh.x), fmaxf(h.y, bh.y), fmaxf(h.z, bh.z), 0.f);
+                children[node] = make_uint2(id, b); nlo[node] = l; nhi[node] = h; count[node] = count[id] + count[b];
+                id = node; keep = true;
+            }
+        }
+        // order-preserving compaction: ballot inside the warp, running sum over the 32 warp totals
+        const uint32_t vote = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_warp[warp] = (uint32_t)__popc(vote);
+        __syncthreads();                                        // also: every read of s_cl / s_lo / s_hi of this round is done
+        uint32_t base = 0u, total = 0u;
+        for (int w = 0; w < kPlocTail / 32; ++w) { const uint32_t c = s_warp[w]; if (w < warp) base += c; total += c; }
+        if (keep) { const uint32_t o = base + (uint32_t)__popc(vote & ((1u << lane) - 1u)); s_cl[o] = id; s_lo[o] = l; s_hi[o] = h; }
+        __syncthreads();
+        m = (int)total; ++done;
+    }
+    if (i == 0) { cl[0] = s_cl[0]; *m_io = 1u; *rounds += done; }
+}
+
 __global__ void k_ploc_compact(const uint32_t* __restrict__ cl, const float4* __restrict__ clo, const float4* __restrict__ chi, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offset, const uint32_t* __restrict__ m_in,
                                uint32_t* __restrict__ cl_out, float4* __restrict__ clo_out, float4* __restrict__ chi_out, uint32_t* __restrict__ m_out, uint32_t* __restrict__ rounds) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, m = *m_in;
@@ -451,8 +507,15 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         LB_CUDA(cudaMemcpyAsync(m_dev.p, h_m, sizeof h_m, cudaMemcpyHostToDevice, s));
         k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
         uint32_t m = n; int cur = 0; uint32_t slot = 0u;
-        constexpr int kRoundsPerBatch = 16;
+        constexpr int kRoundsPerBatch = 8;
         while (m > 1u) {
+            if (m <= (uint32_t)kPlocTail) {                     // the rest in one block
+                uint32_t* m_io = m_dev.p + slot;
+                if (ploc_radius >= 128) k_ploc_tail<128><<<1, kPlocTail, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, m_io, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, m_dev.p + 3);
+                else if (ploc_radius >= 64) k_ploc_tail<64><<<1, kPlocTail, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, m_io, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, m_dev.p + 3);
+                else k_ploc_tail<16><<<1, kPlocTail, 0, s>>>(cl[cur].p, clo[cur].p, chi[cur].p, m_io, children.p, nlo.p, nhi.p, count.p, m_dev.p + 1, m_dev.p + 3);
+                LB_LAUNCH_CHECK();
+            } else
             for (int b = 0; b < kRoundsPerBatch; ++b) {
                 const uint32_t* m_in = m_dev.p + slot; uint32_t* m_out = m_dev.p + (slot ^ 2u);
                 if (ploc_radius >= 128) k_ploc_nearest<128><<<grid_for(m, kPlocBlock), kPlocBlock, 0, s>>>(clo[cur].p, chi[cur].p, m_in, nearest.p);
