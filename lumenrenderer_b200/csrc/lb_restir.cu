@@ -591,14 +591,14 @@ LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i)
 // One pixel of SpatialNeighbourSamplingInternal (ReSTIRKernels.cu:787-980). `geom_at(nx, ny, index)` returns the similarity record (surface
 // plane 1: normal, signed depth) of a pixel inside the image — from global memory (k_spatial) or from the tile staged in shared memory
 // (k_spatial_tma).
-template <bool UNBIASED, class GeomAt>
-LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed, int x, int y, const GeomAt& geom_at) {
-    const size_t np = fv.npix;
+// The two halves of a pixel: the probes (which of the five drawn neighbours are similar) and the merge of their reservoirs.
+// spatial_probe returns the number of accepted neighbours in nb[] (pixel indices), or -1 for a pixel without a surface (nothing to do).
+template <class GeomAt>
+LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const GeomAt& geom_at, uint32_t nb[kSpatialSamples]) {
     const int W = (int)fv.width, H = (int)fv.height;
-    const bool degenerate = seed == 0u;
     const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
     const SurfGeom gc = surf_geom_unpack(geom_at(x, y, i));
-    if (gc.flagged) return;
+    if (gc.flagged) return -1;
     uint32_t s = wang_hash(seed + i + fv.pix0);
     // all five neighbour probes are issued before any is tested (5 independent 16-byte reads in flight)
     uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
@@ -610,12 +610,18 @@ LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, floa
         ni[k] = inside[k] ? (uint32_t)ny * fv.width + (uint32_t)nx : i;
         ng[k] = inside[k] ? geom_at(nx, ny, ni[k]) : geom_at(x, y, i);
     }
-    uint32_t nb[kSpatialSamples]; int count = 0;
+    int count = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kSpatialSamples; ++k) {
         const SurfGeom gn = surf_geom_unpack(ng[k]);
         if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) nb[count++] = ni[k];
     }
+    return count;
+}
+template <bool UNBIASED>
+LB_D void spatial_merge(const FrameView& fv, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed, uint32_t i, int count, const uint32_t nb[kSpatialSamples]) {
+    const size_t np = fv.npix;
+    const bool degenerate = seed == 0u;
     if (count > 1) {
         ResProbe cur = res_probe(in, np, nb[0]);
         Surface p0; surface_load_shading(fv.surf_cur, np, nb[0], p0);      // resampled at the FIRST accepted neighbour
@@ -659,6 +665,13 @@ LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, floa
     }
 }
 
+template <bool UNBIASED, class GeomAt>
+LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed, int x, int y, const GeomAt& geom_at) {
+    uint32_t nb[kSpatialSamples];
+    const int count = spatial_probe(fv, seed, x, y, geom_at, nb);
+    if (count >= 0) spatial_merge<UNBIASED>(fv, in, out, seed, (uint32_t)y * fv.width + (uint32_t)x, count, nb);
+}
+
 template <bool UNBIASED>
 __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
     const TileWalk tw(fv);
@@ -671,6 +684,9 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView 
     }
 }
 
+// (Tried and dropped, r02: regrouping the pixels by accepted-neighbour count between the probes and the merge, as k_ris does with its
+// survivors — the merge loop runs at 16 of 32 lanes. Warp instructions fell, the time rose 1.056 -> 1.117 ms for the two passes: the pass
+// waits for its gathers, not for issue slots, and a regrouped warp gathers from 32 rows instead of one. profiles/r02_a_ab.md.)
 // ---- the same pass with the neighbourhood's similarity records staged in shared memory by the TMA unit (north_star item 3).
 // A block owns a 32x16-pixel tile at a time; every neighbour a pixel of the tile can draw lies within +-30 pixels, so ONE tensor copy
 // (cp.async.bulk.tensor.2d over surface plane 1 seen as rows of 8-byte elements: a box of 184 x 76 = 92 x 76 records = 111 872 bytes, each box
