@@ -36,12 +36,17 @@ METRIC = "Mrays/sec @1440p 1spp 3-bounce ReSTIR (ms/frame in ms_per_step)"
 HISTORY_FRAMES = 8          # frames rendered before the warm-up on both arms: the temporal ReSTIR history of a static camera is filled
 # algorithmic bytes per unit (DESIGN.md "roofline"): what a stage must move per ray / pixel, fp32 payloads, every field once
 ALG_BYTES = {"raygen": 40.0, "extend": 40.0, "shadow": 44.0, "extract": 232.0, "motion": 20.0, "nee": 224.0, "bounce": 216.0,
-             "ris": 256.0, "vis_gen": 288.0, "vis_trace": 32.0, "res_shade": 96.0, "temporal": 612.0, "spatial": 336.0, "combine": 416.0, "merge": 84.0}
+             "ris": 256.0, "vis_gen": 288.0, "vis_trace": 32.0, "res_shade": 96.0, "temporal": 424.0, "spatial": 336.0, "combine": 368.0, "merge": 84.0}
+# temporal / combine: SURVEY 8d counts the reference's 176-byte AoS SurfaceData and 80-byte Reservoir records (612 / 416 B per pixel); the SoA planes
+# these kernels HAVE to move are fewer, and with the AoS figure the fraction came out above 1 (1.05 for k_temporal once it got faster). The figures used
+# are the planes each pixel must read and write once: temporal = motion 8 + previous and current similarity plane 2 x 16 + the 7 other shading planes
+# 112 + previous and current reservoir 2 x 80 + DIRECT channel read-modify-write 32 + reservoir store 80 = 424 (ncu: 418 B / pixel of DRAM traffic);
+# combine = two reservoirs 160 + 8 shading planes 128 + store 80 = 368 (ncu: 362).
 
 
-# what bounds each stage (ncu, profiles/r01_v_frame.md): goes into the `roofline` object of the stage where most of the frame goes
+# what bounds each stage (ncu, profiles/r02_s_frame.md): goes into the `roofline` object of the stage where most of the frame goes
 STAGE_NOTES = {
-    "restir_ris": "instruction-issue bound (74 % issue utilisation): 32 Disney BSDF evaluations per pixel on light records staged in shared memory",
+    "restir_ris": "instruction-issue bound (66 % issue utilisation at 16 warps / SM, 30.5 of 32 lanes active after the regrouping by survivor count): 32 candidates, 15.8 Disney BSDF evaluations per pixel on light records staged in shared memory",
     "restir_visibility": "instruction-issue bound (78 % issue utilisation, 20 of 32 lanes active): traversal of incoherent any-hit rays on an L2-resident BVH; DRAM traffic is a fifth of the algorithmic bytes because only the planes a pixel needs are touched",
     "restir_spatial": "L2 gather latency (3.5 stalled warps per issue on long scoreboard) + BSDF re-evaluation",
     "extend": "instruction-issue bound (77 %): BVH8 traversal, BVH entirely L2-resident",
@@ -61,9 +66,9 @@ def stage_table(stage_ms, fc, npix, depth, peak, traffic):
         "shadow": ("k_shadow", sh * A["shadow"], f"{sh} rays x 44 B"),
         "restir_ris": ("k_ris", npix * A["ris"], f"{npix} px x 256 B"),
         "restir_visibility": ("k_visibility_shade", 2 * npix * (A["vis_gen"] + A["res_shade"]) + vis * A["vis_trace"], f"2 x {npix} px x (288 + 96) B + {vis} rays x 32 B"),
-        "restir_temporal": ("k_temporal", npix * A["temporal"], f"{npix} px x 612 B"),
+        "restir_temporal": ("k_temporal", npix * A["temporal"], f"{npix} px x 424 B (SoA planes; the reference's AoS records: 612 B)"),
         "restir_spatial": ("k_spatial", 2 * npix * A["spatial"], f"2 x {npix} px x 336 B"),
-        "restir_combine": ("k_combine", npix * A["combine"], f"{npix} px x 416 B"),
+        "restir_combine": ("k_combine", npix * A["combine"], f"{npix} px x 368 B (SoA planes; the reference's AoS records: 416 B)"),
         "merge": ("k_merge", npix * A["merge"], f"{npix} px x 84 B"),
     }
     rows = []
