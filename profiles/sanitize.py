@@ -24,4 +24,16 @@ for name, scene, kw in cases:
             r.trace_closest(o, d); r.trace_any(o, d, np.full(2000, 5.0, np.float32)); r.read_gbuffer(); r.read_ldr()
         print(f"{name} overlap={overlap}: rays {fc['extend_rays']}+{fc['shadow_rays']}+{fc['visibility_rays']} mean {hdr[..., :3].mean():.4f}", flush=True)
         r.close()
+# the optional TMA-staged spatial pass (mbarrier + cp.async.bulk.tensor), and a transform-only change (refit of both hierarchies) followed by a
+# change that forces the rebuild (device-driven PLOC rounds, single-block tail, batched collapse)
+os.environ["LB_SPATIAL_TMA"] = "1"
+r = lr.Renderer(lr.Settings(width=W, height=H, depth=3, restir=True)); r.load_scene(scenes.material_gallery()); r.render_frames(2)
+assert np.isfinite(r.read_hdr()).all(); r.close(); del os.environ["LB_SPATIAL_TMA"]
+print("gallery with LB_SPATIAL_TMA=1", flush=True)
+r = lr.Renderer(lr.Settings(width=W, height=H, depth=3, restir=True)); r.load_scene(scenes.cornell_box()); r.render_frames(1)
+m = np.eye(4, dtype=np.float32); m[0, 3] = 0.05
+r.set_instance_transform(1, m); r.render_frames(1); fc = r.frame_counters(); assert fc["bvh_refits"] == 1, fc
+r.set_instance_emissiveness(1, 2, (1.0, 0.5, 0.2), 3.0); r.render_frames(1); fc = r.frame_counters(); assert fc["bvh_refits"] == 0 and fc["stack_overflows"] == 0, fc
+assert np.isfinite(r.read_hdr()).all(); r.close()
+print("cornell refit + rebuild", flush=True)
 print("sanitize workload done")
