@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_extend(BvhView bvh, const float4*
 }
 
 // ------------------------------------------------------------------ fused shade: K6 (+K8, K9 at depth 0) + K10 + K11
-template <bool PRIMARY>
+// NEE = false: the instance for waves that draw no light sample (the primary wave when ReSTIR supplies the direct light) — the NEE and
+// compat-volume code is not generated at all: a smaller kernel for the launch that touches every pixel
+template <bool PRIMARY, bool NEE = true>
 __global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv, SceneView sc, int queue, ShadeArgs a) {
     const uint32_t n = fv.counters[queue ? CNT_RAYS_B : CNT_RAYS_A];
     const RayQueue in = fv.rays[queue], out = fv.rays[queue ^ 1];
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kBlock, LB_SHADE_BLOCKS) k_shade(FrameView fv,
         }
 
         const bool owned = pixel >= fv.own_pix0 && pixel < fv.own_pix1;          // halo rows of a band: surface record only
-        if (a.do_nee && owned) {
+        if (NEE && a.do_nee && owned) {
             uint32_t seed = wang_hash(a.seed + gpixel);
             if (a.num_volumes && a.volume_mode == 0 /* LB_VOLUME_COMPAT */ && sc.num_lights) {
                 // VolumetricShadeDirect (GPUVolumetricShadeDirect.cu:8-101): 5 fixed steps, constant density per unit length, the grid is
@@ -305,7 +307,8 @@ void launch_extend(const LaunchCfg& cfg, const FrameView& fv, const BvhView& bvh
         &fv.counters[CNT_TICKET0 + ticket], primary ? fv.primary_hits : fv.hits, tmin, tmax, &fv.stats[STAT_EXTEND], cfg.trace); LB_LAUNCH_CHECK();
 }
 void launch_shade(const LaunchCfg& cfg, const FrameView& fv, const SceneView& sc, int queue, const ShadeArgs& a) {
-    if (a.depth == 0) k_shade<true><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
+    if (a.depth == 0 && !a.do_nee) k_shade<true, false><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
+    else if (a.depth == 0) k_shade<true><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
     else k_shade<false><<<persistent_grid(cfg, 4), kBlock, 0, cfg.stream>>>(fv, sc, queue, a);
     LB_LAUNCH_CHECK();
 }
