@@ -328,11 +328,14 @@ struct Renderer {
         launch_flatten(cfg(), in, d_flat.p);
         {   // LB_BVH_BUILDER=lbvh selects the fastest build (Karras radix tree); default is the SAH-quality PLOC hierarchy
             const char* e = getenv("LB_BVH_BUILDER");
-            bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC);
+            // LB_BVH_SPLIT=k: early split clipping on a grid of (scene extent / k) for triangles larger than a cell (0: off)
+            const char* sp = getenv("LB_BVH_SPLIT");
+            const float split = sp ? (atof(sp) > 0.0 ? 1.f / (float)atof(sp) : 0.f) : 0.f;
+            bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC, 16, split);
             // LB_BVH_ANYHIT=same: one hierarchy for every ray (halves the build); default: a second PLOC hierarchy with a 128-wide search window
             const char* a = getenv("LB_BVH_ANYHIT");
             dual_bvh = !(a && !strcmp(a, "same")) && total_tris > 1u;
-            if (dual_bvh) bvh_build(stream, d_flat.p, total_tris, bvh_any, BvhBuilder::PLOC, a && !strcmp(a, "ploc64") ? 64 : 128);
+            if (dual_bvh) bvh_build(stream, d_flat.p, total_tris, bvh_any, BvhBuilder::PLOC, a && !strcmp(a, "ploc64") ? 64 : 128, split);
         }
         // the traversal keeps one pending sibling group per level (+ one transient entry) on a kTraceStack-entry stack: refuse a hierarchy it
         // cannot walk without dropping groups instead of rendering wrong hits
@@ -367,7 +370,7 @@ struct Renderer {
     // on the renderer's stream behind the frames in flight. LB_REFIT_MAX bounds how many refits may follow a build (boxes only ever loosen).
     void refit_scene() {
         static const uint32_t max_refits = []() { const char* e = getenv("LB_REFIT_MAX"); return e ? (uint32_t)atoi(e) : 4096u; }();
-        if (!total_tris || bvh.num_tris != total_tris || bvh.refits >= max_refits) { scene_dirty = true; commit_scene(); return; }
+        if (!total_tris || bvh.src_tris != total_tris || bvh.refits >= max_refits) { scene_dirty = true; commit_scene(); return; }
         for (size_t i = 0; i < instances.size(); ++i)
             for (uint32_t e = inst_entry_begin[i]; e < inst_entry_begin[i + 1]; ++e) memcpy(h_entries[e].m, instances[i].m, sizeof h_entries[e].m);
         d_entries.upload(h_entries.data(), h_entries.size(), stream);

@@ -60,6 +60,122 @@ __global__ void k_tri_bounds(const DevTri* __restrict__ tris, uint32_t n, float4
     }
 }
 
+// ---- early split clipping (Ernst & Greiner 2007; the pre-pass PLOC is usually paired with): a triangle whose box is much larger than
+// the scene's typical primitive — the floors, walls and arches of a real asset — enters the build as several REFERENCES, one per cell of a
+// world-aligned grid its (clipped) area reaches, each with the box of the part inside the cell. The hierarchy then separates space across
+// a large triangle instead of wrapping it in one box that overlaps half the scene. The leaf arrays hold the triangle once per reference;
+// a ray that meets the same triangle through two leaves computes the same (t, u, v) twice, and the tie rule keeps the first — hits are a
+// pure function of (ray, triangle set) as before. Boxes: the clipped polygon's box padded like every leaf box (the clip computes cut points
+// in float: the padding is orders above that error, so neighbouring references overlap instead of leaving a gap).
+constexpr int kSplitMaxCells = 512;
+struct SplitParams { float cell; uint32_t enabled; };
+
+__device__ __forceinline__ float axis_of(const float3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+__device__ __forceinline__ void set_axis(float3& v, int a, float x) { if (a == 0) v.x = x; else if (a == 1) v.y = x; else v.z = x; }
+// Sutherland-Hodgman against one axis-aligned half space (keep x_a >= bound when `greater`, else x_a <= bound); returns the new vertex count
+__device__ int clip_half_space(const float3* in, int n, float3* out, int a, float bound, bool greater) {
+    int m = 0;
+    for (int k = 0; k < n; ++k) {
+        const float3 p = in[k], q = in[k + 1 == n ? 0 : k + 1];
+        const float pa = axis_of(p, a), qa = axis_of(q, a);
+        const bool pin = greater ? pa >= bound : pa <= bound, qin = greater ? qa >= bound : qa <= bound;
+        if (pin) out[m++] = p;
+        if (pin != qin) {
+            const float t = (bound - pa) / (qa - pa);
+            float3 x = f3(p.x + t * (q.x - p.x), p.y + t * (q.y - p.y), p.z + t * (q.z - p.z));
+            set_axis(x, a, bound);
+            out[m++] = x;
+        }
+    }
+    return m;
+}
+// the part of triangle (a, b, c) inside the box [lo, hi]: false when (numerically) nothing is left; else its bounds
+__device__ bool clipped_bounds(const float3& a, const float3& b, const float3& c, const float3& lo, const float3& hi, float3& blo, float3& bhi) {
+    float3 p0[10], p1[10];
+    p0[0] = a; p0[1] = b; p0[2] = c; int n = 3;
+    for (int ax = 0; ax < 3 && n > 0; ++ax) {
+        n = clip_half_space(p0, n, p1, ax, axis_of(lo, ax), true);
+        if (n == 0) break;
+        n = clip_half_space(p1, n, p0, ax, axis_of(hi, ax), false);
+    }
+    if (n == 0) return false;
+    blo = p0[0]; bhi = p0[0];
+    for (int k = 1; k < n; ++k) { blo = f3(fminf(blo.x, p0[k].x), fminf(blo.y, p0[k].y), fminf(blo.z, p0[k].z)); bhi = f3(fmaxf(bhi.x, p0[k].x), fmaxf(bhi.y, p0[k].y), fmaxf(bhi.z, p0[k].z)); }
+    return true;
+}
+// the grid a triangle is cut on: the global cell size, doubled until the triangle's box spans at most kSplitMaxCells cells
+struct SplitGrid { float cell; int i0[3], n[3]; bool split; };
+__device__ SplitGrid split_grid(const float3& l, const float3& h, float cell0) {
+    SplitGrid g; g.cell = cell0;
+    const float longest = fmaxf(h.x - l.x, fmaxf(h.y - l.y, h.z - l.z));
+    g.split = cell0 > 0.f && longest > cell0 && isfinite(longest);
+    g.n[0] = g.n[1] = g.n[2] = 1; g.i0[0] = g.i0[1] = g.i0[2] = 0;
+    if (!g.split) return g;
+    for (int it = 0; it < 24; ++it) {
+        long long total = 1;
+        for (int a = 0; a < 3; ++a) {
+            const float fl = floorf(axis_of(l, a) / g.cell), fh = floorf(axis_of(h, a) / g.cell);
+            g.i0[a] = (int)fl; g.n[a] = (int)(fh - fl) + 1; total *= g.n[a];
+        }
+        if (total <= kSplitMaxCells) break;
+        g.cell *= 2.f;
+    }
+    return g;
+}
+// MODE 0: count the references of every triangle; MODE 1: write them (boxes + owning triangle) at offset[i]
+template <int MODE>
+__global__ void k_split(const DevTri* __restrict__ tris, uint32_t n, SplitParams sp, const uint32_t* __restrict__ offset, uint32_t* __restrict__ counts,
+                        float4* __restrict__ rlo, float4* __restrict__ rhi, uint32_t* __restrict__ ref_tri) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 a = f3(tris[i].v0), b = f3(tris[i].v1), c = f3(tris[i].v2);
+    const float3 l = f3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+    const float3 h = f3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+    const float3 pad = f3(pad_of(l.x, h.x), pad_of(l.y, h.y), pad_of(l.z, h.z));
+    const float3 tl = l - pad, th = h + pad;                    // the triangle's own leaf box (k_tri_bounds)
+    uint32_t emitted = 0u; const uint32_t base = MODE ? offset[i] : 0u;
+    const SplitGrid g = split_grid(l, h, sp.enabled ? sp.cell : 0.f);
+    if (g.split) {
+        for (int z = 0; z < g.n[2]; ++z) for (int y = 0; y < g.n[1]; ++y) for (int x = 0; x < g.n[0]; ++x) {
+            const float3 cl = f3((float)(g.i0[0] + x) * g.cell, (float)(g.i0[1] + y) * g.cell, (float)(g.i0[2] + z) * g.cell);
+            const float3 ch = f3((float)(g.i0[0] + x + 1) * g.cell, (float)(g.i0[1] + y + 1) * g.cell, (float)(g.i0[2] + z + 1) * g.cell);
+            // the cell widened by the leaf padding before the clip: a point of the triangle on a cell border belongs to both neighbours
+            const float3 cp = f3(pad_of(cl.x, ch.x), pad_of(cl.y, ch.y), pad_of(cl.z, ch.z));
+            float3 bl, bh;
+            if (!clipped_bounds(a, b, c, cl - cp, ch + cp, bl, bh)) continue;
+            if (MODE) {
+                const float3 bp = f3(pad_of(bl.x, bh.x), pad_of(bl.y, bh.y), pad_of(bl.z, bh.z));
+                bl = bl - bp; bh = bh + bp;
+                rlo[base + emitted] = make_float4(fmaxf(bl.x, tl.x), fmaxf(bl.y, tl.y), fmaxf(bl.z, tl.z), 0.f);
+                rhi[base + emitted] = make_float4(fminf(bh.x, th.x), fminf(bh.y, th.y), fminf(bh.z, th.z), 0.f);
+                ref_tri[base + emitted] = i;
+            }
+            ++emitted;
+        }
+    }
+    if (emitted == 0u) {                                        // not split (or degenerate: nothing survived the clip): the triangle's own box
+        if (MODE) { rlo[base] = f4(tl, 0.f); rhi[base] = f4(th, 0.f); ref_tri[base] = i; }
+        emitted = 1u;
+    }
+    if (!MODE) counts[i] = emitted;
+}
+// centroid bounds of the references (what k_tri_bounds computes for triangles), for the Morton codes
+__global__ void k_ref_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, int* __restrict__ cbounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    float3 c = f3(0.f);
+    if (in) c = (f3(lo[i]) + f3(hi[i])) * 0.5f;
+    const bool ok = in && isfinite(c.x) && isfinite(c.y) && isfinite(c.z);
+    int mn[3] = {ok ? float_order(c.x) : INT_MAX, ok ? float_order(c.y) : INT_MAX, ok ? float_order(c.z) : INT_MAX};
+    int mx[3] = {ok ? float_order(c.x) : INT_MIN, ok ? float_order(c.y) : INT_MIN, ok ? float_order(c.z) : INT_MIN};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { mn[k] = __reduce_min_sync(0xFFFFFFFFu, mn[k]); mx[k] = __reduce_max_sync(0xFFFFFFFFu, mx[k]); }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&cbounds[k], mn[k]); atomicMax(&cbounds[3 + k], mx[k]); }
+    }
+}
+
 __device__ __forceinline__ uint64_t spread21(uint64_t x) {
     x &= 0x1FFFFFull;
     x = (x | x << 32) & 0x1F00000000FFFFull;
@@ -348,7 +464,7 @@ __global__ void k_refit_level(Bvh8Node* __restrict__ nodes, uint32_t first, uint
 
 __global__ void k_collapse(const WorkItem* __restrict__ items, const uint32_t* __restrict__ n_items_in, WorkItem* __restrict__ next, uint32_t* __restrict__ next_count, uint32_t* __restrict__ counters /* 0: nodes, 1: tris */,
                            int n, const uint2* __restrict__ children, const uint32_t* __restrict__ count, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                           const uint32_t* __restrict__ sorted, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out,
+                           const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ ref_tri, const DevTri* __restrict__ tris_in, Bvh8Node* __restrict__ nodes, DevTri* __restrict__ tris_out,
                            uint32_t* __restrict__ perm_out) {
     // the level's item count lives on the device (written by the previous level's launch): a fixed grid strides over it
     const uint32_t n_items = *n_items_in;
@@ -424,7 +540,7 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, const uint32_t* _
             uint32_t walk[kLeafMax + 1]; int wp = 0; walk[wp++] = node;
             while (wp > 0) {
                 const uint32_t b = walk[--wp];
-                if (b >= first_leaf) { const uint32_t src = sorted[b - first_leaf]; perm_out[tri_base + tri_off] = src; tris_out[tri_base + tri_off++] = tris_in[src]; }
+                if (b >= first_leaf) { const uint32_t ref = sorted[b - first_leaf], src = ref_tri ? ref_tri[ref] : ref; perm_out[tri_base + tri_off] = src; tris_out[tri_base + tri_off++] = tris_in[src]; }
                 else { const uint2 ch = children[b]; walk[wp++] = ch.y; walk[wp++] = ch.x; }
             }
         } else {
@@ -447,19 +563,64 @@ __global__ void k_collapse(const WorkItem* __restrict__ items, const uint32_t* _
 
 } // namespace
 
-void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder, int ploc_radius) {
-    out.num_nodes = 0; out.num_tris = 0; out.levels = 0; out.build_ms = 0.f; out.ploc_rounds = 0;
-    if (n == 0) return;
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n_tris, DeviceBvh& out, BvhBuilder builder, int ploc_radius, float split_fraction) {
+    out.num_nodes = 0; out.num_tris = 0; out.src_tris = 0; out.levels = 0; out.build_ms = 0.f; out.ploc_rounds = 0;
+    if (n_tris == 0) return;
     static const bool timing = getenv("LB_BVH_TIMING") != nullptr;
-    auto tick = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(s); static double last = 0; timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; fprintf(stderr, "[bvh %u] %-10s +%.3f ms\n", n, what, last ? now - last : 0.0); last = now; };
+    auto tick = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(s); static double last = 0; timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; fprintf(stderr, "[bvh %u] %-10s +%.3f ms\n", n_tris, what, last ? now - last : 0.0); last = now; };
     tick("enter");
-    cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0, e1, e_split; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1)); LB_CUDA(cudaEventCreate(&e_split));
+    const int B = 256;
+    const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+
+    // ---- references: one per triangle, or several for the triangles early split clipping cuts up (see k_split). Their number decides the
+    //      size of everything below, so this stage runs first, with its own scratch.
+    StreamBuf<float4> tlo, thi, rlo, rhi; StreamBuf<int> cbounds; StreamBuf<uint32_t> ref_tri, split_counts, split_offsets; StreamBuf<unsigned char> cub_tmp;
+    tlo.reserve(n_tris, s); thi.reserve(n_tris, s); cbounds.reserve(6, s);
+    LB_CUDA(cudaEventRecord(e_split, s));
+    LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
+    k_tri_bounds<<<grid_for(n_tris, B), B, 0, s>>>(tris_in, n_tris, tlo.p, thi.p, cbounds.p); LB_LAUNCH_CHECK();
+    uint32_t n = n_tris; const float4 *lo_p = tlo.p, *hi_p = thi.p; const uint32_t* ref_tri_p = nullptr;
+    out.split_cell = 0.f;
+    if (split_fraction > 0.f && n_tris > 1u) {
+        int hb[6];
+        LB_CUDA(cudaMemcpyAsync(hb, cbounds.p, sizeof hb, cudaMemcpyDeviceToHost, s)); LB_CUDA(cudaStreamSynchronize(s));
+        auto of = [](int i) { const int u = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &u, 4); return f; };
+        const float extent = std::max(of(hb[3]) - of(hb[0]), std::max(of(hb[4]) - of(hb[1]), of(hb[5]) - of(hb[2])));
+        if (extent > 0.f && std::isfinite(extent)) {
+            split_counts.reserve(n_tris, s); split_offsets.reserve(n_tris, s);
+            size_t scan_bytes = 0;
+            LB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, split_counts.p, split_offsets.p, (int)n_tris, s));
+            cub_tmp.reserve(scan_bytes, s);
+            SplitParams sp{extent * split_fraction, 1u};
+            uint32_t total = n_tris;
+            for (int attempt = 0; attempt < 10; ++attempt, sp.cell *= 2.f) {         // the references may at most double the leaf arrays
+                k_split<0><<<grid_for(n_tris, B), B, 0, s>>>(tris_in, n_tris, sp, nullptr, split_counts.p, nullptr, nullptr, nullptr); LB_LAUNCH_CHECK();
+                LB_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, scan_bytes, split_counts.p, split_offsets.p, (int)n_tris, s));
+                uint32_t last_off = 0, last_cnt = 0;
+                LB_CUDA(cudaMemcpyAsync(&last_off, split_offsets.p + (n_tris - 1u), 4, cudaMemcpyDeviceToHost, s));
+                LB_CUDA(cudaMemcpyAsync(&last_cnt, split_counts.p + (n_tris - 1u), 4, cudaMemcpyDeviceToHost, s));
+                LB_CUDA(cudaStreamSynchronize(s));
+                total = last_off + last_cnt;
+                if ((uint64_t)total <= 2ull * n_tris) break;
+            }
+            if (total > n_tris && (uint64_t)total <= 2ull * n_tris) {
+                n = total; out.split_cell = sp.cell;
+                rlo.reserve(n, s); rhi.reserve(n, s); ref_tri.reserve(n, s);
+                k_split<1><<<grid_for(n_tris, B), B, 0, s>>>(tris_in, n_tris, sp, split_offsets.p, nullptr, rlo.p, rhi.p, ref_tri.p); LB_LAUNCH_CHECK();
+                LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
+                k_ref_bounds<<<grid_for(n, B), B, 0, s>>>(rlo.p, rhi.p, n, cbounds.p); LB_LAUNCH_CHECK();
+                lo_p = rlo.p; hi_p = rhi.p; ref_tri_p = ref_tri.p;
+            }
+        }
+    }
+    tick("split");
     timespec a0, a1; clock_gettime(CLOCK_MONOTONIC, &a0);
 
     const uint32_t n_binary = 2u * n - 1u;
-    StreamBuf<float4> tlo, thi, nlo, nhi; StreamBuf<int> cbounds; StreamBuf<uint64_t> keys, keys_sorted; StreamBuf<uint32_t> vals, sorted, count, counters;
-    StreamBuf<uint2> children; StreamBuf<WorkItem> items_a, items_b; StreamBuf<unsigned char> cub_tmp;
-    tlo.reserve(n, s); thi.reserve(n, s); nlo.reserve(n_binary, s); nhi.reserve(n_binary, s); count.reserve(n_binary, s); cbounds.reserve(6, s);
+    StreamBuf<float4> nlo, nhi; StreamBuf<uint64_t> keys, keys_sorted; StreamBuf<uint32_t> vals, sorted, count, counters;
+    StreamBuf<uint2> children; StreamBuf<WorkItem> items_a, items_b;
+    nlo.reserve(n_binary, s); nhi.reserve(n_binary, s); count.reserve(n_binary, s);
     keys.reserve(n, s); keys_sorted.reserve(n, s); vals.reserve(n, s); sorted.reserve(n, s); counters.reserve(4, s);
     children.reserve(n, s); items_a.reserve(n, s); items_b.reserve(n, s);
     tick("scratch");
@@ -472,11 +633,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     // process they take 3 - 10 ms of cudaMalloc / pool growth for C2, more than the build itself.
     clock_gettime(CLOCK_MONOTONIC, &a1); out.alloc_ms = (float)((a1.tv_sec - a0.tv_sec) * 1e3 + (a1.tv_nsec - a0.tv_nsec) * 1e-6);
     LB_CUDA(cudaEventRecord(e0, s));
-    const int h_bounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-    LB_CUDA(cudaMemcpyAsync(cbounds.p, h_bounds, sizeof h_bounds, cudaMemcpyHostToDevice, s));
-    const int B = 256;
-    k_tri_bounds<<<grid_for(n, B), B, 0, s>>>(tris_in, n, tlo.p, thi.p, cbounds.p); LB_LAUNCH_CHECK();
-    k_morton<<<grid_for(n, B), B, 0, s>>>(tlo.p, thi.p, n, cbounds.p, keys.p, vals.p); LB_LAUNCH_CHECK();
+    k_morton<<<grid_for(n, B), B, 0, s>>>(lo_p, hi_p, n, cbounds.p, keys.p, vals.p); LB_LAUNCH_CHECK();
     size_t tmp_bytes = 0;
     LB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, vals.p, sorted.p, (int)n, 0, 63, s));
     cub_tmp.reserve(tmp_bytes, s);
@@ -489,7 +646,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         parent.reserve(n_binary, s); flags.reserve(n, s); range.reserve(n, s);
         flags.zero();
         if (n > 1) { k_hierarchy<<<grid_for(n - 1, B), B, 0, s>>>(keys_sorted.p, (int)n, children.p, parent.p, range.p); LB_LAUNCH_CHECK(); }
-        k_refit<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, (int)n, children.p, parent.p, nlo.p, nhi.p, count.p, flags.p); LB_LAUNCH_CHECK();
+        k_refit<<<grid_for(n, B), B, 0, s>>>(sorted.p, lo_p, hi_p, (int)n, children.p, parent.p, nlo.p, nhi.p, count.p, flags.p); LB_LAUNCH_CHECK();
         LB_CUDA(cudaStreamSynchronize(s));                  // the temporaries above are released here
     } else {
         // PLOC: the cluster arrays ping-pong through a flag / exclusive-scan / scatter compaction every round
@@ -505,7 +662,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
         // first version read the count back after every round (~55 rounds x 2 hierarchies x ~100 us: 12 of the 16 ms of a C2 build).
         const uint32_t h_m[4] = {n, 0u, 0u, 0u};
         LB_CUDA(cudaMemcpyAsync(m_dev.p, h_m, sizeof h_m, cudaMemcpyHostToDevice, s));
-        k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, tlo.p, thi.p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
+        k_ploc_init<<<grid_for(n, B), B, 0, s>>>(sorted.p, lo_p, hi_p, n, cl[0].p, clo[0].p, chi[0].p, nlo.p, nhi.p, count.p); LB_LAUNCH_CHECK();
         uint32_t m = n; int cur = 0; uint32_t slot = 0u;
         constexpr int kRoundsPerBatch = 8;
         while (m > 1u) {
@@ -558,7 +715,7 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     uint32_t launched = 0;
     for (;;) {
         for (uint32_t b = 0; b < kLevelsPerBatch && launched < kMaxLevels; ++b, ++launched) {
-            k_collapse<<<collapse_grid, 128, 0, s>>>(cur, level_items.p + launched, nxt, level_items.p + launched + 1u, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, tris_in,
+            k_collapse<<<collapse_grid, 128, 0, s>>>(cur, level_items.p + launched, nxt, level_items.p + launched + 1u, counters.p, (int)n, children.p, count.p, nlo.p, nhi.p, sorted.p, ref_tri_p, tris_in,
                                                      out.nodes.p, out.tris.p, out.perm.p);
             LB_LAUNCH_CHECK();
             std::swap(cur, nxt);
@@ -577,19 +734,22 @@ void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out
     if (out.num_tris == n) { k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(out.tris.p, n); LB_LAUNCH_CHECK(); }
     LB_CUDA(cudaEventRecord(e1, s)); LB_CUDA(cudaEventSynchronize(e1));
     LB_CUDA(cudaEventElapsedTime(&out.build_ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    out.src_tris = n_tris;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e_split);
     tick("finish");
     if (out.num_tris != n) throw CudaError("bvh_build: triangle count mismatch after collapse");
     if (level_first != out.num_nodes) throw CudaError("bvh_build: level ranges do not cover the nodes");
 }
 
 void bvh_refit(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& bvh) {
-    if (n == 0 || bvh.num_tris != n || bvh.level_start.size() != (size_t)bvh.levels + 1u) throw CudaError("bvh_refit: the hierarchy was not built from this many triangles");
+    if (n == 0 || bvh.src_tris != n || bvh.level_start.size() != (size_t)bvh.levels + 1u) throw CudaError("bvh_refit: the hierarchy was not built from this many triangles");
     cudaEvent_t e0, e1; LB_CUDA(cudaEventCreate(&e0)); LB_CUDA(cudaEventCreate(&e1));
     LB_CUDA(cudaEventRecord(e0, s));
     const int B = 256;
-    k_regather<<<grid_for(n, B), B, 0, s>>>(tris_in, bvh.perm.p, n, bvh.tris.p); LB_LAUNCH_CHECK();
-    k_rotate_tris<<<grid_for(n, B), B, 0, s>>>(bvh.tris.p, n); LB_LAUNCH_CHECK();
+    const uint32_t nl = bvh.num_tris;                       // leaf entries (>= n when triangles were split into references: a refitted reference
+                                                            // gets its whole triangle's box — correct, looser than the clipped box of the build)
+    k_regather<<<grid_for(nl, B), B, 0, s>>>(tris_in, bvh.perm.p, nl, bvh.tris.p); LB_LAUNCH_CHECK();
+    k_rotate_tris<<<grid_for(nl, B), B, 0, s>>>(bvh.tris.p, nl); LB_LAUNCH_CHECK();
     for (int level = (int)bvh.levels - 1; level >= 0; --level) {
         const uint32_t first = bvh.level_start[level], count = bvh.level_start[level + 1] - first;
         if (!count) continue;

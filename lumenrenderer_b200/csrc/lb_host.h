@@ -68,7 +68,8 @@ struct DeviceBvh {
     // what a refit needs (bvh_refit): leaf slot -> index of the source triangle, the first node of every level (nodes are created level by
     // level, so a level is a contiguous range), and a full-precision box per node to hand up to its parent
     DevBuf<uint32_t> perm; DevBuf<float4> box_lo, box_hi; std::vector<uint32_t> level_start;
-    uint32_t num_nodes = 0, num_tris = 0, levels = 0, ploc_rounds = 0, refits = 0;
+    uint32_t num_nodes = 0, num_tris = 0 /* leaf entries: triangle references */, src_tris = 0 /* triangles it was built from */, levels = 0, ploc_rounds = 0, refits = 0;
+    float split_cell = 0.f;     // grid cell of the early split clipping (0: no triangle was split)
     float build_ms = 0.f, alloc_ms = 0.f, refit_ms = 0.f;
     BvhView view(uint32_t* overflow = nullptr) const { return BvhView{nodes.p, tris.p, num_tris, overflow}; }
     size_t bytes() const { return (size_t)num_nodes * sizeof(Bvh8Node) + 3 * (size_t)num_tris * sizeof(DevTri); }      // three rotated triangle copies
@@ -79,7 +80,7 @@ struct DeviceBvh {
 // tris_in: world-space triangles in any order; the builder writes its own leaf-ordered copy into out.tris.
 enum class BvhBuilder { PLOC, LBVH };
 // ploc_radius: neighbour search window of PLOC in Morton order (16, 64 or 128)
-void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC, int ploc_radius = 16);
+void bvh_build(cudaStream_t s, const DevTri* tris_in, uint32_t n, DeviceBvh& out, BvhBuilder builder = BvhBuilder::PLOC, int ploc_radius = 16, float split_fraction = 0.f);
 
 // Same topology, new triangle positions (instances moved): the leaf-ordered triangle copies are re-gathered from `tris_in` (the same source
 // order the hierarchy was built from) and every node's child boxes are recomputed bottom-up, level by level — no sort, no clustering, no

@@ -275,6 +275,38 @@ def test_dynamic_scene_moving_camera_and_instance(oracle):
     g.close(); c.close()
 
 
+def test_split_references_return_the_hits_of_whole_triangles(gpu, monkeypatch):
+    """LB_BVH_SPLIT=k (early split clipping: large triangles enter the build as several clipped references, csrc/lb_bvh.cu k_split): hit
+    records of 200 K random rays — closest-hit and any-hit — are bit-identical to the hierarchy over whole triangles, on the Cornell box (12
+    wall triangles that span the scene: every one is cut into hundreds of references) and on the material gallery; a refit of the split
+    hierarchy (a reference then gets its whole triangle's box) keeps them."""
+    rng = np.random.default_rng(4)
+    o = rng.uniform(-1, 1, (200_000, 3)).astype(np.float32)
+    d = rng.normal(size=(200_000, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:1000] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 1000)] * rng.choice([-1.0, 1.0], (1000, 1)).astype(np.float32)      # along the cutting planes
+    tmax = (rng.random(200_000) * 4).astype(np.float32)
+    st = lr.Settings(width=64, height=48, depth=2, restir=True)
+    for scene_fn in (scenes.cornell_box, scenes.material_gallery):
+        out = []
+        for split in ("0", "16", "64"):
+            monkeypatch.setenv("LB_BVH_SPLIT", split)
+            with api.Renderer(gpu, st) as r:
+                sc = scene_fn()
+                r.load_scene(sc); r.render_frames(1)
+                fc = r.frame_counters(); assert fc["stack_overflows"] == 0
+                out.append((r.trace_closest(o, d), r.trace_any(o, d, tmax), r.read_hdr(), fc["bvh_bytes"]))
+                if split == "64":
+                    t0 = sc.instances[0].get("transform")            # the same transform again: a transform-only change, nothing moves
+                    r.set_instance_transform(0, np.eye(4, dtype=np.float32) if t0 is None else np.asarray(t0, np.float32).reshape(4, 4)); r.render_frames(1)
+                    assert r.frame_counters()["bvh_refits"] == 1
+                    out.append((r.trace_closest(o, d), r.trace_any(o, d, tmax), None, 0))
+        assert out[1][3] > out[0][3]                                 # references were added
+        for other in out[1:]:
+            assert np.array_equal(out[0][0], other[0]) and np.array_equal(out[0][1], other[1])
+        assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][2], out[2][2])
+        assert (out[0][0]["t"] > 0).mean() > 0.3
+
+
 def test_refitted_hierarchy_returns_the_hits_of_a_rebuilt_one(gpu):
     """bvh_refit (instances moved -> same topology, new boxes) against a full rebuild of the same final scene: hit records of 200 K random
     rays bit-identical, closest-hit and any-hit; instances are moved far (boxes that were disjoint at build time now overlap) and back."""
