@@ -331,7 +331,7 @@ struct Renderer {
             // LB_BVH_SPLIT=k: early split clipping on a grid of (scene extent / k) for triangles larger than a cell (0: off)
             const char* sp = getenv("LB_BVH_SPLIT");
             const float split = sp ? (atof(sp) > 0.0 ? 1.f / (float)atof(sp) : 0.f) : 0.f;
-            bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC, 16, split);
+            bvh_build(stream, d_flat.p, total_tris, bvh, (e && !strcmp(e, "lbvh")) ? BvhBuilder::LBVH : BvhBuilder::PLOC, getenv("LB_PLOC_RADIUS") ? atoi(getenv("LB_PLOC_RADIUS")) : 16, split);
             // LB_BVH_ANYHIT=same: one hierarchy for every ray (halves the build); default: a second PLOC hierarchy with a 128-wide search window
             const char* a = getenv("LB_BVH_ANYHIT");
             dual_bvh = !(a && !strcmp(a, "same")) && total_tris > 1u;
@@ -823,6 +823,9 @@ LB_API int lb_frame_stats(LbRenderer r, const char** names, float* micros, uint3
 static int frame_counters_locked(lb::Renderer* R, uint64_t* v, uint32_t cap, uint32_t* count) {     // caller holds R->mu
 #ifdef LB_RIS_STATS
     cudaStreamSynchronize(R->stream); lb::dump_ris_stats();
+#endif
+#ifdef LB_TRACE_STATS
+    cudaDeviceSynchronize(); lb::dump_trace_stats_wavefront(); lb::dump_trace_stats_restir();
 #endif
     unsigned long long s[kNumStats]; uint32_t overflows = 0;
     LB_CUDA(cudaMemcpyAsync(s, R->d_stats.p, sizeof s, cudaMemcpyDeviceToHost, R->stream));

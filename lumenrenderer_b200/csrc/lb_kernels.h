@@ -110,4 +110,7 @@ void build_lights(const LaunchCfg&, const SceneView&, const ScenePrepIn&, const 
 #ifdef LB_RIS_STATS
 void dump_ris_stats();      // debug build: prints and clears the survivor statistics of k_ris
 #endif
+#ifdef LB_TRACE_STATS
+void dump_trace_stats_wavefront(); void dump_trace_stats_restir();      // debug build: print and clear the traversal statistics
+#endif
 } // namespace lb

@@ -821,4 +821,12 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
     }
 }
 
+#ifdef LB_TRACE_STATS
+void dump_trace_stats_restir() {
+    unsigned long long h[8]; cudaMemcpyFromSymbol(h, g_trace_stats, sizeof h);
+    for (int a = 0; a < 2; ++a) if (h[4 * a + 2]) fprintf(stderr, "TRACE stats [restir %s]: rays %llu, node visits / ray %.2f, triangle tests / ray %.2f (%.2f pass the edge test)\n", a ? "any-hit" : "closest",
+        h[4 * a + 2], (double)h[4 * a] / h[4 * a + 2], (double)h[4 * a + 1] / h[4 * a + 2], (double)h[4 * a + 3] / h[4 * a + 2]);
+    memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_trace_stats, h, sizeof h);
+}
+#endif
 } // namespace lb

@@ -77,6 +77,17 @@ LB_D bool tri_test(const float3& org, const RayShear& s, const float3& p0, const
 
 struct HitInfo { uint32_t inst, prim; float u, v, t; };
 
+#ifdef LB_TRACE_STATS
+// debug build: node visits / triangle tests / rays / warp rounds per translation unit (each unit that includes this header has its own copy;
+// lb::dump_trace_stats_<unit> prints and clears it)
+static __device__ unsigned long long g_trace_stats[8];
+#define LB_TSTAT(k) (++tstat[k])
+#define LB_TSTAT_RAY(tr) (++(tr).tstat[2])
+#else
+#define LB_TSTAT(k) ((void)0)
+#define LB_TSTAT_RAY(tr) ((void)0)
+#endif
+
 constexpr int kTraceStack = 64;
 
 LB_D float safe_rcp(float d) { return tdiv(1.0f, fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
@@ -102,6 +113,9 @@ struct Tracer {
     int sp;
     bool found; uint32_t bi, bp; float bu, bv;
     bool dropped;               // set by push() on overflow; owned by the driver (not reset per ray)
+#ifdef LB_TRACE_STATS
+    uint32_t tstat[4] = {0u, 0u, 0u, 0u};      // node steps, triangle tests, rays, triangle tests that passed the edge test
+#endif
     uint2* stack;               // kTraceStack entries of thread-local memory owned by the driver (kept out of this struct so that the
                                 // scalar state above is promoted to registers)
 
@@ -136,6 +150,7 @@ struct Tracer {
 
     // visit the nearest un-visited hit child of the current node group: fetch its 80-byte node, slab-test the 8 children
     LB_D void node_step(const BvhView& bvh) {
+        LB_TSTAT(0);
         const uint32_t hits_imask = cur.y;
         const uint32_t child_bit = 31u - (uint32_t)__clz(hits_imask);
         const uint32_t child_base = cur.x;
@@ -199,12 +214,14 @@ struct Tracer {
     // test ONE pending triangle of the current triangle group. ANY: true = occluded (stop).
     template <bool ANY>
     LB_D bool tri_step(const BvhView& bvh) {
+        LB_TSTAT(1);
         const uint32_t k = (uint32_t)__ffs(cur.y) - 1u;
         cur.y &= cur.y - 1u;
         const float4* tp = reinterpret_cast<const float4*>(bvh.tris + (tri_off + cur.x + k));
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
         float t, u, v;
         if (!tri_test(orot, sh, f3(v0), f3(v1), f3(v2), t, u, v)) return false;
+        LB_TSTAT(3);
         if (!(t > tmin)) return false;
         if (ANY) return t < best;
         const uint32_t ti = __float_as_uint(v0.w), tpi = __float_as_uint(v1.w);
@@ -260,7 +277,7 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
                 item = base + (uint32_t)__popc(idle & lt_mask);
                 if (item < n) {
                     float3 o, d; float tmin, tmax;
-                    if (job.load(item, o, d, tmin, tmax)) { tr.begin(bvh, o, d, tmin, tmax); live = true; }
+                    if (job.load(item, o, d, tmin, tmax)) { tr.begin(bvh, o, d, tmin, tmax); live = true; LB_TSTAT_RAY(tr); }
                     else job.done(item, false, tr);
                 }
             }
@@ -288,6 +305,9 @@ LB_D void trace_queue(const BvhView& bvh, uint32_t n, uint32_t* ticket, Job& job
     }
     if (fin) job.done(item, fin_hit, tr);
     if (tr.dropped && bvh.overflow) atomicAdd(bvh.overflow, 1u);
+#ifdef LB_TRACE_STATS
+    for (int k = 0; k < 4; ++k) { const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, tr.tstat[k]); if (lane == 0u && v) atomicAdd(&g_trace_stats[(ANY ? 4 : 0) + k], (unsigned long long)v); }
+#endif
 }
 
 } // namespace lb

@@ -329,4 +329,12 @@ void launch_gbuffer(const LaunchCfg& cfg, const float4* surf, uint32_t npix, flo
 void launch_resolve(const LaunchCfg& cfg, const FrameView& fv, float inv_frames) {
     k_resolve<<<persistent_grid(cfg, 8), kBlock, 0, cfg.stream>>>(fv, inv_frames); LB_LAUNCH_CHECK();
 }
+#ifdef LB_TRACE_STATS
+void dump_trace_stats_wavefront() {
+    unsigned long long h[8]; cudaMemcpyFromSymbol(h, g_trace_stats, sizeof h);
+    for (int a = 0; a < 2; ++a) if (h[4 * a + 2]) fprintf(stderr, "TRACE stats [wavefront %s]: rays %llu, node visits / ray %.2f, triangle tests / ray %.2f (%.2f pass the edge test)\n", a ? "any-hit" : "closest",
+        h[4 * a + 2], (double)h[4 * a] / h[4 * a + 2], (double)h[4 * a + 1] / h[4 * a + 2], (double)h[4 * a + 3] / h[4 * a + 2]);
+    memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_trace_stats, h, sizeof h);
+}
+#endif
 } // namespace lb
