@@ -111,12 +111,12 @@ struct Renderer {
             return (EncodeFn)p;
         }();
         if (!encode) throw CudaError("LB_SPATIAL_TMA=1: the driver does not export cuTensorMapEncodeTiled");
-        // the plane as a 2-D tensor of 8-byte elements (two per 16-byte record): a box row is then ONE contiguous run (92 records = 184 elements
-        // = 1 472 bytes; the innermost box extent is limited to 256 ELEMENTS, and 16-byte elements do not exist)
-        const cuuint64_t dims[2] = {(cuuint64_t)st.width * 2, st.height}, strides[1] = {(cuuint64_t)st.width * 16};
-        const cuuint32_t box[2] = {(32 + 2 * 30) * 2, 16 + 2 * 30}, estr[2] = {1, 1};
+        // plane 1 = the second float4 of every 32-byte record of plane pair 0 (lb_device.cuh): a 3-D tensor {2 eight-byte elements, W records
+        // with a 32-byte stride, H rows}, based 16 bytes into the buffer
+        const cuuint64_t dims[3] = {2, st.width, st.height}, strides[2] = {32, (cuuint64_t)st.width * 32};
+        const cuuint32_t box[3] = {2, 32 + 2 * 30, 16 + 2 * 30}, estr[3] = {1, 1, 1};
         for (int k = 0; k < 2; ++k)
-            if (encode(&tmap_geom[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_surf[k].p + npix(), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            if (encode(&tmap_geom[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d_surf[k].p + 1, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 throw CudaError("LB_SPATIAL_TMA=1: cuTensorMapEncodeTiled rejected the descriptor of surface plane 1");
         have_tmap = true;

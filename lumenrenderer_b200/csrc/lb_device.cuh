@@ -183,52 +183,65 @@ struct Surface {
 struct LightSample { float3 radiance, normal, position, contribution; float area, pdf; };
 struct Reservoir { float weight_sum, weight; int count; LightSample s; };
 
-LB_D void surface_store(float4* planes, size_t n, size_t i, const Surface& s) {
-    planes[0 * n + i] = f4(s.pos, __uint_as_float(s.flags));
-    planes[1 * n + i] = f4(s.normal, s.flags ? __uint_as_float(__float_as_uint(s.t) | 0x80000000u) : s.t);
-    planes[2 * n + i] = f4(s.tangent, 0.f);
-    planes[3 * n + i] = f4(s.incoming, 0.f);
-    planes[4 * n + i] = f4(s.transport, 0.f);
-    planes[5 * n + i] = s.mat.color;
-    planes[6 * n + i] = s.mat.transmittance;
-    planes[7 * n + i] = s.mat.tint;
-    planes[8 * n + i] = make_float4(__uint_as_float(s.mat.params.x), __uint_as_float(s.mat.params.y), __uint_as_float(s.mat.params.z), __uint_as_float(s.mat.params.w));
+// PHYSICAL LAYOUT of the surface and reservoir planes: planes are stored in PAIRS — {0,1} {2,3} {5,6} {7,8} of a surface, {0,1} {2,3} of a
+// reservoir — as 32-byte records (the two float4 of ONE pixel side by side, pair k of pixel i at float4 index k * 2n + 2i), the odd plane
+// (surface 4 = transport, reservoir 4 = unshadowed contribution) alone at the end. A pair is read and written with one 256-bit access
+// (LDG.E.256 / STG.E.256, new with Blackwell). Why: the reuse kernels gather these records per lane from random neighbours; a 16-byte gather
+// pulls a 32-byte sector and uses half of it, and the spatial pass turned out to be bound by the NUMBER of such requests (33 per pixel,
+// profiles/r02_a_ab.md). Paired, a neighbour's reservoir is 2 requests instead of 4, its shading record 4 instead of 8, every sector
+// fully used; the streaming kernels lose nothing (a warp's 32 pair reads are 1 KB contiguous).
+struct __align__(32) Float8 { float4 a, b; };
+LB_D Float8 ld2(const float4* p) { return *reinterpret_cast<const Float8*>(p); }
+LB_D void st2(float4* p, const float4& a, const float4& b) { Float8 v; v.a = a; v.b = b; *reinterpret_cast<Float8*>(p) = v; }
+LB_D size_t surf_pair(size_t n, int pair, size_t i) { return (size_t)pair * 2u * n + 2u * i; }     // pairs 0..3 = planes {0,1} {2,3} {5,6} {7,8}
+LB_D size_t surf_at(size_t n, int plane, size_t i) {
+    if (plane == 4) return 8u * n + i;
+    const int q = plane < 4 ? plane : plane - 1;
+    return (size_t)(q >> 1) * 2u * n + 2u * i + (size_t)(q & 1);
 }
-LB_D uint32_t surface_flags(const float4* planes, size_t n, size_t i) { return __float_as_uint(planes[0 * n + i].w); }
+LB_D size_t res_pair(size_t n, int pair, size_t i) { return (size_t)pair * 2u * n + 2u * i; }      // pairs 0..1 = planes {0,1} {2,3}
+LB_D size_t res_at(size_t n, int plane, size_t i) { return plane == 4 ? 4u * n + i : (size_t)(plane >> 1) * 2u * n + 2u * i + (size_t)(plane & 1); }
+
+LB_D void surface_store(float4* planes, size_t n, size_t i, const Surface& s) {
+    st2(planes + surf_pair(n, 0, i), f4(s.pos, __uint_as_float(s.flags)), f4(s.normal, s.flags ? __uint_as_float(__float_as_uint(s.t) | 0x80000000u) : s.t));
+    st2(planes + surf_pair(n, 1, i), f4(s.tangent, 0.f), f4(s.incoming, 0.f));
+    planes[surf_at(n, 4, i)] = f4(s.transport, 0.f);
+    st2(planes + surf_pair(n, 2, i), s.mat.color, s.mat.transmittance);
+    st2(planes + surf_pair(n, 3, i), s.mat.tint, make_float4(__uint_as_float(s.mat.params.x), __uint_as_float(s.mat.params.y), __uint_as_float(s.mat.params.z), __uint_as_float(s.mat.params.w)));
+}
+LB_D uint32_t surface_flags(const float4* planes, size_t n, size_t i) { return __float_as_uint(planes[surf_at(n, 0, i)].w); }
 // the similarity record of a pixel: normal, depth, flagged — one 16-byte load
 struct SurfGeom { float3 normal; float t; bool flagged; };
 LB_D SurfGeom surf_geom_unpack(const float4& b) {
     SurfGeom g; g.normal = f3(b); g.flagged = (__float_as_uint(b.w) >> 31) != 0u; g.t = fabsf(b.w);
     return g;
 }
-LB_D SurfGeom surface_geom(const float4* planes, size_t n, size_t i) { return surf_geom_unpack(planes[1 * n + i]); }
-// everything a BSDF evaluation at the pixel needs (no path throughput)
+LB_D SurfGeom surface_geom(const float4* planes, size_t n, size_t i) { return surf_geom_unpack(planes[surf_at(n, 1, i)]); }
+// everything a BSDF evaluation at the pixel needs (no path throughput): four 32-byte reads
 LB_D void surface_load_shading(const float4* planes, size_t n, size_t i, Surface& s) {
-    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
-    s.pos = f3(a); s.flags = __float_as_uint(a.w); s.normal = f3(b); s.t = fabsf(b.w);
-    s.tangent = f3(planes[2 * n + i]); s.incoming = f3(planes[3 * n + i]);
-    s.mat.color = planes[5 * n + i]; s.mat.transmittance = planes[6 * n + i]; s.mat.tint = planes[7 * n + i];
-    const float4 p = planes[8 * n + i];
+    const Float8 p01 = ld2(planes + surf_pair(n, 0, i)), p23 = ld2(planes + surf_pair(n, 1, i)), p56 = ld2(planes + surf_pair(n, 2, i)), p78 = ld2(planes + surf_pair(n, 3, i));
+    s.pos = f3(p01.a); s.flags = __float_as_uint(p01.a.w); s.normal = f3(p01.b); s.t = fabsf(p01.b.w);
+    s.tangent = f3(p23.a); s.incoming = f3(p23.b);
+    s.mat.color = p56.a; s.mat.transmittance = p56.b; s.mat.tint = p78.a;
+    const float4 p = p78.b;
     s.mat.params = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.w));
     s.mat.emissive = make_float4(0.f, 0.f, 0.f, 0.f);
     s.transport = f3(0.f);
 }
 LB_D void surface_load(const float4* planes, size_t n, size_t i, Surface& s) {
     surface_load_shading(planes, n, i, s);
-    s.transport = f3(planes[4 * n + i]);
+    s.transport = f3(planes[surf_at(n, 4, i)]);
 }
 LB_D void reservoir_store(float4* planes, size_t n, size_t i, const Reservoir& r) {
-    planes[0 * n + i] = make_float4(r.weight_sum, r.weight, __int_as_float(r.count), r.s.pdf);
-    planes[1 * n + i] = f4(r.s.position, r.s.area);
-    planes[2 * n + i] = f4(r.s.normal, 0.f);
-    planes[3 * n + i] = f4(r.s.radiance, 0.f);
-    planes[4 * n + i] = f4(r.s.contribution, 0.f);
+    st2(planes + res_pair(n, 0, i), make_float4(r.weight_sum, r.weight, __int_as_float(r.count), r.s.pdf), f4(r.s.position, r.s.area));
+    st2(planes + res_pair(n, 1, i), f4(r.s.normal, 0.f), f4(r.s.radiance, 0.f));
+    planes[res_at(n, 4, i)] = f4(r.s.contribution, 0.f);
 }
 LB_D void reservoir_load(const float4* planes, size_t n, size_t i, Reservoir& r) {
-    const float4 a = planes[0 * n + i], b = planes[1 * n + i];
-    r.weight_sum = a.x; r.weight = a.y; r.count = __float_as_int(a.z); r.s.pdf = a.w;
-    r.s.position = f3(b); r.s.area = b.w;
-    r.s.normal = f3(planes[2 * n + i]); r.s.radiance = f3(planes[3 * n + i]); r.s.contribution = f3(planes[4 * n + i]);
+    const Float8 ab = ld2(planes + res_pair(n, 0, i)), cd = ld2(planes + res_pair(n, 1, i));
+    r.weight_sum = ab.a.x; r.weight = ab.a.y; r.count = __float_as_int(ab.a.z); r.s.pdf = ab.a.w;
+    r.s.position = f3(ab.b); r.s.area = ab.b.w;
+    r.s.normal = f3(cd.a); r.s.radiance = f3(cd.b); r.s.contribution = f3(planes[res_at(n, 4, i)]);
 }
 LB_D Reservoir reservoir_zero() {
     Reservoir r; r.weight_sum = 0.f; r.weight = 0.f; r.count = 0;

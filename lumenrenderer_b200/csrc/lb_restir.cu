@@ -347,9 +347,9 @@ __global__ void __launch_bounds__(kRisBlock, 1) k_ris(FrameView fv, SceneView sc
                 }
                 float3 ppos = f3(0.f), pnormal = f3(0.f);
                 if (i != kNone) {
-                    const float4 a = fv.surf_cur[i];
-                    if (__float_as_uint(a.w)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); i = kNone; }
-                    else { ppos = f3(a); pnormal = f3(fv.surf_cur[np + i]); }
+                    const Float8 s01 = ld2(fv.surf_cur + surf_pair(np, 0, i));      // position | flags, normal | depth
+                    if (__float_as_uint(s01.a.w)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); i = kNone; }
+                    else { ppos = f3(s01.a); pnormal = f3(s01.b); }
                 }
                 uint32_t mask = 0u;
                 if (i != kNone) {
@@ -428,19 +428,20 @@ struct VisibilityJob {
     float4 r0;                                                  // lane state between load and done: weightSum, weight, count, pdf
     LB_D bool load(uint32_t i, float3& o, float3& d, float& t0, float& t1) {
         const size_t np = fv.npix;
-        r0 = fv.res_cur[i];
-        const float4 sp = fv.surf_cur[i];                       // position, flags
+        const Float8 r01 = ld2(fv.res_cur + res_pair(np, 0, i));        // weights | sample position
+        r0 = r01.a;
+        const float4 sp = fv.surf_cur[surf_at(np, 0, i)];       // position, flags
         if (__float_as_uint(sp.w) || !(r0.y > 0.f)) return false;
         o = f3(sp);
-        d = f3(fv.res_cur[np + i]) - o; const float l = length(d); d /= l;
+        d = f3(r01.b) - o; const float l = length(d); d /= l;
         t0 = 0.1f; t1 = l - 0.05f;
         ++traced;
         return true;
     }
     LB_D void done(uint32_t i, bool occluded, const Tracer&) {
-        if (occluded) { r0.y = 0.f; fv.res_cur[i] = r0; return; }
+        if (occluded) { r0.y = 0.f; fv.res_cur[res_at(fv.npix, 0, i)] = r0; return; }
         if (r0.y > 0.f) {
-            const float3 c = f3(fv.res_cur[4 * (size_t)fv.npix + i]) * (r0.y / shaded);
+            const float3 c = f3(fv.res_cur[res_at(fv.npix, 4, i)]) * (r0.y / shaded);
             float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
         }
     }
@@ -486,10 +487,11 @@ __global__ void __launch_bounds__(kBlock) k_vis_bin(FrameView fv, float4* __rest
             bin[k] = 0xFFFFFFFFu;
             if (x < fv.width && y < fv.height) {
                 const uint32_t i = y * fv.width + x;
-                const float4 r0 = fv.res_cur[i], sp = fv.surf_cur[i];
+                const Float8 r01 = ld2(fv.res_cur + res_pair(np, 0, i));
+                const float4 r0 = r01.a, sp = fv.surf_cur[surf_at(np, 0, i)];
                 if (!__float_as_uint(sp.w) && r0.y > 0.f) {
                     const float3 o = f3(sp);
-                    float3 d = f3(fv.res_cur[np + i]) - o; const float l = length(d); d /= l;
+                    float3 d = f3(r01.b) - o; const float l = length(d); d /= l;
                     o4[k] = f4(o, l - 0.05f); d4[k] = f4(d, __uint_as_float(i));
                     bin[k] = direction_bin(d);
                     atomicAdd(&s_hist[bin[k]], 1u);
@@ -535,9 +537,9 @@ struct SortedVisibilityJob {
         return true;
     }
     LB_D void done(uint32_t, bool occluded, const Tracer&) {
-        float* weight = reinterpret_cast<float*>(fv.res_cur + pixel) + 1;
+        float* weight = reinterpret_cast<float*>(fv.res_cur + res_at(fv.npix, 0, pixel)) + 1;
         if (occluded) { *weight = 0.f; return; }
-        const float3 c = f3(fv.res_cur[4 * (size_t)fv.npix + pixel]) * (*weight / shaded);
+        const float3 c = f3(fv.res_cur[res_at(fv.npix, 4, pixel)]) * (*weight / shaded);
         float4 o = fv.channels[pixel]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[pixel] = o;
     }
 };
@@ -584,7 +586,8 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView
 // what spatial reuse reads of a neighbour's reservoir: 4 of its 5 planes (the stored contribution is re-evaluated)
 struct ResProbe { float4 a, b, c, d; };
 LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i) {
-    ResProbe p; p.a = planes[i]; p.b = planes[n + i]; p.c = planes[2 * n + i]; p.d = planes[3 * n + i];
+    const Float8 ab = ld2(planes + res_pair(n, 0, i)), cd = ld2(planes + res_pair(n, 1, i));      // two 32-byte requests
+    ResProbe p; p.a = ab.a; p.b = ab.b; p.c = cd.a; p.d = cd.b;
     return p;
 }
 
@@ -634,7 +637,7 @@ LB_D void spatial_merge(const FrameView& fv, const float4* __restrict__ in, floa
             LightSample q; q.position = f3(cur.b); q.area = cur.b.w; q.normal = f3(cur.c); q.radiance = f3(cur.d); q.pdf = cur.a.w;
             // a geometrically rejected sample keeps its stored contribution, but it can only be selected when the acceptance draw is
             // exactly 0, i.e. for the all-zero xorshift state: only then is plane 4 fetched
-            q.contribution = degenerate ? f3(in[4 * np + nb[k]]) : f3(0.f);
+            q.contribution = degenerate ? f3(in[res_at(np, 4, nb[k])]) : f3(0.f);
             const int qcount = __float_as_int(cur.a.z); const float qweight = cur.a.y;
             LightSample rs; resample(q, p0.pos, p0.normal, ctx, rs);
             reservoir_update(acc, rs, (float)qcount * qweight * rs.pdf, seed);   // kernel-wide seed by value (hazard 14)
@@ -646,7 +649,7 @@ LB_D void spatial_merge(const FrameView& fv, const float4* __restrict__ in, floa
         else {
             // the unbiased branch, ReSTIRKernels.cu:905-970: the selected sample re-evaluated at every accepted neighbour; the reference adds
             // the sample count of the OUTPUT buffer's stale reservoir of this pixel (a_ReservoirsOut[index].sampleCount, :951) — as written
-            const int stale = __float_as_int(out[i].z);
+            const int stale = __float_as_int(out[res_at(np, 0, i)].z);
             int correction = 0;
 #pragma unroll 1
             for (int k = 0; k < count; ++k) {
@@ -660,8 +663,8 @@ LB_D void spatial_merge(const FrameView& fv, const float4* __restrict__ in, floa
         }
         reservoir_store(out, np, i, acc);
     } else {
-        const float4 r0 = out[i];                                   // Reservoir::Reset keeps the stored sample
-        out[i] = make_float4(0.f, 0.f, __int_as_float(0), r0.w);
+        const float4 r0 = out[res_at(np, 0, i)];                    // Reservoir::Reset keeps the stored sample
+        out[res_at(np, 0, i)] = make_float4(0.f, 0.f, __int_as_float(0), r0.w);
     }
 }
 
@@ -675,8 +678,8 @@ LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, floa
 template <bool UNBIASED>
 __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
     const TileWalk tw(fv);
-    const float4* __restrict__ geom = fv.surf_cur + fv.npix;          // plane 1: normal, signed depth
-    auto geom_at = [geom](int, int, uint32_t index) { return geom[index]; };
+    const float4* __restrict__ geom = fv.surf_cur + 1;                // plane 1 (normal, signed depth): the second half of pair 0
+    auto geom_at = [geom](int, int, uint32_t index) { return geom[2u * (size_t)index]; };
     for (uint32_t item = tw.next(ticket); item < tw.nitems; item = tw.next(ticket)) {
         int x, y;
         if (!tw.pixel(fv, item, x, y)) continue;
@@ -689,9 +692,9 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView 
 // waits for its gathers, not for issue slots, and a regrouped warp gathers from 32 rows instead of one. profiles/r02_a_ab.md.)
 // ---- the same pass with the neighbourhood's similarity records staged in shared memory by the TMA unit (north_star item 3).
 // A block owns a 32x16-pixel tile at a time; every neighbour a pixel of the tile can draw lies within +-30 pixels, so ONE tensor copy
-// (cp.async.bulk.tensor.2d over surface plane 1 seen as rows of 8-byte elements: a box of 184 x 76 = 92 x 76 records = 111 872 bytes, each box
-// row one contiguous 1 472-byte run, zero-filled outside the image) brings in everything the five similarity probes of all 512 pixels can
-// touch; the probes — the first dependent step of every pixel — are then shared-memory reads (29 cycles) instead of L2 / DRAM gathers.
+// (cp.async.bulk.tensor.3d over surface plane 1 — the second half of the 32-byte records of plane pair 0, so a tensor of {2 eight-byte
+// elements, W records 32 bytes apart, H rows}: a box of 2 x 92 x 76 = 111 872 bytes, zero-filled outside the image) brings in everything the
+// five similarity probes of all 512 pixels can touch; the probes — the first dependent step of every pixel — are then shared-memory reads (29 cycles) instead of L2 / DRAM gathers.
 // One block of 16 warps per SM with TWO tile buffers: while the warps work on one tile (a row each), the TMA unit fills the other with the
 // next tile the block drew from the ticket. The reservoirs of the ACCEPTED neighbours (4 planes) and the surface of the first one (8 planes)
 // do not fit beside the tiles and stay global gathers. (The first version — a 3-D box with a 16-byte innermost extent, one buffer, two
@@ -709,9 +712,9 @@ LB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier
 LB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-LB_D void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+LB_D void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __global__ void __launch_bounds__(kSpBlock, 1) k_spatial_tma(FrameView fv, const __grid_constant__ CUtensorMap tmap, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(kSpBlock, 1) k_spatial_tma(FrameView fv, const
     auto fetch = [&](int b) {
         const uint32_t t = atomicAdd(ticket, 1u);
         s_tile[b] = t;
-        if (t < ntiles) { int x0, y0; origin(t, x0, y0); mbar_expect_tx(&bar[b], kSpTileBytes); tma_load_2d(tiles[b], &tmap, &bar[b], (x0 - kSpHalo) * 2, y0 - kSpHalo); }
+        if (t < ntiles) { int x0, y0; origin(t, x0, y0); mbar_expect_tx(&bar[b], kSpTileBytes); tma_load_3d(tiles[b], &tmap, &bar[b], 0, x0 - kSpHalo, y0 - kSpHalo); }
     };
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1u); mbar_init(&bar[1], 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); fetch(0); }
     __syncthreads();

@@ -284,14 +284,14 @@ __global__ void __launch_bounds__(kBlock) k_gbuffer(const float4* __restrict__ s
     const uint32_t stride = gridDim.x * blockDim.x;
     const size_t np = npix;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        const float4 g = surf[np + i];                                  // normal, signed depth
+        const float4 g = surf[surf_at(np, 1, i)];                                  // normal, signed depth
         float t = fabsf(g.w);
         if (depth) depth[i] = t < 0.f ? 0.f : xdiv(t - fminf(min_d, t), fmaxf(max_d, t) - fminf(min_d, t));
         if (normal_rough) {
-            const float roughness = unpack8(__float_as_uint(surf[8 * np + i].x), 24);
+            const float roughness = unpack8(__float_as_uint(surf[surf_at(np, 8, i)].x), 24);
             normal_rough[i] = make_float4(half_round(g.x), half_round(g.y), half_round(g.z), half_round(roughness));
         }
-        if (albedo) albedo[i] = surf[5 * np + i];
+        if (albedo) albedo[i] = surf[surf_at(np, 5, i)];
     }
 }
 
