@@ -560,17 +560,19 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_temporal(FrameView
         int cx, cy;
         if (!tw.pixel(fv, item, cx, cy)) continue;
         const uint32_t i = (uint32_t)cy * fv.width + (uint32_t)cx;
+        // two memory round trips per pixel instead of four: everything of the CURRENT pixel is requested together with its motion vector
+        // (it does not depend on it), then the previous frame's similarity record and reservoir together. A pixel that turns out flagged or
+        // dissimilar has read a few planes for nothing — rare, and the pass is bound by its round trips at 16 warps per SM.
         const float2 mvec = fv.motion[i];
+        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
+        Reservoir prev, cur; reservoir_load(fv.res_cur, np, i, cur);
         const int mx = (int)roundf((float)W * mvec.x), my = (int)roundf((float)fv.full_height * mvec.y);
         const int ty = cy + my, tx = cx + mx; uint32_t ti = i;
         if (ty >= 0 && ty < H && tx >= 0 && tx < W) ti = (uint32_t)ty * fv.width + (uint32_t)tx;
         const SurfGeom gp = surface_geom(fv.surf_prev, np, ti);
-        if (gp.flagged) continue;
-        const SurfGeom gc = surface_geom(fv.surf_cur, np, i);
-        if (gc.flagged) continue;
-        if (!similar(gp.t, gc.t, gp.normal, gc.normal)) continue;
-        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
-        Reservoir prev, cur; reservoir_load(fv.res_prev, np, ti, prev); reservoir_load(fv.res_cur, np, i, cur);
+        reservoir_load(fv.res_prev, np, ti, prev);
+        if (gp.flagged || sc.flags) continue;                   // plane 1's sign bit == (flags != 0), lb_device.cuh
+        if (!similar(gp.t, sc.t, gp.normal, sc.normal)) continue;
         if (prev.weight > 0.f) {
             const float3 c = prev.s.contribution * (prev.weight / shaded);
             float4 o = fv.channels[i]; o.x += c.x; o.y += c.y; o.z += c.z; fv.channels[i] = o;
@@ -600,10 +602,10 @@ template <class GeomAt>
 LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const GeomAt& geom_at, uint32_t nb[kSpatialSamples]) {
     const int W = (int)fv.width, H = (int)fv.height;
     const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
-    const SurfGeom gc = surf_geom_unpack(geom_at(x, y, i));
-    if (gc.flagged) return -1;
+    // the pixel's own record and all five neighbour probes are requested together, before any is tested: one memory round trip (a pixel
+    // without a surface has probed for nothing — rare)
+    const float4 own = geom_at(x, y, i);
     uint32_t s = wang_hash(seed + i + fv.pix0);
-    // all five neighbour probes are issued before any is tested (5 independent 16-byte reads in flight)
     uint32_t ni[kSpatialSamples]; float4 ng[kSpatialSamples]; bool inside[kSpatialSamples];
 #pragma unroll
     for (uint32_t k = 0; k < kSpatialSamples; ++k) {
@@ -611,8 +613,10 @@ LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const G
         const int nx = (int)roundf((rand_f(s) * 2.f - 1.f) * (float)kSpatialRadius) + x;
         inside[k] = !(nx < 0 || nx >= W || ny < 0 || ny >= H);
         ni[k] = inside[k] ? (uint32_t)ny * fv.width + (uint32_t)nx : i;
-        ng[k] = inside[k] ? geom_at(nx, ny, ni[k]) : geom_at(x, y, i);
+        ng[k] = geom_at(inside[k] ? nx : x, inside[k] ? ny : y, ni[k]);
     }
+    const SurfGeom gc = surf_geom_unpack(own);
+    if (gc.flagged) return -1;
     int count = 0;
 #pragma unroll
     for (uint32_t k = 0; k < kSpatialSamples; ++k) {
@@ -756,9 +760,9 @@ __global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_combine(FrameView 
     const uint32_t stride = gridDim.x * blockDim.x;
     const size_t np = fv.npix;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < fv.npix; i += stride) {
-        if (surface_flags(fv.surf_cur, np, i)) continue;
-        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);
+        Surface sc; surface_load_shading(fv.surf_cur, np, i, sc);      // one round trip: the flags arrive with the rest
         Reservoir a, b; reservoir_load(fv.res_cur, np, i, a); reservoir_load(nbuf, np, i, b);
+        if (sc.flags) continue;
         reservoir_store(fv.res_cur, np, i, combine_pair(a, b, sc, wang_hash(cseed + i + fv.pix0)));
     }
 }
