@@ -91,7 +91,7 @@ struct Renderer {
     // ---- per-resolution buffers
     DevBuf<float4> d_rays[2][3], d_shadow[3], d_surf[2], d_res[4], d_channels, d_combined, d_accum, d_vol_hits, d_vol_shadow[3];
     DevBuf<uint4> d_hits, d_primary_hits; DevBuf<float2> d_motion; DevBuf<uchar4> d_ldr;
-    DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats; DevBuf<uint2> d_bags, d_ris_order;
+    DevBuf<uint32_t> d_counters; DevBuf<unsigned long long> d_stats, d_spatial_nb; DevBuf<uint2> d_bags, d_ris_order;
     // direction-binned queue of the ReSTIR visibility rays (lb_restir.cu k_vis_bin), LB_VIS_SORT=1. Off by default: measured on C2 the binned
     // trace is 5.5 % faster (1.586 -> 1.499 ms for both passes) but the binning pre-pass costs 0.230 ms (profiles/r02_a_ab.md)
     // TMA descriptors of surface plane 1 (normal + signed depth) of both surface buffers: the spatial-reuse pass stages a 92 x 76 box of it per
@@ -210,7 +210,7 @@ struct Renderer {
 
     void resize() {
         const size_t n = npix();
-        d_ris_order.reserve((n + 255) / 256 + 128);
+        d_ris_order.reserve((n + 255) / 256 + 128); d_spatial_nb.reserve(n);
         if (vis_sort) for (auto& p : d_vis_rays) p.reserve(n);          // + per-bag {start, count} and work tickets (lb_restir.cu k_ris_order)
         for (auto& q : d_rays) for (auto& p : q) p.reserve(n);
         for (auto& p : d_shadow) p.reserve(n);
@@ -485,7 +485,7 @@ struct Renderer {
             RestirArgs ra{seed0, (int)st.restir_temporal, (int)st.restir_spatial};
             static const int ris_simple = []() { const char* e = getenv("LB_RIS_SIMPLE"); return (!e || atoi(e) != 0) ? 1 : 0; }();
             ra.ris_simple = ris_simple; ra.unbiased = st.restir_unbiased ? 1 : 0;
-            RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr, have_tmap ? &tmap_geom[surf_cur] : nullptr};
+            RestirBuffers rb{d_bags.p, d_ris_order.p, vis_sort ? d_vis_rays[0].p : nullptr, vis_sort ? d_vis_rays[1].p : nullptr, have_tmap ? &tmap_geom[surf_cur] : nullptr, d_spatial_nb.p};
             LaunchCfg cr = c;
             if (on_side) {
                 need_side_stream();

@@ -88,7 +88,7 @@ void launch_debug_hits(const LaunchCfg&, const uint4* hits, uint32_t n, void* hi
 
 // ---- ReSTIR (lb_restir.cu)
 struct RestirBuffers { uint2* bags = nullptr; uint2* ris_order = nullptr; float4* vis_ray_o = nullptr; float4* vis_ray_d = nullptr;
-                       const void* tmap_geom = nullptr; };      // CUtensorMap of the current frame's surface plane 1 (k_spatial_tma), nullptr = gather from global memory      // vis_ray_*: binned visibility-ray queue (o.xyz, tmax | d.xyz, pixel), nullptr = trace straight from the reservoirs      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
+                       const void* tmap_geom = nullptr; unsigned long long* spatial_nb = nullptr; };      // spatial_nb: per pixel, the accepted neighbours of the first spatial pass (the second pass draws the same ones)      // CUtensorMap of the current frame's surface plane 1 (k_spatial_tma), nullptr = gather from global memory      // vis_ray_*: binned visibility-ray queue (o.xyz, tmax | d.xyz, pixel), nullptr = trace straight from the reservoirs      // kNumBags*kLightsPerBag entries {light index, pdf bits}; ceil(npix/256) {pixel group, bag} sorted by bag
 void launch_restir(const LaunchCfg&, const FrameView&, const SceneView&, const BvhView&, const RestirBuffers&, const RestirArgs&, uint32_t& ticket);
 
 // ---- scene preparation (lb_scene.cu)

@@ -598,8 +598,10 @@ LB_D ResProbe res_probe(const float4* __restrict__ planes, size_t n, uint32_t i)
 // (k_spatial_tma).
 // The two halves of a pixel: the probes (which of the five drawn neighbours are similar) and the merge of their reservoirs.
 // spatial_probe returns the number of accepted neighbours in nb[] (pixel indices), or -1 for a pixel without a surface (nothing to do).
+// `code` (optional) receives the accepted neighbours as offsets: bits 0-2 the count (7: the pixel has no surface), then 12 bits per neighbour
+// in acceptance order, (dx + 32) | (dy + 32) << 6 with |dx|, |dy| <= 30 — see spatial_unpack.
 template <class GeomAt>
-LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const GeomAt& geom_at, uint32_t nb[kSpatialSamples]) {
+LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const GeomAt& geom_at, uint32_t nb[kSpatialSamples], unsigned long long* code = nullptr) {
     const int W = (int)fv.width, H = (int)fv.height;
     const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
     // the pixel's own record and all five neighbour probes are requested together, before any is tested: one memory round trip (a pixel
@@ -616,12 +618,31 @@ LB_D int spatial_probe(const FrameView& fv, uint32_t seed, int x, int y, const G
         ng[k] = geom_at(inside[k] ? nx : x, inside[k] ? ny : y, ni[k]);
     }
     const SurfGeom gc = surf_geom_unpack(own);
-    if (gc.flagged) return -1;
-    int count = 0;
+    if (gc.flagged) { if (code) *code = 7ull; return -1; }
+    int count = 0; unsigned long long packed = 0ull;
 #pragma unroll
     for (uint32_t k = 0; k < kSpatialSamples; ++k) {
         const SurfGeom gn = surf_geom_unpack(ng[k]);
-        if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) nb[count++] = ni[k];
+        if (inside[k] && !gn.flagged && similar(gn.t, gc.t, gn.normal, gc.normal)) {
+            if (code) {
+                const int ny = (int)(ni[k] / fv.width), nx = (int)(ni[k] - (uint32_t)ny * fv.width);
+                packed |= (unsigned long long)((uint32_t)(nx - x + 32) | ((uint32_t)(ny - y + 32) << 6)) << (3 + 12 * count);
+            }
+            nb[count++] = ni[k];
+        }
+    }
+    if (code) *code = packed | (unsigned long long)count;
+    return count;
+}
+// the accepted neighbours of a pixel from the list its first spatial pass left: both passes run with the same seed (ReSTIR.cpp draws it once
+// for the loop), so they draw the same five neighbours and accept the same ones — similarity is a function of the surfaces alone
+LB_D int spatial_unpack(const FrameView& fv, unsigned long long code, int x, int y, uint32_t nb[kSpatialSamples]) {
+    const int count = (int)(code & 7ull);
+    if (count == 7) return -1;
+#pragma unroll
+    for (int k = 0; k < (int)kSpatialSamples; ++k) {
+        const uint32_t f = (uint32_t)(code >> (3 + 12 * k)) & 0xFFFu;
+        nb[k] = (uint32_t)(y + (int)(f >> 6) - 32) * fv.width + (uint32_t)(x + (int)(f & 63u) - 32);
     }
     return count;
 }
@@ -679,15 +700,21 @@ LB_D void spatial_pixel(const FrameView& fv, const float4* __restrict__ in, floa
     if (count >= 0) spatial_merge<UNBIASED>(fv, in, out, seed, (uint32_t)y * fv.width + (uint32_t)x, count, nb);
 }
 
-template <bool UNBIASED>
-__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed) {
+// PASS 0: probe, leave the accepted neighbours in nb_list, merge. PASS 1 (the second iteration): no probes — the list of pass 0, merge.
+template <bool UNBIASED, int PASS>
+__global__ void __launch_bounds__(kBlock, LB_GATHER_BLOCKS) k_spatial(FrameView fv, uint32_t* ticket, const float4* __restrict__ in, float4* __restrict__ out, uint32_t seed,
+                                                                      unsigned long long* __restrict__ nb_list) {
     const TileWalk tw(fv);
     const float4* __restrict__ geom = fv.surf_cur + 1;                // plane 1 (normal, signed depth): the second half of pair 0
     auto geom_at = [geom](int, int, uint32_t index) { return geom[2u * (size_t)index]; };
     for (uint32_t item = tw.next(ticket); item < tw.nitems; item = tw.next(ticket)) {
         int x, y;
         if (!tw.pixel(fv, item, x, y)) continue;
-        spatial_pixel<UNBIASED>(fv, in, out, seed, x, y, geom_at);
+        const uint32_t i = (uint32_t)y * fv.width + (uint32_t)x;
+        uint32_t nb[kSpatialSamples]; int count;
+        if (PASS == 0) { unsigned long long code; count = spatial_probe(fv, seed, x, y, geom_at, nb, &code); nb_list[i] = code; }
+        else count = spatial_unpack(fv, nb_list[i], x, y, nb);
+        if (count >= 0) spatial_merge<UNBIASED>(fv, in, out, seed, i, count, nb);
     }
 }
 
@@ -813,11 +840,15 @@ void launch_restir(const LaunchCfg& cfg, const FrameView& fv, const SceneView& s
         seed = wang_hash(seed);
         const float4* from = fv.res_cur; float4* to = fv.res_tmp_a;
         for (uint32_t it = 0; it < kSpatialIterations; ++it) {
-            if (a.unbiased) k_spatial<true><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            if (a.unbiased) {
+                if (it == 0) k_spatial<true, 0><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed, rb.spatial_nb);
+                else k_spatial<true, 1><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed, rb.spatial_nb);
+            }
             else if (rb.tmap_geom) {
                 LB_CUDA(cudaFuncSetAttribute(k_spatial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kSpTileBytes)));
                 k_spatial_tma<<<cfg.sms, kSpBlock, 2 * kSpTileBytes, st>>>(fv, *static_cast<const CUtensorMap*>(rb.tmap_geom), &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
-            } else k_spatial<false><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed);
+            } else if (it == 0) k_spatial<false, 0><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed, rb.spatial_nb);
+            else k_spatial<false, 1><<<cfg.sms * LB_GATHER_BLOCKS, kBlock, 0, st>>>(fv, &fv.counters[CNT_TICKET0 + ticket++], from, to, seed, rb.spatial_nb);
             LB_LAUNCH_CHECK();
             if (it == 0) { from = fv.res_tmp_a; to = fv.res_tmp_b; } else { const float4* t = from; from = to; to = const_cast<float4*>(t); }
         }
