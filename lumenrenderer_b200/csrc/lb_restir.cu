@@ -349,7 +349,14 @@ __global__ void __launch_bounds__(kRisBlock, 1) k_ris(FrameView fv, SceneView sc
                 if (i != kNone) {
                     const Float8 s01 = ld2(fv.surf_cur + surf_pair(np, 0, i));      // position | flags, normal | depth
                     if (__float_as_uint(s01.a.w)) { reservoir_store(fv.res_cur, np, i, reservoir_zero()); i = kNone; }
-                    else { ppos = f3(s01.a); pnormal = f3(s01.b); }
+                    else {
+                        ppos = f3(s01.a); pnormal = f3(s01.b);
+                        // the rest of the pixel's shading record is wanted in phase B, by whichever lane the sort gives the pixel to: ask L2 for
+                        // it now (coalesced, no registers) — k_shade wrote it a millisecond ago and 500 MB of other planes have passed through L2 since
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(fv.surf_cur + surf_pair(np, 1, i)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(fv.surf_cur + surf_pair(np, 2, i)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(fv.surf_cur + surf_pair(np, 3, i)));
+                    }
                 }
                 uint32_t mask = 0u;
                 if (i != kNone) {
