@@ -133,9 +133,11 @@ __global__ void __launch_bounds__(kBlock) k_fill_bags(SceneView sc, uint2* __res
 //    evaluation, which the warp executes max-over-lanes(survivors) times instead of 32. Phase A leaves the xorshift state in
 //    front of every candidate in shared memory, so every random number is the one the sequential loop of the reference
 //    would have drawn.
-//  * All 256 pixels of a block share one light bag (canonical choice of hazard 1: bag = WangHash(seed + pixel / 256)). The block takes
-//    256-pixel groups from a device ticket and first stages the group's bag — 1000 entries, each the full light record + its bag
-//    pdf, 72 KB — in shared memory. A candidate fetch is then 4-5 shared-memory reads instead of a dependent chain of random
+//  * Between the phases the pixels are regrouped by survivor count, so that the 32 lanes of a warp run (nearly) the same number of rounds
+//    (see k_ris below).
+//  * All 256 pixels of a group share one light bag (canonical choice of hazard 1: bag = WangHash(seed + pixel / 256)). The groups are
+//    counting-sorted by bag (k_ris_order); a block stages ONE bag — 1000 entries, each the full light record + its bag pdf, 88 KB — in
+//    shared memory and works through that bag's groups. A candidate fetch is then 4-5 shared-memory reads instead of a dependent chain of random
 //    global gathers (bag entry -> 64-byte light record): ncu showed the first version bound by the L1 data pipe
 //    (l1tex__data_pipe_lsu_wavefronts 77 % of peak, ~8.5 wavefronts per request, profiles/r01_m_frame.md), not by instruction issue.
 struct BagSmem {
