@@ -237,13 +237,19 @@ LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisSlots], 
     atomicAdd(&g_ris_stats[0], (unsigned long long)__popc(mask));
     { uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)__popc(mask)); if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[1], (unsigned long long)mx); }
 #endif
+    // The reservoir's Update replaces the whole 14-float sample when a candidate is accepted; here the loop only remembers WHICH candidate was
+    // accepted last (+ the two things the evaluation produced: its pdf and contribution) and the sample's geometry is drawn again, once, after
+    // the loop, from the candidate's saved xorshift state — the same numbers, 9 selects per round and 9 live registers less.
+    int ksel = -1; float sel_pdf = 0.f; float3 sel_contribution = f3(0.f);
     while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
         const bool active = mask != 0u;
+        uint32_t kcur = 0u;
         BagCandidate c; ResampleGeom g; bool have_g = false;
         c.ls.radiance = f3(0.f); c.ls.normal = f3(0.f); c.ls.position = f3(0.f); c.ls.contribution = f3(0.f); c.ls.area = 0.f; c.ls.pdf = 0.f; c.bag_pdf = 1.f;
         g.dir = f3(0.f); g.solid = 0.f; g.cos_in = 0.f;
         if (active) {
             const uint32_t k = (uint32_t)__ffs(mask) - 1u; mask &= mask - 1u;
+            kcur = k;
             sb = s_state[k][slot];
             draw_candidate_geom(bag, sb, c);
             have_g = resample_geom(c.ls.position, c.ls.normal, c.ls.area, px.pos, px.normal, g);
@@ -255,8 +261,18 @@ LB_D void ris_phase_b(const BagSmem& bag, const uint32_t (*s_state)[kRisSlots], 
         if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_ris_stats[4], 1ull);
 #endif
         if (have_g) resample_shade<MODE>(ctx, g, c.ls);
-        if (active) reservoir_update(fresh, c.ls, (have_g ? c.ls.pdf : 0.f) / c.bag_pdf, sb);
+        if (active) {                                           // Reservoir::Update (ReSTIRData.h:122-141), the sample kept by index
+            const float w = (have_g ? c.ls.pdf : 0.f) / c.bag_pdf;
+            fresh.weight_sum += w; ++fresh.count;
+            uint32_t su = sb;                                   // seed by value (hazard 14)
+            if (rand_f(su) <= (w / fresh.weight_sum)) { ksel = (int)kcur; sel_pdf = c.ls.pdf; sel_contribution = c.ls.contribution; }
+        }
         __syncwarp();
+    }
+    if (ksel >= 0) {
+        BagCandidate c; uint32_t ss = s_state[ksel][slot];
+        draw_candidate_geom(bag, ss, c);
+        fresh.s = c.ls; fresh.s.pdf = sel_pdf; fresh.s.contribution = sel_contribution;
     }
 }
 
