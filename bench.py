@@ -476,6 +476,28 @@ def run_extras(args, lr, torch, dist, rank, world, local, scene, stream, join_co
     if world > 1:
         r5.synchronize(); r5.comm_destroy()
     r5.close()
+    # ---- the reference's own Sponza asset, when it is on this box (it is not part of the repository: LB_SPONZA_GLTF or tmp_assets/)
+    if world == 1:
+        path = os.environ.get("LB_SPONZA_GLTF") or os.path.join(ROOT, "tmp_assets", "Sponza", "Sponza.gltf")
+        if os.path.exists(path):
+            from lumenrenderer_b200 import scenes
+            sp_scene, cam_pos, cam_rot, info, t_load = scenes.real_sponza(path)
+            rs = lr.Renderer(settings(args, W, H)); rs.load_scene(sp_scene); rs.set_stream(stream.cuda_stream); rs.set_camera(cam_pos, cam_rot)
+            rs.render_frames(HISTORY_FRAMES + 3)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = max(3, min(args.steps, 10))
+            a.record(stream); rs.render_frames(n); b.record(stream); torch.cuda.synchronize()
+            fc = rs.frame_counters()
+            rs.set_overlap(0); rs.render_frames(2); rs.synchronize()
+            rays = fc["extend_rays"] + fc["shadow_rays"] + fc["visibility_rays"]
+            ms = a.elapsed_time(b) / n
+            out["sponza_real"] = {"asset": os.path.basename(path), "triangles": info.get("triangles"), "images": info.get("images"), "undecoded_images": info.get("undecoded_images"),
+                                  "load_and_decode_s": t_load, "ms_per_frame": ms, "mrays_per_s": rays / ms / 1e3, "rays_per_frame": rays,
+                                  "bvh_build_ms": fc["bvh_build_us"] / 1e3, "stage_ms": {k: v / 1e3 for k, v in rs.frame_stats().items()},
+                                  "parity": "profiles/sponza_real.py compares this scene with the oracle at 480x270 (profiles/r02_sponza_real.json)"}
+            rs.close()
+        else:
+            out["sponza_real"] = {"skipped": "Sponza.gltf is not on this box (set LB_SPONZA_GLTF); the run with the asset is recorded in profiles/r02_sponza_real.json"}
     return out
 
 

@@ -385,3 +385,25 @@ def material_gallery() -> SceneDescription:
 
 
 SCENES = {"cornell": cornell_box, "atrium": atrium, "instanced_field": instanced_field, "fog_room": fog_room, "gallery": material_gallery}
+
+
+def real_sponza(path):
+    """The reference's own Sponza asset (Sandbox/assets/models/Sponza/Sponza.gltf — not part of this repository) through the native ingest,
+    with the lamps and the camera of profiles/sponza_real.py: Sponza has no emissive material, so — as SURVEY 8d C2 prescribes — eight
+    override-emissive spheres light it; the reference renders the asset unscaled (~3 700 units long), lamps and camera are placed in those
+    units. Returns (scene, camera position, camera rotation, glTF info, seconds spent loading and decoding)."""
+    import time
+    from . import api
+    from .gltf import GltfDocument
+    t0 = time.time()
+    with GltfDocument(path) as doc:
+        info = dict(doc.info); scene = doc.to_scene_description()
+    t_load = time.time() - t0
+    lamp_mat = len(scene.materials)
+    scene.materials.append(dict(diffuse_color=(0.9, 0.9, 0.9, 1.0), metallic_factor=0.0, roughness_factor=1.0, luminance=1.0, index_of_refraction=1.0))
+    scene.meshes.append([sphere(22.0, 16, 8, lamp_mat)]); lamp_mesh = len(scene.meshes) - 1
+    for k in range(8):
+        x = -1000.0 + 650.0 * (k % 4); y = 350.0 if k < 4 else 800.0; z = 120.0 if k % 2 else -120.0
+        scene.instances.append({"mesh": lamp_mesh, "transform": translate(x, y, z), "emission_mode": api.EMISSION_OVERRIDE,
+                                "override_radiance": (4000.0, 3700.0, 3200.0), "emission_scale": 1.0})
+    return scene, (-1150.0, 250.0, 20.0), _quat_y(90.0), info, t_load           # in the nave, looking along +x

@@ -17,17 +17,7 @@ from lumenrenderer_b200.gltf import GltfDocument
 
 path = sys.argv[1] if len(sys.argv) > 1 else "tmp_assets/Sponza/Sponza.gltf"
 out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/r02_sponza_real.json"
-t0 = time.time()
-with GltfDocument(path) as doc:
-    info = dict(doc.info); scene = doc.to_scene_description()
-t_load = time.time() - t0
-lamp_mat = len(scene.materials); scene.materials.append(dict(diffuse_color=(0.9, 0.9, 0.9, 1.0), metallic_factor=0.0, roughness_factor=1.0, luminance=1.0, index_of_refraction=1.0))
-scene.meshes.append([scenes.sphere(22.0, 16, 8, lamp_mat)]); lamp_mesh = len(scene.meshes) - 1
-for k in range(8):
-    x = -1000.0 + 650.0 * (k % 4); y = 350.0 if k < 4 else 800.0; z = 120.0 if k % 2 else -120.0
-    scene.instances.append({"mesh": lamp_mesh, "transform": scenes.translate(x, y, z), "emission_mode": api.EMISSION_OVERRIDE,
-                            "override_radiance": (4000.0, 3700.0, 3200.0), "emission_scale": 1.0})
-cam_pos, cam_rot = (-1150.0, 250.0, 20.0), scenes._quat_y(90.0)           # in the nave, looking along +x
+scene, cam_pos, cam_rot, info, t_load = scenes.real_sponza(path)
 res = {"asset": os.path.basename(path), "gltf_info": info, "load_and_decode_s": t_load, "triangles": scene.triangle_count()}
 
 # ---- parity against the oracle, 480x270, depth 4, ReSTIR, 2 frames
