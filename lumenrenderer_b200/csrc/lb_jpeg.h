@@ -298,25 +298,29 @@ struct Decoder {
 
     // ---- inverse DCT (LLM, 12-bit constants), 8x8 block of dequantised coefficients -> 8-bit samples
     static int fx(double x) { return (int)(x * 4096 + 0.5); }
-    static uint8_t clamp8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
-    struct Idct1 { int x0, x1, x2, x3, t0, t1, t2, t3; };
-    static Idct1 idct1(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7) {
-        static const int c0541 = fx(0.5411961f), c1847 = fx(-1.847759065f), c0765 = fx(0.765366865f), c1175 = fx(1.175875602f), c0298 = fx(0.298631336f),
+    // 64-bit intermediates: identical to stb's `int` arithmetic for every stream a conforming encoder writes (|coefficient x quantiser| stays
+    // far inside 32 bits), and defined — instead of a signed overflow — for the coefficients a corrupt stream can hold (found by the fuzzer)
+    typedef long long i64;
+    struct Idct1 { i64 x0, x1, x2, x3, t0, t1, t2, t3; };
+    static Idct1 idct1(i64 s0, i64 s1, i64 s2, i64 s3, i64 s4, i64 s5, i64 s6, i64 s7) {
+        static const i64 c0541 = fx(0.5411961f), c1847 = fx(-1.847759065f), c0765 = fx(0.765366865f), c1175 = fx(1.175875602f), c0298 = fx(0.298631336f),
                          c2053 = fx(2.053119869f), c3072 = fx(3.072711026f), c1501 = fx(1.501321110f), c0899 = fx(-0.899976223f), c2562 = fx(-2.562915447f),
                          c1961 = fx(-1.961570560f), c0390 = fx(-0.390180644f);
         Idct1 o;
-        int p1 = (s2 + s6) * c0541;
-        const int e2 = p1 + s6 * c1847, e3 = p1 + s2 * c0765;
-        const int e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
+        i64 p1 = (s2 + s6) * c0541;
+        const i64 e2 = p1 + s6 * c1847, e3 = p1 + s2 * c0765;
+        const i64 e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
         o.x0 = e0 + e3; o.x3 = e0 - e3; o.x1 = e1 + e2; o.x2 = e1 - e2;
-        int t0 = s7, t1 = s5, t2 = s3, t3 = s1;
-        int p3 = t0 + t2, p4 = t1 + t3; p1 = t0 + t3; int p2 = t1 + t2;
-        const int p5 = (p3 + p4) * c1175;
+        i64 t0 = s7, t1 = s5, t2 = s3, t3 = s1;
+        i64 p3 = t0 + t2, p4 = t1 + t3; p1 = t0 + t3; i64 p2 = t1 + t2;
+        const i64 p5 = (p3 + p4) * c1175;
         t0 *= c0298; t1 *= c2053; t2 *= c3072; t3 *= c1501;
         p1 = p5 + p1 * c0899; p2 = p5 + p2 * c2562; p3 *= c1961; p4 *= c0390;
         o.t3 = t3 + p1 + p4; o.t2 = t2 + p2 + p3; o.t1 = t1 + p2 + p4; o.t0 = t0 + p1 + p3;
         return o;
     }
+    static uint8_t clamp8(i64 x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+    static int wrap32(i64 x) { return (int)(uint32_t)(unsigned long long)x; }      // what stb's int would hold (two's complement)
     static void idct(uint8_t* out, int stride, const int16_t* d) {
         int v[64];
         for (int i = 0; i < 8; ++i) {                                             // columns
@@ -328,15 +332,15 @@ struct Decoder {
             }
             Idct1 o = idct1(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
             o.x0 += 512; o.x1 += 512; o.x2 += 512; o.x3 += 512;
-            v[0 * 8 + i] = (o.x0 + o.t3) >> 10; v[7 * 8 + i] = (o.x0 - o.t3) >> 10;
-            v[1 * 8 + i] = (o.x1 + o.t2) >> 10; v[6 * 8 + i] = (o.x1 - o.t2) >> 10;
-            v[2 * 8 + i] = (o.x2 + o.t1) >> 10; v[5 * 8 + i] = (o.x2 - o.t1) >> 10;
-            v[3 * 8 + i] = (o.x3 + o.t0) >> 10; v[4 * 8 + i] = (o.x3 - o.t0) >> 10;
+            v[0 * 8 + i] = wrap32((o.x0 + o.t3) >> 10); v[7 * 8 + i] = wrap32((o.x0 - o.t3) >> 10);
+            v[1 * 8 + i] = wrap32((o.x1 + o.t2) >> 10); v[6 * 8 + i] = wrap32((o.x1 - o.t2) >> 10);
+            v[2 * 8 + i] = wrap32((o.x2 + o.t1) >> 10); v[5 * 8 + i] = wrap32((o.x2 - o.t1) >> 10);
+            v[3 * 8 + i] = wrap32((o.x3 + o.t0) >> 10); v[4 * 8 + i] = wrap32((o.x3 - o.t0) >> 10);
         }
         for (int r = 0; r < 8; ++r, out += stride) {                              // rows
             const int* w = v + r * 8;
             Idct1 o = idct1(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
-            const int bias = 65536 + (128 << 17);
+            const i64 bias = 65536 + (128 << 17);
             o.x0 += bias; o.x1 += bias; o.x2 += bias; o.x3 += bias;
             out[0] = clamp8((o.x0 + o.t3) >> 17); out[7] = clamp8((o.x0 - o.t3) >> 17);
             out[1] = clamp8((o.x1 + o.t2) >> 17); out[6] = clamp8((o.x1 - o.t2) >> 17);

@@ -60,6 +60,20 @@ def test_gltf_loader_survives_mutated_files(tmp_path):
     with GltfDocument(str(tmp_path / "png_cases.glb")) as doc_:
         assert doc_.info["images"] == len(views) and doc_.info["undecoded_images"] == 0
     files.append(str(tmp_path / "png_cases.glb"))
+    # the same for the JPEG decoder (csrc/lb_jpeg.h): baseline / progressive, every sampling ratio, restart intervals, CMYK, 16-bit tables
+    cases = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    blob = b""; views = []
+    for name in sorted({k.split("/")[0] for k in cases.files}):
+        data = cases[name + "/file"].tobytes()
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)}); blob += data + b"\0" * (-len(data) % 4)
+    doc = json.dumps({"asset": {"version": "2.0"}, "buffers": [{"byteLength": len(blob)}], "bufferViews": views,
+                      "images": [{"bufferView": i, "mimeType": "image/jpeg"} for i in range(len(views))]}).encode()
+    doc += b" " * (-len(doc) % 4)
+    with open(tmp_path / "jpeg_cases.glb", "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(doc) + 8 + len(blob)) + struct.pack("<II", len(doc), 0x4E4F534A) + doc + struct.pack("<II", len(blob), 0x004E4942) + blob)
+    with GltfDocument(str(tmp_path / "jpeg_cases.glb")) as doc_:
+        assert doc_.info["images"] == len(views) and doc_.info["undecoded_images"] == 0
+    files.append(str(tmp_path / "jpeg_cases.glb"))
     env = dict(os.environ, FUZZ_TMP=str(tmp_path))
     res = subprocess.run([exe, "700", "4711", *files], capture_output=True, text=True, timeout=600, env=env)
-    assert res.returncode == 0 and "fuzzed 3500 inputs" in res.stdout, (res.stdout[-500:], res.stderr[-3000:])
+    assert res.returncode == 0 and "fuzzed 4200 inputs" in res.stdout, (res.stdout[-500:], res.stderr[-3000:])
