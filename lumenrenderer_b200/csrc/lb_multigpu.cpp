@@ -170,8 +170,10 @@ LB_API int lb_comm_reduce_accum(LbRenderer r, int root, uint32_t total_frames) {
     MG_LB(lb_get_settings(r, &st)); MG_CUDA(cudaSetDevice(st.device));
     MG_LB(lb_reduce_begin(r, &side, &send, &recv, &bytes));
     // the one collective of the path, on the renderer's side stream: the frames that follow overlap it
-    MG_NCCL(nccl().Reduce(send, c.rank == root ? recv : send, bytes / 4, ncclFloat, ncclSum, root, c.comm, (cudaStream_t)side));
-    MG_LB(lb_reduce_end(r, c.rank == root ? 1 : 0, total_frames));
+    const ncclResult_t nr = nccl().Reduce(send, c.rank == root ? recv : send, bytes / 4, ncclFloat, ncclSum, root, c.comm, (cudaStream_t)side);
+    const int er = lb_reduce_end(r, c.rank == root && nr == ncclSuccess ? 1 : 0, total_frames);      // always closes what lb_reduce_begin opened
+    if (nr != ncclSuccess) return mfail(LB_ERR_CUDA, std::string("ncclReduce: ") + nccl().GetErrorString(nr));
+    if (er != LB_OK) return mfail(er, std::string("lb_reduce_end: ") + lb_last_error());
     return LB_OK;
 }
 LB_API int lb_comm_gather_bands(LbRenderer r, int root, void* full_frame_device) {
